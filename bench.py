@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the ARAP hot path on the headline workload (BASELINE.json configs[2]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nu 316] [--precision f64|f32]
+
+A "step" is ONE ARAP iteration (local step + global step, reference inc/deform/arap.h:122-129) on the
+class-I geodesic icosphere nu=316 (V = 998,562; 5 % lowest-z vertices anchored, 1 % highest-z vertices
+dragged by Rz(30 deg) + (0,0,0.3)), PrecisionType double. Prints ONE JSON line (see DESIGN.md "Measurement").
+
+  value     ARAP iterations/s, state resident in HBM, K steps timed with CUDA events on the engine's stream
+  e2e       the same through the public C-ABI call arap_deform(host_mesh, 1): one iteration plus the
+            write-back of p' into a pinned HOST mesh buffer every step (the reference's deform(1), arap.h:101-138)
+  roofline  the dominant kernel of the step (largest share of step time), algorithmic bytes / CUDA-event time
+  cpu_baseline  the oracle (C restatement of arap.h, 1 thread) timed on this box's host cores
+
+N > 1 (torchrun): the batched-independent-deformations sharding -- every rank deforms its own 1M-vertex mesh,
+no data-path collective; value = N x K iterations / max-over-ranks time.
+
+--impl reference: the CPU oracle alone (the reference itself cannot be built here: no Eigen), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "arap_iterations_per_sec_1M_verts"
+UNIT = "iterations/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", p
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def build_workload(nu):
+    from mesh_deform_b200 import meshgen as G
+    P, F = G.icosphere(nu)
+    idx, tgt = G.cap_constraints(P)
+    return P, F, idx, tgt
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(V, nF, nnz, s):
+    """Per-launch algorithmic bytes (SURVEY.md section 8d / BASELINE.md section 3), s = sizeof(scalar)."""
+    d = nnz / V
+    return {
+        "local_step": V * (15 * s + 4 + (4 + s) * d),
+        "rhs_residual": V * (18 * s + 8 + (4 + s) * d),
+        "cg_spmv": nF * ((s + 4) * (d + 1) + 4 + 6 * 8),          # CG vectors are always fp64
+        "cg_update": nF * (6 * 24 + 8),
+        "cg_direction": nF * (3 * 24 + 8),
+        "apply_update": nF * (24 + 2 * 3 * s),
+    }
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    return rank, world, local_rank, dist
+
+
+def barrier_and_sync(dist):
+    import torch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, local_rank, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_cpu_oracle(P, F, idx, tgt, iters, real):
+    """prepare + `iters` iterations of the oracle; returns (seconds per phase dict, mesh, energy, oracle)."""
+    from oracle import oracle as O
+    mesh = P.astype(real)
+    o = O.ArapOracle(mesh, F, real)
+    for i, t in zip(idx, tgt):
+        o.setConstraint(int(i), t)
+    t0 = time.perf_counter()
+    ok = o.deform(0)
+    t_prepare = time.perf_counter() - t0
+    assert ok
+    return o, mesh, t_prepare
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle restatement; the reference itself needs Eigen,
+    which is not in this image) on the same config/metric. Single thread: the reference has no threading."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    real = np.float64 if args.precision == "f64" else np.float32
+    P, F, idx, tgt = build_workload(args.nu)
+    o, mesh, t_prepare = run_cpu_oracle(P, F, idx, tgt, 0, real)
+    for _ in range(args.warmup):
+        o.deform(1)
+    o.reset_timers()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.deform(1)
+    dt = time.perf_counter() - t0
+    tm = o.timers()
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"icosphere nu={args.nu} V={P.shape[0]} 5% anchors + 1% handles (BASELINE.json configs[2])",
+                   "vertices": int(P.shape[0]), "faces": int(F.shape[0]), "n_free": int(o.nFree)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"full workload, {args.steps} ARAP iterations after prepare (prepare {t_prepare:.1f} s incl. "
+                                   f"LDL^T factor, excluded like the GPU arm's prepare); per-iteration seconds: "
+                                   f"local {tm['local'] / args.steps:.3f} rhs {tm['rhs'] / args.steps:.3f} solve {tm['solve'] / args.steps:.3f}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "prepare_s": t_prepare, "factor_nnz": o.factor_nnz(),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nu", type=int, default=316, help="icosphere frequency (316 -> 998,562 vertices)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=2, help="oracle iterations in the cpu_baseline sample")
+    ap.add_argument("--cg-tol", type=float, default=0.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank, world, local_rank, dist = dist_setup(args.gpus)
+    import torch  # plumbing only: device selection, barrier, max-over-ranks
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use gpurun")
+    torch.cuda.set_device(local_rank)
+    from mesh_deform_b200 import capi
+
+    real = np.float64 if args.precision == "f64" else np.float32
+    s = np.dtype(real).itemsize
+    P, F, idx, tgt = build_workload(args.nu)
+    V = P.shape[0]
+    peak_gbs, peak_src, peaks = load_peaks()
+
+    opts = {"device": local_rank}
+    if args.cg_tol > 0:
+        opts["cg_tolerance"] = args.cg_tol
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    pinned = capi.PinnedArray((V, 3), real)
+    mesh = pinned.array
+    mesh[...] = P.astype(real)
+    arap = capi.AsRigidAsPossibleDeformation(mesh, F, real, **opts)
+    arap.setConstraints(idx, tgt)
+    t0 = time.perf_counter()
+    rc = arap.prepare()
+    arap.synchronize()
+    prepare_ms = 1e3 * (time.perf_counter() - t0)
+    assert rc == capi.ARAP_OK
+    rp, ci, _ = arap.cotanWeights()
+    nnz = int(ci.size)
+    _, n_free = arap.freeIdxMap()
+
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # parity at full size on the first iterations: same inputs, same iteration count as the oracle sample
+        arap.iterate(args.cpu_iters)
+        gpu_pos = arap.positions(np.float64)
+        gpu_e = arap.energy()
+        parity = {"iterations": args.cpu_iters, "gpu_positions": gpu_pos, "gpu_energy": gpu_e}
+        extra_warm = max(0, args.warmup - args.cpu_iters)
+    else:
+        extra_warm = args.warmup
+    arap.iterate(extra_warm)
+    arap.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    arap.profile_reset()
+    barrier_and_sync(dist)
+    arap.timer_start()
+    arap.iterate(args.steps)
+    ms = arap.timer_stop()
+    barrier_and_sync(dist)
+    ms = max_over_ranks(dist, local_rank, ms)
+    prof_plain = arap.profile()
+    stats = arap.solver_stats()
+    launches = sum(v["launches"] for v in prof_plain.values())
+
+    # ---- per-kernel pass: the same K steps with every launch bracketed by CUDA events -----------
+    arap.profile_enable(True)
+    arap.profile_reset()
+    arap.timer_start()
+    arap.iterate(args.steps)
+    ms_profiled = arap.timer_stop()
+    prof = arap.profile()
+    arap.profile_enable(False)
+    stats2 = arap.solver_stats()
+
+    # ---- end-to-end arm: public call with a HOST mesh, write-back inside the timed region ---------
+    arap.deform(1)
+    barrier_and_sync(dist)
+    t0 = time.perf_counter()
+    arap.timer_start()
+    for _ in range(args.steps):
+        assert arap.deform(1)                      # arap_deform(h, host_mesh, 1): iterate + D2H write-back
+    e2e_ms_dev = arap.timer_stop()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    barrier_and_sync(dist)
+    e2e_ms = max_over_ranks(dist, local_rank, max(e2e_ms, e2e_ms_dev))
+    clocks = sampler.stop()
+
+    # ---- frame protocol of the reference demos (informational): setConstraint + deform(5), dirty every frame
+    t0 = time.perf_counter()
+    arap.setConstraints(idx, tgt)
+    assert arap.deform(5)
+    frame_ms = 1e3 * (time.perf_counter() - t0)
+
+    if rank != 0:
+        return 0
+
+    value = world * args.steps / (ms * 1e-3)
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    ab = algorithmic_bytes(V, n_free, nnz, s)
+    total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        avg_ms = v["ms"] / v["launches"]
+        entry = {"launches_per_step": v["launches"] / args.steps, "avg_us": 1e3 * avg_ms, "share": v["ms"] / total_kernel_ms}
+        if name in ab and avg_ms > 0:
+            entry["algorithmic_bytes"] = ab[name]
+            entry["achieved_gbs"] = ab[name] / (avg_ms * 1e-3) / 1e9
+            entry["frac_of_peak"] = entry["achieved_gbs"] / peak_gbs
+        kernels[name] = entry
+    dominant = max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["share"])
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak_gbs,
+                "unit": "GB/s", "frac": kernels[dominant]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                "share_of_step": kernels[dominant]["share"], "avg_launch_us": kernels[dominant]["avg_us"]}
+    local = kernels.get("local_step", {})
+
+    cpu_baseline = None
+    parity_out = None
+    if parity is not None:
+        o, omesh, t_prep = run_cpu_oracle(P, F, idx, tgt, 0, real)
+        o.reset_timers()
+        t0 = time.perf_counter()
+        o.deform(args.cpu_iters)
+        dt = time.perf_counter() - t0
+        tm = o.timers()
+        diag = float(np.linalg.norm(P.max(0) - P.min(0)))
+        cpu_e = o.energy()
+        parity_out = {"iterations": args.cpu_iters,
+                      "max_dp_over_bbox_diag": float(np.abs(parity["gpu_positions"] - omesh.astype(np.float64)).max() / diag),
+                      "rel_energy_diff": abs(parity["gpu_energy"] - cpu_e) / cpu_e, "tolerance": {"dp": 1e-5, "dE": 1e-6}}
+        cpu_baseline = {"value": args.cpu_iters / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"full workload (V={V}), {args.cpu_iters} ARAP iterations after prepare; prepare {t_prep:.1f} s "
+                                  f"(LDL^T factor, {o.factor_nnz()} nnz) excluded; per-iteration s: local {tm['local'] / args.cpu_iters:.3f} "
+                                  f"rhs {tm['rhs'] / args.cpu_iters:.3f} solve {tm['solve'] / args.cpu_iters:.3f}; host cores available: {os.cpu_count()}"}
+
+    working_set_mb = (V * (3 * 4 * s + 8) + nnz * (4 + s) + V * 4 + V * 4 * 24) / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"icosphere nu={args.nu} V={V} 5% anchors + 1% handles (BASELINE.json configs[2])",
+                   "vertices": int(V), "faces": int(F.shape[0]), "nnz": nnz, "n_free": int(n_free),
+                   "sharding": "one independent deformation per GPU, no collective" if world > 1 else "single GPU",
+                   "solver": "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "cg_tolerance": float(arap_tolerance(args)),
+                   "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
+                "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "local_step": {"achieved_gbs": local.get("achieved_gbs"), "frac_of_measured_peak": local.get("frac_of_peak"),
+                       "frac_of_nominal_8TBs": (local.get("achieved_gbs") or 0) / 8000.0, "avg_us": local.get("avg_us")},
+        "kernels": kernels,
+        "cg": {"iterations_per_arap_iteration": stats["cg_iterations_total"] / max(1, stats["global_steps"]),
+               "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
+        "prepare_ms": prepare_ms,
+        "frame": {"protocol": "setConstraints(all) + deform(5) with the dirty rebuild (reference demo loop)", "ms": frame_ms},
+        "profiled_pass_ms_per_step": ms_profiled / args.steps,
+        "cpu_baseline": cpu_baseline,
+        "parity": parity_out,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def arap_tolerance(args):
+    return args.cg_tol if args.cg_tol > 0 else 1e-10
+
+
+if __name__ == "__main__":
+    sys.exit(main())

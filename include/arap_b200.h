@@ -1,0 +1,157 @@
+/*
+ * arap_b200.h -- C ABI of libarap_b200.so, the B200 (sm_100a) engine behind the header-only C++
+ * API of cheind/mesh-deform (reference inc/deform/arap.h).
+ *
+ * The reference has no FFI/plugin layer: its boundary is the C++ template class
+ * deform::AsRigidAsPossibleDeformation<MeshType, PrecisionType> (reference inc/deform/arap.h:49-466),
+ * instantiated in the caller's translation unit. This C ABI is what that class's three public
+ * members now bind to (see inc/deform/arap.h in this repo and INTEGRATION.md):
+ *
+ *   reference member (file:line)                         C-ABI entry point(s)
+ *   ---------------------------------------------------  -------------------------------------------
+ *   ctor + initializeMeshTopology   arap.h:66-70,149-155  arap_create
+ *   (implicit destructor)                                 arap_destroy
+ *   setConstraint                   arap.h:81-85          arap_set_constraints
+ *   deform: the `_dirty` block      arap.h:102-120        arap_prepare   (geometry, cotan weights + CSR,
+ *                                                          rotations, free map, constraints, system setup)
+ *   deform: the iteration loop      arap.h:122-129        arap_iterate   (estimateRotations + estimatePositions)
+ *   deform: write-back              arap.h:133-135        arap_get_positions
+ *   deform, whole                   arap.h:101-138        arap_deform    (prepare-if-dirty + iterate + write-back)
+ *   PrivateAccessor::cotanWeights   tests/accessor.h:16-22 arap_get_csr_nnz / arap_get_csr
+ *
+ * Conventions: plain pointers and sizes only; all pointers are HOST pointers owned by the caller
+ * and are copied during the call; xyz arrays are V x 3 (x,y,z per vertex) in the handle's
+ * precision unless a scalar-size argument says otherwise; indices are int32. Every function
+ * returns an int status (ARAP_OK == 0; > 0 informational; < 0 error) and never throws.
+ * A handle is not re-entrant; distinct handles may be used from distinct threads.
+ * There is no CPU fallback: without a CUDA device every call fails with ARAP_ERR_CUDA.
+ */
+#ifndef ARAP_B200_H
+#define ARAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARAP_B200_ABI_VERSION 1
+
+enum {
+    ARAP_OK = 0,
+    ARAP_UNCONSTRAINED = 1,   /* prepare(): no vertex is constrained -> nothing to solve (arap.h:113-114) */
+    ARAP_ERR_INVALID = -1,    /* bad argument / call order */
+    ARAP_ERR_CUDA = -2,       /* CUDA runtime failure (message in arap_last_error) */
+    ARAP_ERR_SOLVER = -3,     /* linear system unusable: the reference's `return false` (arap.h:116-117) */
+    ARAP_ERR_ALLOC = -4
+};
+
+enum {
+    ARAP_SOLVER_AUTO = 0,
+    ARAP_SOLVER_PCG_JACOBI = 1,   /* warm-started Jacobi-preconditioned CG, matrix-free on the one-ring CSR */
+    ARAP_SOLVER_PCG_MG = 2        /* CG preconditioned by an aggregation multigrid V-cycle */
+};
+
+typedef struct arap_handle arap_handle;
+
+typedef struct arap_options {
+    int32_t struct_size;        /* = sizeof(arap_options); lets the struct grow compatibly */
+    int32_t device;             /* CUDA device ordinal, -1 = current device */
+    int32_t solver;             /* ARAP_SOLVER_* */
+    int32_t max_cg_iterations;  /* per global step; <= 0 -> default */
+    double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> default */
+    int32_t cg_check_interval;  /* CG iterations between convergence polls; <= 0 -> default */
+    int32_t profile;            /* != 0: time every kernel launch with CUDA events (see arap_profile_*) */
+} arap_options;
+
+/* Fill `opt` with the defaults (and struct_size). */
+void arap_default_options(arap_options *opt);
+
+/* ctor: copies the F x 3 face array to the device. precision_bytes: 4 (float) or 8 (double) = PrecisionType. */
+int arap_create(const int32_t *faces, int32_t n_faces, int32_t n_vertices, int32_t precision_bytes,
+                const arap_options *opt, arap_handle **out);
+void arap_destroy(arap_handle *h);
+
+/* setConstraint for n vertices at once: overwrite-or-insert, constraints accumulate, marks the handle dirty.
+ * xyz: n x 3 in scalars of xyz_scalar_bytes (4|8), cast to the handle precision like arap.h:83. */
+int arap_set_constraints(arap_handle *h, int32_t n, const int32_t *vertex_idx, const void *xyz, int32_t xyz_scalar_bytes);
+
+/* 1 if the next arap_deform would run the dirty block (arap.h:102). */
+int arap_is_dirty(const arap_handle *h);
+
+/* The dirty block (arap.h:107-119) from the rest pose `rest_xyz` (V x 3, scalars of rest_scalar_bytes).
+ * Returns ARAP_OK, ARAP_UNCONSTRAINED (weights/CSR are still built; handle stays dirty) or an error. */
+int arap_prepare(arap_handle *h, const void *rest_xyz, int32_t rest_scalar_bytes);
+
+/* n x (local step, global step) on the device (arap.h:122-129). Requires a successful arap_prepare. */
+int arap_iterate(arap_handle *h, int32_t n_iterations);
+
+/* Current p' (V x 3) cast to scalars of out_scalar_bytes (arap.h:133-135). */
+int arap_get_positions(arap_handle *h, void *out_xyz, int32_t out_scalar_bytes);
+
+/* Whole deform() with `mesh_xyz` playing the role of the reference's Mesh& (arap.h:101-138):
+ * if dirty, the rest pose is re-read from mesh_xyz; after the iterations p' is written back into mesh_xyz.
+ * Returns ARAP_OK (true), ARAP_UNCONSTRAINED (true, nothing written) or an error (false). */
+int arap_deform(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32_t n_iterations);
+
+/* _edgeWeights (arap.h:453): CSR V x V, columns ascending, no diagonal, values in handle precision. */
+int arap_get_csr_nnz(arap_handle *h, int32_t *nnz);
+int arap_get_csr(arap_handle *h, int32_t *rowptr /*V+1*/, int32_t *colidx /*nnz*/, void *weights /*nnz*/);
+
+/* _freeIdxMap / _numberOfFreeVariables (arap.h:456-457). Either pointer may be NULL. */
+int arap_get_free_map(arap_handle *h, int32_t *free_idx /*V*/, int32_t *n_free);
+
+/* _rotations (arap.h:454) as V x 9 row-major 3x3 matrices in handle precision. */
+int arap_get_rotations(arap_handle *h, void *rot9);
+
+/* ARAP energy sum_i sum_j w_ij |(p'_i-p'_j) - R_i (p_i-p_j)|^2 (Sorkine & Alexa eq. 3; the reference has none). */
+int arap_energy(arap_handle *h, double *energy);
+
+/* Statistics of the global solves since the last arap_prepare. */
+typedef struct arap_solver_stats {
+    int64_t cg_iterations_total;   /* CG iterations summed over all global steps */
+    int32_t global_steps;
+    int32_t last_cg_iterations;
+    double last_relative_residual; /* |r| / |rhs| at the end of the last global step */
+    int32_t last_converged;
+    int32_t reserved;
+} arap_solver_stats;
+int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
+
+/* Per-kernel profile (filled when options.profile != 0 or after arap_profile_enable(h, 1)). */
+enum {
+    ARAP_K_WEIGHTS_COUNT = 0, ARAP_K_WEIGHTS_FILL, ARAP_K_ROW_SORT_MERGE, ARAP_K_CSR_COMPACT, ARAP_K_SCAN,
+    ARAP_K_INIT_STATE, ARAP_K_DIAGONAL, ARAP_K_LOCAL_STEP, ARAP_K_RHS_RESIDUAL, ARAP_K_CG_SPMV,
+    ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC, ARAP_K_COUNT_MAX = 32
+};
+typedef struct arap_profile {
+    int64_t launches[ARAP_K_COUNT_MAX];
+    double milliseconds[ARAP_K_COUNT_MAX];   /* only when event timing is enabled */
+} arap_profile;
+int arap_profile_enable(arap_handle *h, int32_t enable);
+int arap_profile_reset(arap_handle *h);
+int arap_profile_get(arap_handle *h, arap_profile *out);
+const char *arap_kernel_name(int32_t kernel_id);
+
+/* Device-side timing of a span of calls with CUDA events on the handle's stream. */
+int arap_timer_start(arap_handle *h);
+int arap_timer_stop(arap_handle *h, double *milliseconds);
+int arap_synchronize(arap_handle *h);
+
+/* Page-locked host memory for mesh buffers handed to arap_deform / arap_prepare / arap_get_positions
+ * (optional: pageable memory works too, pinned memory makes the copies run at full PCIe rate). */
+int arap_host_alloc(size_t bytes, void **out);
+int arap_host_free(void *ptr);
+
+/* Message of the last error on this handle ("" if none). Valid until the next call on the handle. */
+const char *arap_last_error(const arap_handle *h);
+/* Message of the last failed arap_create on this thread. */
+const char *arap_create_error(void);
+
+int arap_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARAP_B200_H */

@@ -1,0 +1,275 @@
+"""ctypes binding of the C ABI in include/arap_b200.h (libarap_b200.so).
+
+This is the only way Python reaches the engine: plain pointers and sizes, no torch types. The
+library is loaded from inside the package directory (built in-tree by `__graft_entry__.build()` or
+`make -C mesh_deform_b200/csrc`). There is NO fallback: if the shared library is missing or cannot
+be loaded the import of the symbols fails loudly, and every entry point fails with ARAP_ERR_CUDA
+when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarap_b200.so")
+
+ARAP_OK = 0
+ARAP_UNCONSTRAINED = 1
+ARAP_ERR_INVALID = -1
+ARAP_ERR_CUDA = -2
+ARAP_ERR_SOLVER = -3
+ARAP_ERR_ALLOC = -4
+
+SOLVER_AUTO, SOLVER_PCG_JACOBI, SOLVER_PCG_MG = 0, 1, 2
+K_COUNT_MAX = 32
+
+# every symbol include/arap_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "arap_default_options", "arap_create", "arap_destroy", "arap_set_constraints", "arap_is_dirty",
+    "arap_prepare", "arap_iterate", "arap_get_positions", "arap_deform", "arap_get_csr_nnz", "arap_get_csr",
+    "arap_get_free_map", "arap_get_rotations", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
+    "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
+    "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
+    "arap_abi_version",
+)
+
+
+class Options(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("solver", C.c_int32),
+                ("max_cg_iterations", C.c_int32), ("cg_tolerance", C.c_double),
+                ("cg_check_interval", C.c_int32), ("profile", C.c_int32)]
+
+
+class SolverStats(C.Structure):
+    _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
+                ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("launches", C.c_int64 * K_COUNT_MAX), ("milliseconds", C.c_double * K_COUNT_MAX)]
+
+
+_lib = None
+
+
+class EngineMissingError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libarap_b200.so (once). Raises EngineMissingError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineMissingError(
+            f"{LIB_PATH} not found: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C mesh_deform_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int32
+    L.arap_default_options.argtypes = [C.POINTER(Options)]
+    L.arap_default_options.restype = None
+    L.arap_create.argtypes = [vp, i32, i32, i32, C.POINTER(Options), C.POINTER(vp)]
+    L.arap_destroy.argtypes = [vp]
+    L.arap_destroy.restype = None
+    L.arap_set_constraints.argtypes = [vp, i32, vp, vp, i32]
+    L.arap_is_dirty.argtypes = [vp]
+    L.arap_prepare.argtypes = [vp, vp, i32]
+    L.arap_iterate.argtypes = [vp, i32]
+    L.arap_get_positions.argtypes = [vp, vp, i32]
+    L.arap_deform.argtypes = [vp, vp, i32, i32]
+    L.arap_get_csr_nnz.argtypes = [vp, C.POINTER(i32)]
+    L.arap_get_csr.argtypes = [vp, vp, vp, vp]
+    L.arap_get_free_map.argtypes = [vp, vp, C.POINTER(i32)]
+    L.arap_get_rotations.argtypes = [vp, vp]
+    L.arap_energy.argtypes = [vp, C.POINTER(C.c_double)]
+    L.arap_get_solver_stats.argtypes = [vp, C.POINTER(SolverStats)]
+    L.arap_profile_enable.argtypes = [vp, i32]
+    L.arap_profile_reset.argtypes = [vp]
+    L.arap_profile_get.argtypes = [vp, C.POINTER(Profile)]
+    L.arap_kernel_name.argtypes = [i32]
+    L.arap_kernel_name.restype = C.c_char_p
+    L.arap_timer_start.argtypes = [vp]
+    L.arap_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.arap_synchronize.argtypes = [vp]
+    L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.arap_host_free.argtypes = [vp]
+    L.arap_last_error.argtypes = [vp]
+    L.arap_last_error.restype = C.c_char_p
+    L.arap_create_error.restype = C.c_char_p
+    L.arap_abi_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def default_options():
+    o = Options()
+    lib().arap_default_options(C.byref(o))
+    return o
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """A numpy array backed by page-locked host memory (arap_host_alloc); keep the object alive."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = C.c_void_p()
+        rc = lib().arap_host_alloc(nbytes, C.byref(self._ptr))
+        if rc != ARAP_OK:
+            raise ArapError(rc, "arap_host_alloc failed")
+        buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "_ptr", None) and self._ptr.value:
+            self.array = None
+            lib().arap_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+
+class ArapError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"arap_b200 error {code}: {msg}")
+        self.code = code
+
+
+class AsRigidAsPossibleDeformation:
+    """Host-side mirror of the reference class deform::AsRigidAsPossibleDeformation<MeshType,
+    PrecisionType> (reference inc/deform/arap.h:49-138) on top of the C ABI.
+
+    The "mesh" is a (V,3) float32/float64 numpy array (the reference's `Mesh&`; float32 is the
+    OpenMesh default scalar) plus an (F,3) int32 face array. Same call protocol and semantics:
+    `setConstraint(idx, loc)`, `deform(n) -> bool` (re-reads the rest pose from the mesh when a
+    constraint changed, writes p' back into the mesh array).
+    """
+
+    def __init__(self, positions, faces, precision=None, **options):
+        if positions.dtype not in (np.float32, np.float64) or not positions.flags.c_contiguous:
+            raise TypeError("positions must be a C-contiguous float32/float64 (V,3) array")
+        self.mesh = positions
+        self.faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+        self.real = np.dtype(precision if precision is not None else positions.dtype)
+        self.nV = positions.shape[0]
+        opt = default_options()
+        for k, v in options.items():
+            setattr(opt, k, v)
+        self._h = C.c_void_p()
+        rc = lib().arap_create(_ptr(self.faces), self.faces.shape[0], self.nV, self.real.itemsize, C.byref(opt),
+                               C.byref(self._h))
+        if rc != ARAP_OK:
+            self._h = None
+            raise ArapError(rc, lib().arap_create_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().arap_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ArapError(rc, lib().arap_last_error(self._h).decode())
+        return rc
+
+    # -- reference API ------------------------------------------------------------------------
+    def setConstraint(self, vidx, loc):
+        self.setConstraints(np.array([vidx], np.int32), np.asarray(loc, np.float64).reshape(1, 3))
+
+    def setConstraints(self, indices, locations):
+        """Batched setConstraint: n indices, (n,3) locations (float32 or float64)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        loc = np.ascontiguousarray(locations)
+        if loc.dtype not in (np.float32, np.float64):
+            loc = loc.astype(np.float64)
+        self._check(lib().arap_set_constraints(self._h, idx.size, _ptr(idx), _ptr(loc), loc.dtype.itemsize))
+
+    def deform(self, numberOfIterations):
+        """-> bool, like the reference (False only when the linear system is unusable)."""
+        rc = lib().arap_deform(self._h, _ptr(self.mesh), self.mesh.dtype.itemsize, int(numberOfIterations))
+        if rc in (ARAP_ERR_INVALID, ARAP_ERR_CUDA, ARAP_ERR_ALLOC):
+            raise ArapError(rc, lib().arap_last_error(self._h).decode())
+        return rc >= 0
+
+    # -- split protocol (what deform() is made of) ----------------------------------------------
+    @property
+    def dirty(self):
+        return bool(lib().arap_is_dirty(self._h))
+
+    def prepare(self, rest=None):
+        rest = self.mesh if rest is None else np.ascontiguousarray(rest)
+        return self._check(lib().arap_prepare(self._h, _ptr(rest), rest.dtype.itemsize))
+
+    def iterate(self, n):
+        return self._check(lib().arap_iterate(self._h, int(n)))
+
+    def positions(self, dtype=None):
+        out = np.zeros((self.nV, 3), dtype or self.real)
+        self._check(lib().arap_get_positions(self._h, _ptr(out), out.dtype.itemsize))
+        return out
+
+    # -- inspection -----------------------------------------------------------------------------
+    def cotanWeights(self):
+        """(rowptr, colidx, values) of _edgeWeights -- reference tests/accessor.h:16-22."""
+        nnz = C.c_int32()
+        self._check(lib().arap_get_csr_nnz(self._h, C.byref(nnz)))
+        rp = np.zeros(self.nV + 1, np.int32)
+        ci = np.zeros(nnz.value, np.int32)
+        w = np.zeros(nnz.value, self.real)
+        self._check(lib().arap_get_csr(self._h, _ptr(rp), _ptr(ci), _ptr(w)))
+        return rp, ci, w
+
+    def freeIdxMap(self):
+        out = np.zeros(self.nV, np.int32)
+        n = C.c_int32()
+        self._check(lib().arap_get_free_map(self._h, _ptr(out), C.byref(n)))
+        return out, n.value
+
+    def rotations(self):
+        out = np.zeros((self.nV, 3, 3), self.real)
+        self._check(lib().arap_get_rotations(self._h, _ptr(out)))
+        return out
+
+    def energy(self):
+        e = C.c_double()
+        self._check(lib().arap_energy(self._h, C.byref(e)))
+        return e.value
+
+    def solver_stats(self):
+        s = SolverStats()
+        self._check(lib().arap_get_solver_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in SolverStats._fields_ if f[0] != "reserved"}
+
+    # -- measurement ----------------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(lib().arap_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(lib().arap_profile_reset(self._h))
+
+    def profile(self):
+        p = Profile()
+        self._check(lib().arap_profile_get(self._h, C.byref(p)))
+        out = {}
+        for k in range(K_COUNT_MAX):
+            name = lib().arap_kernel_name(k).decode()
+            if name and p.launches[k]:
+                out[name] = {"launches": int(p.launches[k]), "ms": float(p.milliseconds[k])}
+        return out
+
+    def timer_start(self):
+        self._check(lib().arap_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(lib().arap_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        self._check(lib().arap_synchronize(self._h))

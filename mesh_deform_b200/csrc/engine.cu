@@ -1,0 +1,648 @@
+// engine.cu -- host side of libarap_b200.so: device-memory ownership, kernel sequencing, and the
+// extern "C" entry points declared in include/arap_b200.h. Thin by design: every number is computed
+// by the kernels in kernels.cuh; the host only allocates, launches and copies.
+//
+// Mirrors the control flow of the reference's deform() (reference inc/deform/arap.h:101-138):
+//   prepare()  = the `_dirty` block (:102-120),  iterate() = the loop (:122-129),
+//   get_positions() = the write-back (:133-135).
+#include "../../include/arap_b200.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace arap {
+
+static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
+    "weights_count", "weights_fill", "row_sort_merge", "csr_compact", "scan",
+    "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
+    "cg_update", "cg_direction", "apply_update", "energy", "misc"};
+
+static thread_local std::string g_create_error;
+
+struct Status {
+    int code = ARAP_OK;
+    std::string msg;
+};
+
+#define ARAP_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t err__ = (expr);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            return fail(ARAP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));       \
+        }                                                                                            \
+    } while (0)
+
+static inline int grid_for(size_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+template <typename T>
+struct DeviceBuffer {
+    T *ptr = nullptr;
+    size_t count = 0;
+    ~DeviceBuffer() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= count && ptr) return cudaSuccess;
+        release();
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+        if (e == cudaSuccess) count = n;
+        return e;
+    }
+};
+
+class EngineBase {
+public:
+    virtual ~EngineBase() {}
+    virtual int set_constraints(int n, const int *idx, const void *xyz, int scalar_bytes) = 0;
+    virtual int prepare(const void *rest_xyz, int scalar_bytes) = 0;
+    virtual int iterate(int n) = 0;
+    virtual int get_positions(void *out, int scalar_bytes) = 0;
+    virtual int get_csr_nnz(int *nnz) = 0;
+    virtual int get_csr(int *rowptr, int *colidx, void *weights) = 0;
+    virtual int get_free_map(int *free_idx, int *n_free) = 0;
+    virtual int get_rotations(void *rot9) = 0;
+    virtual int energy(double *e) = 0;
+
+    int fail(int code, const std::string &msg) {
+        last_error = msg;
+        return code;
+    }
+    void activate() { cudaSetDevice(device); }   // every C-ABI entry runs on the handle's device
+
+    // ---- profiling -------------------------------------------------------------------------------
+    struct TimedLaunch { int id; cudaEvent_t start, stop; };
+    void begin_launch(int id) {
+        profile.launches[id] += 1;
+        if (!profile_events) return;
+        TimedLaunch t;
+        t.id = id;
+        cudaEventCreate(&t.start);
+        cudaEventCreate(&t.stop);
+        cudaEventRecord(t.start, stream);
+        pending.push_back(t);
+    }
+    void end_launch() {
+        if (!profile_events) return;
+        cudaEventRecord(pending.back().stop, stream);
+        if (pending.size() >= 4096) collect_profile();
+    }
+    void collect_profile() {
+        if (pending.empty()) return;
+        cudaStreamSynchronize(stream);
+        for (auto &t : pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) profile.milliseconds[t.id] += ms;
+            cudaEventDestroy(t.start);
+            cudaEventDestroy(t.stop);
+        }
+        pending.clear();
+    }
+
+    int n_vertices = 0, n_faces = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    arap_options opt;
+    bool dirty = true;
+    bool prepared = false;
+    std::string last_error;
+    arap_profile profile;
+    bool profile_events = false;
+    std::vector<TimedLaunch> pending;
+    arap_solver_stats stats;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+};
+
+#define LAUNCH(id, kernel, grid, ...)                                                \
+    do {                                                                             \
+        begin_launch(id);                                                            \
+        kernel<<<(grid), kBlock, 0, stream>>>(__VA_ARGS__);                          \
+        end_launch();                                                                \
+    } while (0)
+
+template <typename S>
+class Engine : public EngineBase {
+public:
+    // ---- device state (see kernels.cuh for the layout) -------------------------------------------
+    DeviceBuffer<int> faces;                       // _faces
+    DeviceBuffer<S> rest_xyz;                      // rest pose as uploaded (V x 3)
+    DeviceBuffer<unsigned char> is_constrained;    // key set of _constrainedLocations
+    DeviceBuffer<S> target_xyz;                    // values of _constrainedLocations (dense, V x 3)
+    DeviceBuffer<int> rowptr, colidx;              // _edgeWeights
+    DeviceBuffer<S> weight;
+    DeviceBuffer<int> free_idx;                    // _freeIdxMap
+    DeviceBuffer<Vec4T<S>> rest4, cur4, quat;      // _p, _pprime, _rotations
+    DeviceBuffer<double> inv_diag;
+    DeviceBuffer<Vec3d> cg_r, cg_d, cg_ad, cg_x;
+    DeviceBuffer<double> partials;
+    DeviceBuffer<unsigned> counter;
+    DeviceBuffer<CgScalars> cg;
+    DeviceBuffer<double> energy_dev;
+    // scratch for the CSR build
+    DeviceBuffer<int> row_count, raw_rowptr, row_cursor, raw_col, unique_count, scan_tiles, flags;
+    DeviceBuffer<S> raw_val;
+    DeviceBuffer<unsigned> raw_tag;
+    DeviceBuffer<unsigned char> staging;           // uploads / downloads in a foreign scalar type
+
+    int nnz = 0;
+    int n_free = 0;
+    int n_constrained_calls = 0;
+    CgScalars *cg_host = nullptr;                  // pinned mirror for convergence polls
+    cudaEvent_t poll_event[2] = {nullptr, nullptr};
+
+    ~Engine() override {
+        collect_profile();
+        if (cg_host) cudaFreeHost(cg_host);
+        for (auto &e : poll_event) if (e) cudaEventDestroy(e);
+        if (timer_start) cudaEventDestroy(timer_start);
+        if (timer_stop) cudaEventDestroy(timer_stop);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int init(const int *faces_host, int nf, int nv, const arap_options &o) {
+        opt = o;
+        n_vertices = nv;
+        n_faces = nf;
+        std::memset(&profile, 0, sizeof(profile));
+        std::memset(&stats, 0, sizeof(stats));
+        profile_events = o.profile != 0;
+        int count = 0;
+        ARAP_CUDA(cudaGetDeviceCount(&count));
+        if (count <= 0) return fail(ARAP_ERR_CUDA, "no CUDA device");
+        if (o.device >= 0) {
+            ARAP_CUDA(cudaSetDevice(o.device));
+            device = o.device;
+        } else {
+            ARAP_CUDA(cudaGetDevice(&device));
+        }
+        ARAP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        ARAP_CUDA(cudaEventCreate(&timer_start));
+        ARAP_CUDA(cudaEventCreate(&timer_stop));
+        ARAP_CUDA(cudaEventCreateWithFlags(&poll_event[0], cudaEventDisableTiming));
+        ARAP_CUDA(cudaEventCreateWithFlags(&poll_event[1], cudaEventDisableTiming));
+        ARAP_CUDA(cudaMallocHost(&cg_host, 2 * sizeof(CgScalars)));
+        ARAP_CUDA(faces.ensure(3 * (size_t)nf));
+        ARAP_CUDA(cudaMemcpyAsync(faces.ptr, faces_host, sizeof(int) * 3 * (size_t)nf, cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(is_constrained.ensure((size_t)nv));
+        ARAP_CUDA(target_xyz.ensure(3 * (size_t)nv));
+        ARAP_CUDA(cudaMemsetAsync(is_constrained.ptr, 0, (size_t)(nv > 0 ? nv : 1), stream));
+        ARAP_CUDA(cudaMemsetAsync(target_xyz.ptr, 0, sizeof(S) * 3 * (size_t)(nv > 0 ? nv : 1), stream));
+        ARAP_CUDA(partials.ensure((size_t)(grid_for((size_t)nv) + 1) * 8));
+        ARAP_CUDA(counter.ensure(1));
+        ARAP_CUDA(cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned), stream));
+        ARAP_CUDA(cg.ensure(1));
+        ARAP_CUDA(cudaMemsetAsync(cg.ptr, 0, sizeof(CgScalars), stream));
+        ARAP_CUDA(energy_dev.ensure(1));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+
+    // exclusive scan of in[0..n) into out[0..n] on the stream
+    int exclusive_scan(const int *in, int n, int *out) {
+        const int tiles = (n + kScanTile - 1) / kScanTile;
+        if (tiles == 0) {
+            ARAP_CUDA(cudaMemsetAsync(out, 0, sizeof(int), stream));
+            return ARAP_OK;
+        }
+        ARAP_CUDA(scan_tiles.ensure((size_t)tiles + 1));
+        begin_launch(ARAP_K_SCAN);
+        scan_tile_sums<<<tiles, kBlock, 0, stream>>>(in, n, scan_tiles.ptr);
+        scan_spine<<<1, kBlock, 0, stream>>>(scan_tiles.ptr, tiles);
+        scan_apply<<<tiles, kBlock, 0, stream>>>(in, n, scan_tiles.ptr, tiles, out);
+        end_launch();
+        ARAP_CUDA(cudaGetLastError());
+        return ARAP_OK;
+    }
+
+    // upload a host xyz array of n scalars in `scalar_bytes` precision into a device S array
+    int upload_cast(const void *host, size_t n, int scalar_bytes, S *dst) {
+        if (scalar_bytes == (int)sizeof(S)) {
+            ARAP_CUDA(cudaMemcpyAsync(dst, host, n * sizeof(S), cudaMemcpyHostToDevice, stream));
+            return ARAP_OK;
+        }
+        ARAP_CUDA(staging.ensure(n * (size_t)scalar_bytes));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr, host, n * (size_t)scalar_bytes, cudaMemcpyHostToDevice, stream));
+        begin_launch(ARAP_K_MISC);
+        if (scalar_bytes == 4) cast_xyz_kernel<S, float><<<grid_for(n), kBlock, 0, stream>>>(n, (const float *)staging.ptr, dst);
+        else cast_xyz_kernel<S, double><<<grid_for(n), kBlock, 0, stream>>>(n, (const double *)staging.ptr, dst);
+        end_launch();
+        ARAP_CUDA(cudaGetLastError());
+        return ARAP_OK;
+    }
+
+    int set_constraints(int n, const int *idx, const void *xyz, int scalar_bytes) override {
+        if (n < 0 || (n > 0 && (!idx || !xyz)) || (scalar_bytes != 4 && scalar_bytes != 8))
+            return fail(ARAP_ERR_INVALID, "set_constraints: bad arguments");
+        for (int k = 0; k < n; ++k)
+            if (idx[k] < 0 || idx[k] >= n_vertices) return fail(ARAP_ERR_INVALID, "set_constraints: vertex index out of range");
+        dirty = true;                                                    // arap.h:84
+        if (n == 0) return ARAP_OK;
+        const size_t idx_bytes = sizeof(int) * (size_t)n, xyz_bytes = (size_t)scalar_bytes * 3 * (size_t)n;
+        const size_t xyz_off = (idx_bytes + 15) & ~(size_t)15;
+        ARAP_CUDA(staging.ensure(xyz_off + xyz_bytes));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr, idx, idx_bytes, cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr + xyz_off, xyz, xyz_bytes, cudaMemcpyHostToDevice, stream));
+        begin_launch(ARAP_K_MISC);
+        if (scalar_bytes == 4)
+            set_constraints_kernel<S, float><<<grid_for((size_t)n), kBlock, 0, stream>>>(
+                n, (const int *)staging.ptr, (const float *)(staging.ptr + xyz_off), n_vertices, is_constrained.ptr, target_xyz.ptr);
+        else
+            set_constraints_kernel<S, double><<<grid_for((size_t)n), kBlock, 0, stream>>>(
+                n, (const int *)staging.ptr, (const double *)(staging.ptr + xyz_off), n_vertices, is_constrained.ptr, target_xyz.ptr);
+        end_launch();
+        ARAP_CUDA(cudaGetLastError());
+        ARAP_CUDA(cudaStreamSynchronize(stream));   // host buffers are caller-owned: finish the copies before returning
+        return ARAP_OK;
+    }
+
+    int prepare(const void *rest_host, int scalar_bytes) override {
+        if (!rest_host || (scalar_bytes != 4 && scalar_bytes != 8)) return fail(ARAP_ERR_INVALID, "prepare: bad arguments");
+        const int V = n_vertices, F = n_faces;
+        prepared = false;
+        std::memset(&stats, 0, sizeof(stats));
+        // ---- initializeMeshGeometry (arap.h:162-168)
+        ARAP_CUDA(rest_xyz.ensure(3 * (size_t)V));
+        { int rc = upload_cast(rest_host, 3 * (size_t)V, scalar_bytes, rest_xyz.ptr); if (rc) return rc; }
+        // ---- computeCotanWeights (arap.h:182-239)
+        ARAP_CUDA(row_count.ensure((size_t)V + 1));
+        ARAP_CUDA(raw_rowptr.ensure((size_t)V + 1));
+        ARAP_CUDA(row_cursor.ensure((size_t)V + 1));
+        ARAP_CUDA(unique_count.ensure((size_t)V + 1));
+        ARAP_CUDA(rowptr.ensure((size_t)V + 1));
+        ARAP_CUDA(raw_col.ensure(6 * (size_t)F));
+        ARAP_CUDA(raw_val.ensure(6 * (size_t)F));
+        ARAP_CUDA(raw_tag.ensure(6 * (size_t)F));
+        ARAP_CUDA(cudaMemsetAsync(row_count.ptr, 0, sizeof(int) * ((size_t)V + 1), stream));
+        ARAP_CUDA(cudaMemsetAsync(row_cursor.ptr, 0, sizeof(int) * ((size_t)V + 1), stream));
+        if (F > 0) LAUNCH(ARAP_K_WEIGHTS_COUNT, weights_count_kernel, grid_for((size_t)F), faces.ptr, F, row_count.ptr);
+        { int rc = exclusive_scan(row_count.ptr, V, raw_rowptr.ptr); if (rc) return rc; }
+        if (F > 0)
+            LAUNCH(ARAP_K_WEIGHTS_FILL, weights_fill_kernel<S>, grid_for((size_t)F), faces.ptr, F, rest_xyz.ptr, raw_rowptr.ptr,
+                   row_cursor.ptr, raw_col.ptr, raw_val.ptr, raw_tag.ptr);
+        if (V > 0)
+            LAUNCH(ARAP_K_ROW_SORT_MERGE, row_sort_merge_kernel<S>, grid_for((size_t)V), V, raw_rowptr.ptr, raw_col.ptr, raw_val.ptr,
+                   raw_tag.ptr, unique_count.ptr);
+        { int rc = exclusive_scan(unique_count.ptr, V, rowptr.ptr); if (rc) return rc; }
+        ARAP_CUDA(cudaMemcpyAsync(&nnz, rowptr.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(colidx.ensure((size_t)nnz));
+        ARAP_CUDA(weight.ensure((size_t)nnz));
+        if (V > 0)
+            LAUNCH(ARAP_K_CSR_COMPACT, csr_compact_kernel<S>, grid_for((size_t)V), V, raw_rowptr.ptr, raw_col.ptr, raw_val.ptr,
+                   rowptr.ptr, colidx.ptr, weight.ptr);
+        // ---- initializeFreeVariableMapping (arap.h:261-272)
+        ARAP_CUDA(flags.ensure((size_t)V + 1));
+        ARAP_CUDA(free_idx.ensure((size_t)V + 1));
+        if (V > 0) LAUNCH(ARAP_K_MISC, free_flag_kernel, grid_for((size_t)V), V, is_constrained.ptr, flags.ptr);
+        { int rc = exclusive_scan(flags.ptr, V, row_count.ptr); if (rc) return rc; }   // row_count reused as the prefix array
+        ARAP_CUDA(cudaMemcpyAsync(&n_free, row_count.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (V > 0) LAUNCH(ARAP_K_MISC, free_map_kernel, grid_for((size_t)V), V, is_constrained.ptr, row_count.ptr, free_idx.ptr);
+        // ---- initializeMeshGeometry / Rotations / Constraints into the solver layout (arap.h:162-168,246-249,277-281)
+        ARAP_CUDA(rest4.ensure((size_t)V));
+        ARAP_CUDA(cur4.ensure((size_t)V));
+        ARAP_CUDA(quat.ensure((size_t)V));
+        ARAP_CUDA(inv_diag.ensure((size_t)V));
+        if (V > 0)
+            LAUNCH(ARAP_K_INIT_STATE, init_state_kernel<S>, grid_for((size_t)V), V, rest_xyz.ptr, is_constrained.ptr, target_xyz.ptr,
+                   rowptr.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr);
+        ARAP_CUDA(cudaGetLastError());
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        if (n_free == V) return ARAP_UNCONSTRAINED;                      // arap.h:113-114: stays dirty, nothing solved
+        // ---- setupLinearSystem (arap.h:292-340): matrix-free L, nothing to factor; allocate the CG vectors
+        ARAP_CUDA(cg_r.ensure((size_t)V));
+        ARAP_CUDA(cg_d.ensure((size_t)V));
+        ARAP_CUDA(cg_ad.ensure((size_t)V));
+        ARAP_CUDA(cg_x.ensure((size_t)V));
+        CgScalars init;
+        std::memset(&init, 0, sizeof(init));
+        const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : 1e-10;
+        init.tol2 = tol * tol;
+        cg_host[0] = init;
+        ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        dirty = false;                                                   // arap.h:119
+        prepared = true;
+        return ARAP_OK;
+    }
+
+    int global_step() {
+        const int V = n_vertices, G = grid_for((size_t)V);
+        LAUNCH(ARAP_K_RHS_RESIDUAL, rhs_residual_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+               inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg_x.ptr, partials.ptr, counter.ptr, cg.ptr);
+        const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
+        const int check = opt.cg_check_interval > 0 ? opt.cg_check_interval : 32;
+        // Batches of `check` CG iterations are enqueued one batch ahead of the convergence poll, so
+        // the device never idles waiting for the host; once converged the kernels return immediately.
+        int issued = 0, slot = 0;
+        bool have_poll[2] = {false, false};
+        bool done = false;
+        while (!done) {
+            const int batch = (max_it - issued < check) ? (max_it - issued) : check;
+            for (int it = 0; it < batch; ++it) {
+                LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+                       partials.ptr, counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, G, V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
+                       counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, G, V, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+            }
+            issued += batch;
+            ARAP_CUDA(cudaMemcpyAsync(&cg_host[slot], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaEventRecord(poll_event[slot], stream));
+            have_poll[slot] = true;
+            const int prev = slot ^ 1;
+            if (have_poll[prev]) {
+                ARAP_CUDA(cudaEventSynchronize(poll_event[prev]));
+                if (cg_host[prev].converged) done = true;
+            }
+            if (issued >= max_it || batch == 0) done = true;
+            slot ^= 1;
+        }
+        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, V, rest4.ptr, cg_x.ptr, cur4.ptr);
+        ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        stats.global_steps += 1;
+        stats.cg_iterations_total += cg_host[0].iterations;
+        stats.last_cg_iterations = cg_host[0].iterations;
+        stats.last_converged = cg_host[0].converged;
+        stats.last_relative_residual = cg_host[0].ref2 > 0 ? sqrt(cg_host[0].rr / cg_host[0].ref2) : 0.0;
+        if (!(cg_host[0].rr == cg_host[0].rr)) return fail(ARAP_ERR_SOLVER, "global step: CG residual is NaN");
+        return ARAP_OK;
+    }
+
+    int iterate(int n) override {
+        if (!prepared) return fail(ARAP_ERR_INVALID, "iterate: arap_prepare has not succeeded");
+        const int V = n_vertices, G = grid_for((size_t)V);
+        for (int it = 0; it < n; ++it) {
+            LAUNCH(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
+            int rc = global_step();
+            if (rc) return rc;
+        }
+        ARAP_CUDA(cudaGetLastError());
+        return ARAP_OK;
+    }
+
+    int get_positions(void *out, int scalar_bytes) override {
+        if (!out || (scalar_bytes != 4 && scalar_bytes != 8)) return fail(ARAP_ERR_INVALID, "get_positions: bad arguments");
+        if (!cur4.ptr) return fail(ARAP_ERR_INVALID, "get_positions: no state (call arap_prepare first)");
+        const int V = n_vertices;
+        const size_t bytes = (size_t)scalar_bytes * 3 * (size_t)V;
+        ARAP_CUDA(staging.ensure(bytes));
+        begin_launch(ARAP_K_MISC);
+        if (scalar_bytes == 4) export_positions_kernel<S, float><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, cur4.ptr, (float *)staging.ptr);
+        else export_positions_kernel<S, double><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, cur4.ptr, (double *)staging.ptr);
+        end_launch();
+        ARAP_CUDA(cudaMemcpyAsync(out, staging.ptr, bytes, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+
+    int get_csr_nnz(int *out) override {
+        if (!rowptr.ptr) return fail(ARAP_ERR_INVALID, "get_csr: weights not built (call arap_prepare first)");
+        *out = nnz;
+        return ARAP_OK;
+    }
+    int get_csr(int *rp, int *ci, void *w) override {
+        if (!rowptr.ptr) return fail(ARAP_ERR_INVALID, "get_csr: weights not built (call arap_prepare first)");
+        ARAP_CUDA(cudaMemcpyAsync(rp, rowptr.ptr, sizeof(int) * ((size_t)n_vertices + 1), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaMemcpyAsync(ci, colidx.ptr, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaMemcpyAsync(w, weight.ptr, sizeof(S) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+    int get_free_map(int *fi, int *nf) override {
+        if (!free_idx.ptr) return fail(ARAP_ERR_INVALID, "get_free_map: call arap_prepare first");
+        if (fi) ARAP_CUDA(cudaMemcpyAsync(fi, free_idx.ptr, sizeof(int) * (size_t)n_vertices, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        if (nf) *nf = n_free;
+        return ARAP_OK;
+    }
+    int get_rotations(void *rot9) override {
+        if (!quat.ptr) return fail(ARAP_ERR_INVALID, "get_rotations: call arap_prepare first");
+        const int V = n_vertices;
+        ARAP_CUDA(staging.ensure(sizeof(S) * 9 * (size_t)V));
+        LAUNCH(ARAP_K_MISC, export_rotations_kernel<S>, grid_for((size_t)V), V, quat.ptr, (S *)staging.ptr);
+        ARAP_CUDA(cudaMemcpyAsync(rot9, staging.ptr, sizeof(S) * 9 * (size_t)V, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+    int energy(double *e) override {
+        if (!quat.ptr || !rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
+        const int V = n_vertices;
+        LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+               partials.ptr, counter.ptr, energy_dev.ptr);
+        ARAP_CUDA(cudaMemcpyAsync(e, energy_dev.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+};
+
+}  // namespace arap
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+struct arap_handle {
+    arap::EngineBase *engine;
+    int precision_bytes;
+};
+
+extern "C" {
+
+int arap_abi_version(void) { return ARAP_B200_ABI_VERSION; }
+
+void arap_default_options(arap_options *opt) {
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->struct_size = (int32_t)sizeof(arap_options);
+    opt->device = -1;
+    opt->solver = ARAP_SOLVER_AUTO;
+    opt->max_cg_iterations = 20000;
+    opt->cg_tolerance = 1e-10;
+    opt->cg_check_interval = 32;
+    opt->profile = 0;
+}
+
+const char *arap_create_error(void) { return arap::g_create_error.c_str(); }
+
+int arap_create(const int32_t *faces, int32_t n_faces, int32_t n_vertices, int32_t precision_bytes, const arap_options *opt,
+                arap_handle **out) {
+    if (!out) return ARAP_ERR_INVALID;
+    *out = nullptr;
+    if (n_faces < 0 || n_vertices < 0 || (n_faces > 0 && !faces) || (precision_bytes != 4 && precision_bytes != 8)) {
+        arap::g_create_error = "arap_create: bad arguments";
+        return ARAP_ERR_INVALID;
+    }
+    for (size_t k = 0; k < 3 * (size_t)n_faces; ++k)
+        if (faces[k] < 0 || faces[k] >= n_vertices) {
+            arap::g_create_error = "arap_create: face references a vertex index out of range";
+            return ARAP_ERR_INVALID;
+        }
+    arap_options o;
+    arap_default_options(&o);
+    if (opt) {
+        size_t sz = opt->struct_size > 0 ? (size_t)opt->struct_size : sizeof(arap_options);
+        if (sz > sizeof(arap_options)) sz = sizeof(arap_options);
+        std::memcpy(&o, opt, sz);
+        o.struct_size = (int32_t)sizeof(arap_options);
+    }
+    arap_handle *h = new (std::nothrow) arap_handle;
+    if (!h) return ARAP_ERR_ALLOC;
+    h->precision_bytes = precision_bytes;
+    int rc;
+    if (precision_bytes == 4) {
+        auto *e = new (std::nothrow) arap::Engine<float>();
+        if (!e) { delete h; return ARAP_ERR_ALLOC; }
+        rc = e->init(faces, n_faces, n_vertices, o);
+        h->engine = e;
+    } else {
+        auto *e = new (std::nothrow) arap::Engine<double>();
+        if (!e) { delete h; return ARAP_ERR_ALLOC; }
+        rc = e->init(faces, n_faces, n_vertices, o);
+        h->engine = e;
+    }
+    if (rc != ARAP_OK) {
+        arap::g_create_error = h->engine->last_error;
+        delete h->engine;
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return ARAP_OK;
+}
+
+void arap_destroy(arap_handle *h) {
+    if (!h) return;
+    delete h->engine;
+    delete h;
+}
+
+#define ARAP_ENGINE_OR_FAIL(h) do { if (!(h) || !(h)->engine) return ARAP_ERR_INVALID; (h)->engine->activate(); } while (0)
+
+int arap_set_constraints(arap_handle *h, int32_t n, const int32_t *idx, const void *xyz, int32_t xyz_scalar_bytes) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->set_constraints(n, idx, xyz, xyz_scalar_bytes);
+}
+
+int arap_is_dirty(const arap_handle *h) { return (h && h->engine) ? (h->engine->dirty ? 1 : 0) : 1; }
+
+int arap_prepare(arap_handle *h, const void *rest_xyz, int32_t rest_scalar_bytes) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->prepare(rest_xyz, rest_scalar_bytes);
+}
+
+int arap_iterate(arap_handle *h, int32_t n) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (n < 0) return h->engine->fail(ARAP_ERR_INVALID, "iterate: negative iteration count");
+    return h->engine->iterate(n);
+}
+
+int arap_get_positions(arap_handle *h, void *out_xyz, int32_t out_scalar_bytes) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->get_positions(out_xyz, out_scalar_bytes);
+}
+
+int arap_deform(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32_t n_iterations) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!mesh_xyz) return h->engine->fail(ARAP_ERR_INVALID, "deform: null mesh");
+    if (h->engine->dirty) {                                               /* arap.h:102 */
+        int rc = h->engine->prepare(mesh_xyz, mesh_scalar_bytes);
+        if (rc != ARAP_OK) return rc;                                     /* UNCONSTRAINED -> true, no write-back (:113-114) */
+    }
+    int rc = h->engine->iterate(n_iterations);
+    if (rc != ARAP_OK) return rc;
+    return h->engine->get_positions(mesh_xyz, mesh_scalar_bytes);         /* arap.h:133-135 */
+}
+
+int arap_get_csr_nnz(arap_handle *h, int32_t *nnz) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!nnz) return ARAP_ERR_INVALID;
+    return h->engine->get_csr_nnz(nnz);
+}
+int arap_get_csr(arap_handle *h, int32_t *rowptr, int32_t *colidx, void *weights) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!rowptr || !colidx || !weights) return ARAP_ERR_INVALID;
+    return h->engine->get_csr(rowptr, colidx, weights);
+}
+int arap_get_free_map(arap_handle *h, int32_t *free_idx, int32_t *n_free) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->get_free_map(free_idx, n_free);
+}
+int arap_get_rotations(arap_handle *h, void *rot9) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!rot9) return ARAP_ERR_INVALID;
+    return h->engine->get_rotations(rot9);
+}
+int arap_energy(arap_handle *h, double *energy) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!energy) return ARAP_ERR_INVALID;
+    return h->engine->energy(energy);
+}
+int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!out) return ARAP_ERR_INVALID;
+    *out = h->engine->stats;
+    return ARAP_OK;
+}
+
+int arap_profile_enable(arap_handle *h, int32_t enable) {
+    ARAP_ENGINE_OR_FAIL(h);
+    h->engine->collect_profile();
+    h->engine->profile_events = enable != 0;
+    return ARAP_OK;
+}
+int arap_profile_reset(arap_handle *h) {
+    ARAP_ENGINE_OR_FAIL(h);
+    h->engine->collect_profile();
+    std::memset(&h->engine->profile, 0, sizeof(arap_profile));
+    return ARAP_OK;
+}
+int arap_profile_get(arap_handle *h, arap_profile *out) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!out) return ARAP_ERR_INVALID;
+    h->engine->collect_profile();
+    *out = h->engine->profile;
+    return ARAP_OK;
+}
+const char *arap_kernel_name(int32_t id) {
+    if (id < 0 || id >= ARAP_K_COUNT_MAX || !arap::kKernelNames[id]) return "";
+    return arap::kKernelNames[id];
+}
+
+int arap_timer_start(arap_handle *h) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return cudaEventRecord(h->engine->timer_start, h->engine->stream) == cudaSuccess ? ARAP_OK : ARAP_ERR_CUDA;
+}
+int arap_timer_stop(arap_handle *h, double *ms) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (cudaEventRecord(h->engine->timer_stop, h->engine->stream) != cudaSuccess) return ARAP_ERR_CUDA;
+    if (cudaEventSynchronize(h->engine->timer_stop) != cudaSuccess) return ARAP_ERR_CUDA;
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, h->engine->timer_start, h->engine->timer_stop) != cudaSuccess) return ARAP_ERR_CUDA;
+    if (ms) *ms = (double)f;
+    return ARAP_OK;
+}
+int arap_synchronize(arap_handle *h) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return cudaStreamSynchronize(h->engine->stream) == cudaSuccess ? ARAP_OK : ARAP_ERR_CUDA;
+}
+
+int arap_host_alloc(size_t bytes, void **out) {
+    if (!out) return ARAP_ERR_INVALID;
+    *out = nullptr;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? ARAP_OK : ARAP_ERR_CUDA;
+}
+int arap_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? ARAP_OK : ARAP_ERR_CUDA; }
+
+const char *arap_last_error(const arap_handle *h) { return (h && h->engine) ? h->engine->last_error.c_str() : "invalid handle"; }
+
+}  // extern "C"

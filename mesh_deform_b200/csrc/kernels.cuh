@@ -1,0 +1,433 @@
+// kernels.cuh -- the CUDA kernels of the ARAP hot path (sm_100a). One thread per face / vertex / row;
+// all are HBM-bound gather/stream kernels (no tensor cores: there is no dense contraction here).
+//
+// Data layout in HBM (S = float|double = the reference's PrecisionType):
+//   rest4[V], cur4[V]  Vec4T<S>: (x,y,z,mask) rest pose p, (x,y,z,-) current pose p'.  rest4.w = 1 free / 0 constrained.
+//   quat[V]            Vec4T<S>: unit quaternion (w,x,y,z) of R_i (the reference stores 3x3 matrices, arap.h:454).
+//   rowptr[V+1], colidx[nnz] int32, weight[nnz] S: _edgeWeights CSR (arap.h:453), columns ascending.
+//   cg vectors         Vec3d[V]: one (x,y,z) triple of doubles per vertex (three right-hand sides solved together).
+#pragma once
+
+#include "arap_math.cuh"
+#include "device_utils.cuh"
+
+namespace arap {
+
+template <typename S> __device__ __forceinline__ Vec4T<S> load4(const Vec4T<S> *p);
+template <> __device__ __forceinline__ Vec4T<float> load4<float>(const Vec4T<float> *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    return Vec4T<float>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Vec4T<double> load4<double>(const Vec4T<double> *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return Vec4T<double>{a.x, a.y, b.x, b.y};
+}
+template <typename S> __device__ __forceinline__ void store4(Vec4T<S> *p, S x, S y, S z, S w);
+template <> __device__ __forceinline__ void store4<float>(Vec4T<float> *p, float x, float y, float z, float w) {
+    *reinterpret_cast<float4 *>(p) = make_float4(x, y, z, w);
+}
+template <> __device__ __forceinline__ void store4<double>(Vec4T<double> *p, double x, double y, double z, double w) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(x, y);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(z, w);
+}
+
+// =================================================================================================
+// Setup path: cotan weights + CSR (reference arap.h:182-239), free map (:261-272), constraints (:277-281)
+// =================================================================================================
+
+// K1a: how many raw triplets land in each row. Each face emits, per edge, (lo,hi) and (hi,lo)  (arap.h:225-232).
+__global__ void __launch_bounds__(kBlock) weights_count_kernel(const int *__restrict__ faces, int n_faces, int *__restrict__ row_count) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const int v0 = faces[3 * (size_t)f], v1 = faces[3 * (size_t)f + 1], v2 = faces[3 * (size_t)f + 2];
+    atomicAdd(&row_count[v0], 2);   // v0 is an end point of e0 and e2
+    atomicAdd(&row_count[v1], 2);   // e0, e1
+    atomicAdd(&row_count[v2], 2);   // e1, e2
+}
+
+// K1b: compute the three half-cotans of every face and scatter the 6 triplets into their rows.
+// tag = insertion index of the triplet in the reference's triplet list (6 f + slot), used to sum
+// duplicates in the reference's order.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) weights_fill_kernel(const int *__restrict__ faces, int n_faces, const S *__restrict__ rest_xyz,
+                                                              const int *__restrict__ raw_rowptr, int *__restrict__ row_cursor,
+                                                              int *__restrict__ raw_col, S *__restrict__ raw_val, unsigned *__restrict__ raw_tag) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    int vid[3];
+    S pos[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vid[k] = faces[3 * (size_t)f + k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pos[k][d] = rest_xyz[3 * (size_t)vid[k] + d];
+    }
+    S hw[3];
+    cotan_half_weights<S>(pos[0], pos[1], pos[2], hw);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = vid[k], b = vid[(k + 1) % 3];
+        const int lo = a > b ? b : a, hi = a > b ? a : b;           // undirectedEdge (arap.h:435-440)
+        int slot = raw_rowptr[lo] + atomicAdd(&row_cursor[lo], 1);
+        raw_col[slot] = hi; raw_val[slot] = hw[k]; raw_tag[slot] = 6u * (unsigned)f + (unsigned)k;
+        slot = raw_rowptr[hi] + atomicAdd(&row_cursor[hi], 1);
+        raw_col[slot] = lo; raw_val[slot] = hw[k]; raw_tag[slot] = 6u * (unsigned)f + 3u + (unsigned)k;
+    }
+}
+
+// K2a: setFromTriplets for one row (arap.h:238): sort the row's raw triplets by (column, insertion order),
+// sum duplicates in insertion order, leave the unique entries at the front of the raw segment.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) row_sort_merge_kernel(int n_rows, const int *__restrict__ raw_rowptr, int *__restrict__ raw_col,
+                                                                S *__restrict__ raw_val, unsigned *__restrict__ raw_tag,
+                                                                int *__restrict__ unique_count) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int lo = raw_rowptr[r], hi = raw_rowptr[r + 1];
+    for (int a = lo + 1; a < hi; ++a) {                              // insertion sort: rows are ~12 entries long
+        const int cj = raw_col[a]; const S cv = raw_val[a]; const unsigned ct = raw_tag[a];
+        int b = a - 1;
+        while (b >= lo && (raw_col[b] > cj || (raw_col[b] == cj && raw_tag[b] > ct))) {
+            raw_col[b + 1] = raw_col[b]; raw_val[b + 1] = raw_val[b]; raw_tag[b + 1] = raw_tag[b];
+            --b;
+        }
+        raw_col[b + 1] = cj; raw_val[b + 1] = cv; raw_tag[b + 1] = ct;
+    }
+    int out = lo;
+    for (int a = lo; a < hi;) {
+        const int cj = raw_col[a];
+        S s = raw_val[a];
+        ++a;
+        while (a < hi && raw_col[a] == cj) { s = add_rn(s, raw_val[a]); ++a; }
+        raw_col[out] = cj; raw_val[out] = s; ++out;
+    }
+    unique_count[r] = out - lo;
+}
+
+// K2b: pack the unique entries into the final CSR.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) csr_compact_kernel(int n_rows, const int *__restrict__ raw_rowptr, const int *__restrict__ raw_col,
+                                                             const S *__restrict__ raw_val, const int *__restrict__ rowptr,
+                                                             int *__restrict__ colidx, S *__restrict__ weight) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int src = raw_rowptr[r], dst = rowptr[r], n = rowptr[r + 1] - dst;
+    for (int k = 0; k < n; ++k) { colidx[dst + k] = raw_col[src + k]; weight[dst + k] = raw_val[src + k]; }
+}
+
+// setConstraint (arap.h:81-85): scatter n (index, location) pairs into the dense constraint table.
+template <typename S, typename T>
+__global__ void __launch_bounds__(kBlock) set_constraints_kernel(int n, const int *__restrict__ idx, const T *__restrict__ xyz,
+                                                                 int n_vertices, unsigned char *__restrict__ is_constrained,
+                                                                 S *__restrict__ target_xyz) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int v = idx[k];
+    if (v < 0 || v >= n_vertices) return;
+    is_constrained[v] = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) target_xyz[3 * (size_t)v + d] = (S)xyz[3 * (size_t)k + d];
+}
+
+template <typename S, typename T>
+__global__ void __launch_bounds__(kBlock) cast_xyz_kernel(size_t n, const T *__restrict__ in, S *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (S)in[i];
+}
+
+__global__ void __launch_bounds__(kBlock) free_flag_kernel(int n, const unsigned char *__restrict__ is_constrained, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = is_constrained[i] ? 0 : 1;
+}
+
+// initializeFreeVariableMapping (arap.h:261-272): prefix -> free index, -1 for constrained.
+__global__ void __launch_bounds__(kBlock) free_map_kernel(int n, const unsigned char *__restrict__ is_constrained,
+                                                          const int *__restrict__ prefix, int *__restrict__ free_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) free_idx[i] = is_constrained[i] ? -1 : prefix[i];
+}
+
+// initializeMeshGeometry + initializeRotations + initializeConstraints (arap.h:162-168, 246-249, 277-281)
+// plus the Jacobi preconditioner 1 / L_ii = 1 / sum_j w_ij (the diagonal of arap.h:332).
+template <typename S>
+__global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const S *__restrict__ rest_xyz, const unsigned char *__restrict__ is_constrained,
+                                                            const S *__restrict__ target_xyz, const int *__restrict__ rowptr,
+                                                            const S *__restrict__ weight, Vec4T<S> *__restrict__ rest4,
+                                                            Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
+                                                            double *__restrict__ inv_diag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool con = is_constrained[i] != 0;
+    const S x = rest_xyz[3 * (size_t)i], y = rest_xyz[3 * (size_t)i + 1], z = rest_xyz[3 * (size_t)i + 2];
+    store4<S>(&rest4[i], x, y, z, con ? S(0) : S(1));
+    if (con) store4<S>(&cur4[i], target_xyz[3 * (size_t)i], target_xyz[3 * (size_t)i + 1], target_xyz[3 * (size_t)i + 2], S(0));
+    else store4<S>(&cur4[i], x, y, z, S(0));
+    store4<S>(&quat[i], S(1), S(0), S(0), S(0));
+    double diag = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) diag += (double)weight[k];
+    inv_diag[i] = diag > 0.0 ? 1.0 / diag : 0.0;
+}
+
+// =================================================================================================
+// Local step (reference arap.h:354-384): S_i = sum_j w_ij (p_i-p_j)(p'_i-p'_j)^T, R_i from its SVD.
+// =================================================================================================
+template <typename S>
+__global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                            const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec4T<S> pi = load4<S>(&rest4[i]);
+    const Vec4T<S> qi = load4<S>(&cur4[i]);
+    const int k0 = rowptr[i], k1 = rowptr[i + 1];
+    S cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = k0; k < k1; ++k) {
+        const int j = __ldg(&colidx[k]);
+        const S w = __ldg(&weight[k]);
+        const Vec4T<S> pj = load4<S>(&rest4[j]);
+        const Vec4T<S> qj = load4<S>(&cur4[j]);
+        const S ex = w * (pi.x - pj.x), ey = w * (pi.y - pj.y), ez = w * (pi.z - pj.z);
+        const S dx = qi.x - qj.x, dy = qi.y - qj.y, dz = qi.z - qj.z;
+        cov[0] += ex * dx; cov[1] += ex * dy; cov[2] += ex * dz;
+        cov[3] += ey * dx; cov[4] += ey * dy; cov[5] += ey * dz;
+        cov[6] += ez * dx; cov[7] += ez * dy; cov[8] += ez * dz;
+    }
+    S q[4];
+    rotation_from_covariance<S>(cov, q);
+    store4<S>(&quat[i], q[0], q[1], q[2], q[3]);
+}
+
+// =================================================================================================
+// Global step, part 1 (reference arap.h:393-414 + the residual of L p' = b at the current p').
+//   rhs_i = sum_j (w_ij/2) (R_i + R_j) (p_i - p_j)                     (arap.h:406-413)
+//   r_i   = rhs_i - sum_j w_ij (p'_i - p'_j)      for free i; 0 for constrained i.
+// The second sum runs over ALL neighbours with constrained p'_j = their targets, which is exactly
+// bFixed (arap.h:327) moved back to the left-hand side, so no separate bFixed array is read.
+// Also starts the CG: x = 0, d = z = r / L_ii, rho = r.z, and the reference norm |rhs|^2.
+// =================================================================================================
+struct CgScalars {
+    double rho[3];       // r.z per coordinate
+    double alpha[3];
+    double beta[3];
+    double rr;           // |r|^2 over the three coordinates
+    double ref2;         // |rhs|^2 over the three coordinates
+    double tol2;         // tolerance^2
+    int converged;
+    int iterations;
+    int pad[2];
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                              const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                              const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
+                                                              const double *__restrict__ inv_diag, Vec3d *__restrict__ r_out,
+                                                              Vec3d *__restrict__ d_out, Vec3d *__restrict__ x_out,
+                                                              double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                              CgScalars *__restrict__ cg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[5] = {0, 0, 0, 0, 0};   // rho x,y,z ; rr ; ref2
+    if (i < n) {
+        const Vec4T<S> pi = load4<S>(&rest4[i]);
+        Vec3d r = {0, 0, 0}, z = {0, 0, 0};
+        if (pi.w != S(0)) {
+            const Vec4T<S> ci = load4<S>(&cur4[i]);
+            const Vec4T<S> qi = load4<S>(&quat[i]);
+            double rot_j[3] = {0, 0, 0};     // sum_j (w/2) R_j e_ij
+            double se[3] = {0, 0, 0};        // sum_j (w/2) e_ij
+            double lap[3] = {0, 0, 0};       // sum_j w (p'_i - p'_j)
+            const int k0 = rowptr[i], k1 = rowptr[i + 1];
+            for (int k = k0; k < k1; ++k) {
+                const int j = __ldg(&colidx[k]);
+                const S w = __ldg(&weight[k]);
+                const Vec4T<S> pj = load4<S>(&rest4[j]);
+                const Vec4T<S> cj = load4<S>(&cur4[j]);
+                const Vec4T<S> qj = load4<S>(&quat[j]);
+                const S hw = S(0.5) * w;
+                const S ex = hw * (pi.x - pj.x), ey = hw * (pi.y - pj.y), ez = hw * (pi.z - pj.z);
+                S rj[9];
+                quat_to_matrix<S>(qj.x, qj.y, qj.z, qj.w, rj);     // quat stored as (w,x,y,z) in (.x,.y,.z,.w)
+                rot_j[0] += (double)(rj[0] * ex + rj[1] * ey + rj[2] * ez);
+                rot_j[1] += (double)(rj[3] * ex + rj[4] * ey + rj[5] * ez);
+                rot_j[2] += (double)(rj[6] * ex + rj[7] * ey + rj[8] * ez);
+                se[0] += (double)ex; se[1] += (double)ey; se[2] += (double)ez;
+                lap[0] += (double)w * ((double)ci.x - (double)cj.x);
+                lap[1] += (double)w * ((double)ci.y - (double)cj.y);
+                lap[2] += (double)w * ((double)ci.z - (double)cj.z);
+            }
+            double ri[9];
+            quat_to_matrix<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, ri);
+            const double rhs0 = rot_j[0] + ri[0] * se[0] + ri[1] * se[1] + ri[2] * se[2];
+            const double rhs1 = rot_j[1] + ri[3] * se[0] + ri[4] * se[1] + ri[5] * se[2];
+            const double rhs2 = rot_j[2] + ri[6] * se[0] + ri[7] * se[1] + ri[8] * se[2];
+            r.x = rhs0 - lap[0]; r.y = rhs1 - lap[1]; r.z = rhs2 - lap[2];
+            const double idg = inv_diag[i];
+            z.x = r.x * idg; z.y = r.y * idg; z.z = r.z * idg;
+            red[0] = r.x * z.x; red[1] = r.y * z.y; red[2] = r.z * z.z;
+            red[3] = r.x * r.x + r.y * r.y + r.z * r.z;
+            red[4] = rhs0 * rhs0 + rhs1 * rhs1 + rhs2 * rhs2;
+        }
+        r_out[i] = r;
+        d_out[i] = z;
+        x_out[i] = Vec3d{0, 0, 0};
+    }
+    double total[5];
+    if (grid_sum_last_block<5>(red, partials, counter, total)) {
+        cg->rho[0] = total[0]; cg->rho[1] = total[1]; cg->rho[2] = total[2];
+        cg->rr = total[3];
+        cg->ref2 = total[4];
+        cg->iterations = 0;
+        cg->converged = (total[3] <= cg->tol2 * total[4]) ? 1 : 0;
+    }
+}
+
+// =================================================================================================
+// Global step, part 2: Jacobi-preconditioned CG on L (free x free), three right-hand sides at once,
+// matrix-free on the one-ring CSR: (L d)_i = sum_j w_ij (d_i - d_j) for free i (d_j = 0 on constrained j).
+// Replaces SimplicialLDLT::solve (reference arap.h:418-421).
+// =================================================================================================
+template <typename S>
+__global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                         const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                         const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
+                                                         double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                         CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[3] = {0, 0, 0};
+    if (i < n) {
+        Vec3d out = {0, 0, 0};
+        if (rest4[i].w != S(0)) {
+            const Vec3d di = d[i];
+            const int k0 = rowptr[i], k1 = rowptr[i + 1];
+            for (int k = k0; k < k1; ++k) {
+                const int j = __ldg(&colidx[k]);
+                const double w = (double)__ldg(&weight[k]);
+                const Vec3d dj = d[j];
+                out.x += w * (di.x - dj.x); out.y += w * (di.y - dj.y); out.z += w * (di.z - dj.z);
+            }
+            red[0] = di.x * out.x; red[1] = di.y * out.y; red[2] = di.z * out.z;
+        }
+        ad[i] = out;
+    }
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cg->alpha[c] = (total[c] > 0.0) ? cg->rho[c] / total[c] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *__restrict__ inv_diag, const Vec3d *__restrict__ d,
+                                                           const Vec3d *__restrict__ ad, Vec3d *__restrict__ x, Vec3d *__restrict__ r,
+                                                           double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                           CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[4] = {0, 0, 0, 0};
+    if (i < n) {
+        const double a0 = cg->alpha[0], a1 = cg->alpha[1], a2 = cg->alpha[2];
+        const Vec3d di = d[i], adi = ad[i];
+        Vec3d xi = x[i], ri = r[i];
+        xi.x += a0 * di.x; xi.y += a1 * di.y; xi.z += a2 * di.z;
+        ri.x -= a0 * adi.x; ri.y -= a1 * adi.y; ri.z -= a2 * adi.z;
+        x[i] = xi; r[i] = ri;
+        const double idg = inv_diag[i];
+        red[0] = ri.x * ri.x * idg; red[1] = ri.y * ri.y * idg; red[2] = ri.z * ri.z * idg;
+        red[3] = ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
+    }
+    double total[4];
+    if (grid_sum_last_block<4>(red, partials, counter, total)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
+            cg->rho[c] = total[c];
+        }
+        cg->rr = total[3];
+        cg->iterations += 1;
+        if (total[3] <= cg->tol2 * cg->ref2) cg->converged = 1;
+    }
+}
+
+// d = z + beta d. Launched after cg_update; skipped (like everything else) once converged.
+__global__ void __launch_bounds__(kBlock) cg_direction_kernel(int n, const double *__restrict__ inv_diag, const Vec3d *__restrict__ r,
+                                                              Vec3d *__restrict__ d, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double idg = inv_diag[i];
+    const Vec3d ri = r[i];
+    Vec3d di = d[i];
+    di.x = ri.x * idg + cg->beta[0] * di.x;
+    di.y = ri.y * idg + cg->beta[1] * di.y;
+    di.z = ri.z * idg + cg->beta[2] * di.z;
+    d[i] = di;
+}
+
+// p' += x on the free vertices (the scatter of arap.h:423-428); constrained vertices keep their targets.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) apply_update_kernel(int n, const Vec4T<S> *__restrict__ rest4, const Vec3d *__restrict__ x,
+                                                              Vec4T<S> *__restrict__ cur4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (rest4[i].w == S(0)) return;
+    const Vec4T<S> c = cur4[i];
+    const Vec3d xi = x[i];
+    store4<S>(&cur4[i], (S)((double)c.x + xi.x), (S)((double)c.y + xi.y), (S)((double)c.z + xi.z), c.w);
+}
+
+// =================================================================================================
+// ARAP energy (not in the reference): E = sum_i sum_j w_ij |(p'_i-p'_j) - R_i (p_i-p_j)|^2, fp64.
+// =================================================================================================
+template <typename S>
+__global__ void __launch_bounds__(kBlock) energy_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                        const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                        const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
+                                                        double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                        double *__restrict__ energy_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[1] = {0};
+    if (i < n) {
+        const Vec4T<S> pi = load4<S>(&rest4[i]);
+        const Vec4T<S> ci = load4<S>(&cur4[i]);
+        const Vec4T<S> qi = load4<S>(&quat[i]);
+        double ri[9];
+        quat_to_matrix<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, ri);
+        double e = 0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            const Vec4T<S> pj = load4<S>(&rest4[j]);
+            const Vec4T<S> cj = load4<S>(&cur4[j]);
+            const double ex = (double)pi.x - (double)pj.x, ey = (double)pi.y - (double)pj.y, ez = (double)pi.z - (double)pj.z;
+            const double dx = (double)ci.x - (double)cj.x - (ri[0] * ex + ri[1] * ey + ri[2] * ez);
+            const double dy = (double)ci.y - (double)cj.y - (ri[3] * ex + ri[4] * ey + ri[5] * ez);
+            const double dz = (double)ci.z - (double)cj.z - (ri[6] * ex + ri[7] * ey + ri[8] * ez);
+            e += (double)weight[k] * (dx * dx + dy * dy + dz * dz);
+        }
+        red[0] = e;
+    }
+    double total[1];
+    if (grid_sum_last_block<1>(red, partials, counter, total)) *energy_out = total[0];
+}
+
+// ---- readout helpers ----------------------------------------------------------------------------
+template <typename S, typename T>
+__global__ void __launch_bounds__(kBlock) export_positions_kernel(int n, const Vec4T<S> *__restrict__ cur4, T *__restrict__ out_xyz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec4T<S> c = cur4[i];
+    out_xyz[3 * (size_t)i] = (T)c.x; out_xyz[3 * (size_t)i + 1] = (T)c.y; out_xyz[3 * (size_t)i + 2] = (T)c.z;
+}
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock) export_rotations_kernel(int n, const Vec4T<S> *__restrict__ quat, S *__restrict__ rot9) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec4T<S> q = quat[i];
+    S r[9];
+    quat_to_matrix<S>(q.x, q.y, q.z, q.w, r);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rot9[9 * (size_t)i + k] = r[k];
+}
+
+}  // namespace arap

@@ -255,11 +255,12 @@ static void computeCotanWeights(Oracle *o) {
     for (int f = 0; f < o->nF; ++f) {
         const int *vids = o->faces + 3 * (size_t)f;
         const REAL *v0 = o->p + 3 * (size_t)vids[0], *v1 = o->p + 3 * (size_t)vids[1], *v2 = o->p + 3 * (size_t)vids[2];
-        REAL l0 = 0, l1 = 0, l2 = 0;
-        for (int d = 0; d < 3; ++d) {
-            REAL a = v1[d] - v0[d], b = v2[d] - v1[d], c = v0[d] - v2[d];
-            l0 += a * a; l1 += b * b; l2 += c * c;
-        }
+        /* squaredNorm() of a fixed-size 3-vector: Eigen's unrolled reduction is x^2 + (y^2 + z^2) */
+        REAL ea[3], eb[3], ec[3];
+        for (int d = 0; d < 3; ++d) { ea[d] = v1[d] - v0[d]; eb[d] = v2[d] - v1[d]; ec[d] = v0[d] - v2[d]; }
+        REAL l0 = ea[0] * ea[0] + (ea[1] * ea[1] + ea[2] * ea[2]);
+        REAL l1 = eb[0] * eb[0] + (eb[1] * eb[1] + eb[2] * eb[2]);
+        REAL l2 = ec[0] * ec[0] + (ec[1] * ec[1] + ec[2] * ec[2]);
         l0 = rmax((REAL)1e-8, l0); l1 = rmax((REAL)1e-8, l1); l2 = rmax((REAL)1e-8, l2);      /* :199-201 */
         l0 = (REAL)sqrt((double)l0); l1 = (REAL)sqrt((double)l1); l2 = (REAL)sqrt((double)l2); /* :203-205 */
         const REAL semip = (REAL)0.5 * (l0 + l1 + l2);                                         /* :207 */
@@ -270,10 +271,10 @@ static void computeCotanWeights(Oracle *o) {
         REAL cot1 = (l0 * l0 - l1 * l1 + l2 * l2) * denom;
         REAL cot2 = (l0 * l0 + l1 * l1 - l2 * l2) * denom;
         cot0 = rmax((REAL)1e-10, cot0); cot1 = rmax((REAL)1e-10, cot1); cot2 = rmax((REAL)1e-10, cot2); /* :216-218 */
-        const int ea[3] = {vids[0], vids[1], vids[2]}, eb[3] = {vids[1], vids[2], vids[0]};    /* :220-222 */
+        const int va[3] = {vids[0], vids[1], vids[2]}, vb[3] = {vids[1], vids[2], vids[0]};    /* :220-222 */
         const REAL cw[3] = {cot0 * (REAL)0.5, cot1 * (REAL)0.5, cot2 * (REAL)0.5};
         for (int k = 0; k < 3; ++k) {
-            int lo = ea[k] > eb[k] ? eb[k] : ea[k], hi = ea[k] > eb[k] ? ea[k] : eb[k];
+            int lo = va[k] > vb[k] ? vb[k] : va[k], hi = va[k] > vb[k] ? va[k] : vb[k];
             ti[6 * (long)f + k] = lo; tj[6 * (long)f + k] = hi; tv[6 * (long)f + k] = cw[k];              /* :225-227 */
             ti[6 * (long)f + 3 + k] = hi; tj[6 * (long)f + 3 + k] = lo; tv[6 * (long)f + 3 + k] = cw[k];  /* :230-232 */
         }

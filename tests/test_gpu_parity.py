@@ -1,0 +1,228 @@
+"""GPU parity tests (pytest -m gpu): the CUDA engine, called through the C ABI (ctypes), against
+the CPU oracle on the same inputs. Tolerances are BASELINE.json's: max vertex displacement
+<= 1e-5 x bounding-box diagonal, ARAP energy <= 1e-6 relative; CSR indices bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import bbox_diag
+from oracle import oracle as O
+from mesh_deform_b200 import meshgen as G
+from mesh_deform_b200.capi import AsRigidAsPossibleDeformation as ARAP
+from mesh_deform_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5      # x bbox diagonal (north_star)
+E_TOL = 1e-6        # relative (north_star)
+
+
+def constrain(a, idx, tgt):
+    for i, t in zip(idx, tgt):
+        a.setConstraint(int(i), t)
+
+
+def test_cotan_weights_reference_test():
+    """reference tests/test_cotan.cpp:20-54 against the engine (float precision like the reference)."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    F = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    arap = ARAP(P, F)                       # PrecisionType defaults to the mesh scalar (float)
+    assert arap.deform(0) is True
+    assert arap.dirty                       # unconstrained: early return, stays dirty (arap.h:113-114)
+    rp, ci, w = arap.cotanWeights()
+    dense = np.zeros((4, 4), np.float32)
+    for r in range(4):
+        dense[r, ci[rp[r]:rp[r + 1]]] = w[rp[r]:rp[r + 1]]
+    expected = np.array([[0, .5, 0, .5], [.5, 0, .5, 0], [0, .5, 0, .5], [.5, 0, .5, 0]], np.float32)
+    assert np.linalg.norm(dense - expected) <= 1e-4 * min(np.linalg.norm(dense), np.linalg.norm(expected))
+    assert rp.tolist() == [0, 3, 5, 8, 10] and ci.tolist() == [1, 2, 3, 0, 2, 0, 1, 3, 0, 2]
+    assert np.array_equal(P, np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))   # no write-back
+
+
+@pytest.mark.parametrize("prec", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["bar", "sphere", "plane"])
+def test_csr_bit_exact(name, prec, meshes, golden):
+    P, F = meshes[name]
+    mesh = P.astype(prec)
+    a = ARAP(mesh, F, prec)
+    constrain(a, golden[name + "_idx"], golden[name + "_tgt"])
+    assert a.deform(0)
+    rp, ci, w = a.cotanWeights()
+    o = O.ArapOracle(P.astype(prec), F, prec)
+    o.deform(0)
+    orp, oci, ow = o.cotanWeights()
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci)       # indices: bit-exact
+    assert np.array_equal(w, ow)                                      # weights: bit-exact too (same rounding sequence)
+    if prec == np.float64:
+        assert np.array_equal(rp, golden[name + "_rowptr"]) and np.array_equal(ci, golden[name + "_colidx"])
+        assert np.array_equal(w, golden[name + "_w"])
+    fm, nfree = a.freeIdxMap()
+    o2 = O.ArapOracle(P.astype(prec), F, prec)
+    constrain(o2, golden[name + "_idx"], golden[name + "_tgt"])
+    o2.deform(0)
+    assert nfree == o2.nFree and np.array_equal(fm, o2.freeIdxMap())
+
+
+@pytest.mark.parametrize("name", ["bar", "sphere", "plane"])
+def test_deform_matches_golden_fp64(name, meshes, golden):
+    P, F = meshes[name]
+    iters = int(golden[name + "_iters"])
+    mesh = P.copy()
+    a = ARAP(mesh, F, np.float64)
+    a.setConstraints(golden[name + "_idx"], golden[name + "_tgt"])
+    energies = []
+    for _ in range(iters):
+        assert a.deform(1)
+        energies.append(a.energy())
+    diag = bbox_diag(P)
+    assert np.abs(mesh - golden[name + "_positions"]).max() <= POS_TOL * diag
+    assert np.allclose(energies, golden[name + "_energies"], rtol=E_TOL)
+    # much tighter in practice: report
+    print(name, "max dp / diag", np.abs(mesh - golden[name + "_positions"]).max() / diag,
+          "rel dE", abs(energies[-1] - golden[name + "_energies"][-1]) / golden[name + "_energies"][-1], a.solver_stats())
+    assert np.abs(a.rotations() - golden[name + "_rotations"]).max() < 1e-6
+
+
+def test_first_local_step_rotations_match_oracle(meshes, golden):
+    """R_i after one iteration, vertex by vertex (local step arap.h:354-384)."""
+    P, F = meshes["bar"]
+    mesh, omesh = P.copy(), P.copy()
+    a, o = ARAP(mesh, F, np.float64), O.ArapOracle(omesh, F, np.float64)
+    constrain(a, golden["bar_idx"], golden["bar_tgt"])
+    constrain(o, golden["bar_idx"], golden["bar_tgt"])
+    a.deform(1)
+    o.deform(1)
+    R, Ro = a.rotations(), o.rotations()
+    assert np.abs(R - Ro).max() < 1e-9
+    assert np.abs(np.einsum("nij,nkj->nik", R, R) - np.eye(3)).max() < 1e-12
+    assert np.abs(mesh - omesh).max() <= 1e-8 * bbox_diag(P)
+
+
+@pytest.mark.parametrize("name", ["bar", "sphere"])
+def test_deform_float_precision(name, meshes, golden):
+    """PrecisionType = float (the sphere demo's default, deform_sphere.cpp:55): within the float
+    reference's own error of the fp64 oracle."""
+    P, F = meshes[name]
+    iters = int(golden[name + "_iters"])
+    mesh = P.astype(np.float32)
+    a = ARAP(mesh, F, np.float32)
+    a.setConstraints(golden[name + "_idx"], golden[name + "_tgt"])
+    assert a.deform(iters)
+    omesh = P.astype(np.float32)
+    o = O.ArapOracle(omesh, F, np.float32)
+    constrain(o, golden[name + "_idx"], golden[name + "_tgt"])
+    o.deform(iters)
+    diag = bbox_diag(P)
+    err_gpu = np.abs(mesh - golden[name + "_positions"]).max() / diag
+    err_ref = np.abs(omesh - golden[name + "_positions"]).max() / diag
+    print(name, "float: gpu err", err_gpu, "float-oracle err", err_ref)
+    assert err_gpu <= max(2 * err_ref, 2e-5)
+
+
+def test_dirty_protocol_and_warm_continuation(meshes):
+    """SURVEY.md section 8b semantics (1)-(6)."""
+    P, F = meshes["sphere"]
+    mesh = P.astype(np.float32)                  # mesh scalar float, PrecisionType double (deform_bar.cpp:38)
+    a = ARAP(mesh, F, np.float64)
+    a.setConstraint(37, P[37])
+    a.setConstraint(32, P[32] + [0, 0, 0.5])
+    assert a.dirty and a.deform(0) and not a.dirty
+    assert np.allclose(mesh[32], (P[32] + [0, 0, 0.5]).astype(np.float32))     # (3) deform(0) snaps handles
+    assert np.array_equal(mesh[0], P[0].astype(np.float32))
+    m2 = P.astype(np.float32)
+    b = ARAP(m2, F, np.float64)
+    b.setConstraint(37, P[37])
+    b.setConstraint(32, P[32] + [0, 0, 0.5])
+    a.deform(2); a.deform(3)                                                  # (4) warm continuation
+    b.deform(5)
+    assert np.abs(mesh - m2).max() <= 1e-6
+    # (1) a constraint change re-reads the rest pose from the deformed mesh
+    omesh = mesh.copy()
+    o = O.ArapOracle(omesh, F, np.float64)
+    o.setConstraint(37, P[37]); o.setConstraint(32, P[32] + [0, 0, 0.6])
+    a.setConstraint(32, P[32] + [0, 0, 0.6])
+    assert a.dirty
+    a.deform(3); o.deform(3)
+    assert np.abs(mesh - omesh).max() <= POS_TOL * bbox_diag(P)
+    assert abs(a.energy() - o.energy()) <= 1e-5 * o.energy() + 1e-12
+
+
+def test_rigid_motion_of_all_constraints_gives_rigid_result(meshes):
+    P, F = meshes["sphere"]
+    R = G.rot_z(0.7) @ G.rot_x(-0.4)
+    t = np.array([0.3, -0.2, 0.5])
+    idx = np.arange(0, len(P), 7)
+    mesh = P.copy()
+    a = ARAP(mesh, F, np.float64)
+    a.setConstraints(idx, P[idx] @ R.T + t)
+    assert a.deform(30)
+    assert np.abs(mesh - (P @ R.T + t)).max() < 1e-6
+    assert a.energy() < 1e-10
+
+
+def test_energy_monotone_and_csr_properties():
+    P, F = G.icosphere(24)                      # 5762 vertices
+    idx, tgt = G.cap_constraints(P)
+    mesh = P.copy()
+    a = ARAP(mesh, F, np.float64)
+    a.setConstraints(idx, tgt)
+    prev = None
+    for _ in range(6):
+        assert a.deform(1)
+        e = a.energy()
+        # energy after each global step, measured with the rotations of that iteration's local step, is non-increasing
+        if prev is not None:
+            assert e <= prev * (1 + 1e-9)
+        prev = e
+    rp, ci, w = a.cotanWeights()
+    import scipy.sparse as sp
+    W = sp.csr_matrix((w, ci, rp), shape=(len(P),) * 2)
+    assert (abs(W - W.T)).max() == 0 and W.diagonal().max() == 0
+    assert all(np.all(np.diff(ci[rp[r]:rp[r + 1]]) > 0) for r in range(0, len(P), 37))
+
+
+@pytest.mark.parametrize("nu,iters", [(64, 4)])
+def test_midsize_icosphere_parity(nu, iters):
+    """Config 3's construction at a size the oracle finishes in seconds (40,962 vertices)."""
+    P, F = G.icosphere(nu)
+    idx, tgt = G.cap_constraints(P)
+    mesh, omesh = P.copy(), P.copy()
+    a, o = ARAP(mesh, F, np.float64), O.ArapOracle(omesh, F, np.float64)
+    a.setConstraints(idx, tgt)
+    constrain(o, idx, tgt)
+    assert a.deform(iters) and o.deform(iters)
+    diag = bbox_diag(P)
+    err = np.abs(mesh - omesh).max() / diag
+    de = abs(a.energy() - o.energy()) / o.energy()
+    print("ico", nu, "err/diag", err, "rel dE", de, a.solver_stats())
+    assert err <= POS_TOL and de <= E_TOL
+
+
+def test_edge_cases():
+    # empty constraint set on a real mesh: true, stays dirty, mesh untouched, weights available
+    P, F = G.icosphere(4)
+    mesh = P.copy()
+    a = ARAP(mesh, F, np.float64)
+    assert a.deform(5) and a.dirty and np.array_equal(mesh, P)
+    assert a.cotanWeights()[1].size == 6 * (len(P) - 2)
+    # every vertex constrained: nothing free, result = targets
+    b = ARAP(mesh, F, np.float64)
+    b.setConstraints(np.arange(len(P)), P * 1.5)
+    assert b.deform(3) and np.allclose(mesh, P * 1.5)
+    # degenerate (zero-area) face and an isolated vertex: clamps of arap.h:199-218 keep everything finite
+    P2 = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0], [5, 5, 5]], np.float64)
+    F2 = np.array([[0, 1, 2], [0, 1, 3]], np.int32)
+    m2 = P2.copy()
+    c = ARAP(m2, F2, np.float64)
+    c.setConstraint(0, P2[0]); c.setConstraint(3, P2[3] + [0, 0, 0.2])
+    o2 = P2.copy()
+    o = O.ArapOracle(o2, F2, np.float64)
+    o.setConstraint(0, P2[0]); o.setConstraint(3, P2[3] + [0, 0, 0.2])
+    assert np.array_equal(c.prepare() >= 0, True)
+    rp, ci, w = c.cotanWeights()
+    o.deform(0)
+    orp, oci, ow = o.cotanWeights()
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(w, ow)
+    assert np.isfinite(w).all()
+    # invalid arguments are reported, not UB
+    with pytest.raises(capi.ArapError):
+        a.setConstraint(10 ** 6, [0, 0, 0])
