@@ -112,6 +112,11 @@ def algorithmic_bytes(V, nF, nnz, s):
         "cg_update": nF * (6 * 24 + 8),
         "cg_direction": nF * (3 * 24 + 8),
         "apply_update": nF * (24 + 2 * 3 * s),
+        # multigrid-preconditioned path, fine level (coarse levels are < 20 % of the work and launch-bound)
+        "mg_fine_residual": nF * ((s + 4) * d + 4 + 8 + 3 * 24),
+        "mg_fine_postsmooth": nF * ((s + 4) * d + 4 + 8 + 8 + 3 * 24),
+        "cg_update_mg": nF * (7 * 24 + 8),
+        "cg_direction_mg": nF * (3 * 24),
     }
 
 
@@ -205,6 +210,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=2, help="oracle iterations in the cpu_baseline sample")
     ap.add_argument("--cg-tol", type=float, default=0.0)
+    ap.add_argument("--solver", default="auto", choices=["auto", "jacobi", "mg"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -224,7 +230,7 @@ def main():
     V = P.shape[0]
     peak_gbs, peak_src, peaks = load_peaks()
 
-    opts = {"device": local_rank}
+    opts = {"device": local_rank, "solver": {"auto": 0, "jacobi": 1, "mg": 2}[args.solver]}
     if args.cg_tol > 0:
         opts["cg_tolerance"] = args.cg_tol
 
@@ -349,7 +355,9 @@ def main():
         "config": {"workload": f"icosphere nu={args.nu} V={V} 5% anchors + 1% handles (BASELINE.json configs[2])",
                    "vertices": int(V), "faces": int(F.shape[0]), "nnz": nnz, "n_free": int(n_free),
                    "sharding": "one independent deformation per GPU, no collective" if world > 1 else "single GPU",
-                   "solver": "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "cg_tolerance": float(arap_tolerance(args)),
+                   "solver": ("warm-started CG, smoothed-aggregation multigrid V(1,1) preconditioner, %d levels, operator complexity %.2f"
+                              % (stats["mg_levels"], stats["mg_operator_complexity"])) if stats["mg_levels"] else
+                   "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "cg_tolerance": float(arap_tolerance(args)),
                    "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
                 "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",
@@ -362,7 +370,7 @@ def main():
         "kernels": kernels,
         "cg": {"iterations_per_arap_iteration": stats["cg_iterations_total"] / max(1, stats["global_steps"]),
                "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
-        "prepare_ms": prepare_ms,
+        "prepare_ms": prepare_ms, "prepare_host_setup_ms": stats["setup_host_ms"],
         "frame": {"protocol": "setConstraints(all) + deform(5) with the dirty rebuild (reference demo loop)", "ms": frame_ms},
         "profiled_pass_ms_per_step": ms_profiled / args.steps,
         "cpu_baseline": cpu_baseline,

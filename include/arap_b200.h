@@ -50,7 +50,7 @@ enum {
 enum {
     ARAP_SOLVER_AUTO = 0,
     ARAP_SOLVER_PCG_JACOBI = 1,   /* warm-started Jacobi-preconditioned CG, matrix-free on the one-ring CSR */
-    ARAP_SOLVER_PCG_MG = 2        /* CG preconditioned by an aggregation multigrid V-cycle */
+    ARAP_SOLVER_PCG_MG = 2        /* CG preconditioned by a smoothed-aggregation multigrid V-cycle (AUTO picks this) */
 };
 
 typedef struct arap_handle arap_handle;
@@ -115,7 +115,9 @@ typedef struct arap_solver_stats {
     int32_t last_cg_iterations;
     double last_relative_residual; /* |r| / |rhs| at the end of the last global step */
     int32_t last_converged;
-    int32_t reserved;
+    int32_t mg_levels;             /* 0 when the Jacobi preconditioner is in use */
+    double mg_operator_complexity;
+    double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 
@@ -123,7 +125,10 @@ int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 enum {
     ARAP_K_WEIGHTS_COUNT = 0, ARAP_K_WEIGHTS_FILL, ARAP_K_ROW_SORT_MERGE, ARAP_K_CSR_COMPACT, ARAP_K_SCAN,
     ARAP_K_INIT_STATE, ARAP_K_DIAGONAL, ARAP_K_LOCAL_STEP, ARAP_K_RHS_RESIDUAL, ARAP_K_CG_SPMV,
-    ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC, ARAP_K_COUNT_MAX = 32
+    ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC,
+    ARAP_K_MG_FINE_RESIDUAL, ARAP_K_MG_FINE_POSTSMOOTH, ARAP_K_MG_CSR_RESIDUAL, ARAP_K_MG_RESTRICT, ARAP_K_MG_PROLONG,
+    ARAP_K_MG_CSR_POSTSMOOTH, ARAP_K_MG_DENSE_SOLVE, ARAP_K_CG_UPDATE_MG, ARAP_K_CG_DIRECTION_MG, ARAP_K_CG_DOT,
+    ARAP_K_COUNT_MAX = 32
 };
 typedef struct arap_profile {
     int64_t launches[ARAP_K_COUNT_MAX];

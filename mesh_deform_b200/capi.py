@@ -43,7 +43,8 @@ class Options(C.Structure):
 
 class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
-                ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("reserved", C.c_int32)]
+                ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
+                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double)]
 
 
 class Profile(C.Structure):

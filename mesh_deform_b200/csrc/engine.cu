@@ -7,11 +7,15 @@
 //   get_positions() = the write-back (:133-135).
 #include "../../include/arap_b200.h"
 #include "kernels.cuh"
+#include "mg_kernels.cuh"
+#include "mg_setup.h"
 
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <chrono>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -21,7 +25,9 @@ namespace arap {
 static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "weights_count", "weights_fill", "row_sort_merge", "csr_compact", "scan",
     "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
-    "cg_update", "cg_direction", "apply_update", "energy", "misc"};
+    "cg_update", "cg_direction", "apply_update", "energy", "misc",
+    "mg_fine_residual", "mg_fine_postsmooth", "mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add",
+    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot"};
 
 static thread_local std::string g_create_error;
 
@@ -129,6 +135,23 @@ public:
         end_launch();                                                                \
     } while (0)
 
+// One multigrid level on the device. Level 0 keeps no explicit A (matrix-free on the one-ring CSR).
+struct MgLevelDev {
+    int n = 0;
+    double omega = 2.0 / 3.0;
+    DeviceBuffer<int> a_rowptr, a_colidx, p_rowptr, p_colidx, r_rowptr, r_colidx;
+    DeviceBuffer<double> a_val, p_val, r_val, inv_diag;
+    DeviceBuffer<Vec3d> b, x, x2, r;
+    Vec3d *xp = nullptr, *x2p = nullptr;      // ping-pong views of x / x2
+};
+
+template <typename T>
+static cudaError_t upload_vector(DeviceBuffer<T> &dst, const std::vector<T> &src, cudaStream_t stream) {
+    cudaError_t e = dst.ensure(src.size());
+    if (e != cudaSuccess || src.empty()) return e;
+    return cudaMemcpyAsync(dst.ptr, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+}
+
 template <typename S>
 class Engine : public EngineBase {
 public:
@@ -152,6 +175,11 @@ public:
     DeviceBuffer<S> raw_val;
     DeviceBuffer<unsigned> raw_tag;
     DeviceBuffer<unsigned char> staging;           // uploads / downloads in a foreign scalar type
+
+    std::vector<std::unique_ptr<MgLevelDev>> mg;   // multigrid hierarchy (empty -> Jacobi preconditioner)
+    DeviceBuffer<double> mg_coarse_inv;
+    bool mg_dense = false;
+    bool use_mg = false;
 
     int nnz = 0;
     int n_free = 0;
@@ -322,6 +350,8 @@ public:
         ARAP_CUDA(cg_d.ensure((size_t)V));
         ARAP_CUDA(cg_ad.ensure((size_t)V));
         ARAP_CUDA(cg_x.ensure((size_t)V));
+        use_mg = (opt.solver != ARAP_SOLVER_PCG_JACOBI);
+        if (use_mg) { int rc = setup_multigrid(); if (rc) return rc; }
         CgScalars init;
         std::memset(&init, 0, sizeof(init));
         const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : 1e-10;
@@ -334,12 +364,144 @@ public:
         return ARAP_OK;
     }
 
+    // ---- multigrid setup: host analysis of L (the reference's _solver.compute(_L), arap.h:337) ------------
+    int setup_multigrid() {
+        const int V = n_vertices;
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<int> h_rowptr((size_t)V + 1), h_colidx((size_t)nnz);
+        std::vector<S> h_w((size_t)nnz);
+        std::vector<unsigned char> h_con((size_t)V);
+        ARAP_CUDA(cudaMemcpyAsync(h_rowptr.data(), rowptr.ptr, sizeof(int) * ((size_t)V + 1), cudaMemcpyDeviceToHost, stream));
+        if (nnz > 0) {
+            ARAP_CUDA(cudaMemcpyAsync(h_colidx.data(), colidx.ptr, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h_w.data(), weight.ptr, sizeof(S) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+        }
+        if (V > 0) ARAP_CUDA(cudaMemcpyAsync(h_con.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        MgHierarchyHost H;
+        MgSetupOptions mo;
+        mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H);
+        mg.clear();
+        for (size_t l = 0; l < H.levels.size(); ++l) {
+            const MgLevelHost &hl = H.levels[l];
+            std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+            d->n = hl.A.n_rows;
+            d->omega = hl.omega;
+            if (l > 0) {
+                ARAP_CUDA(upload_vector(d->a_rowptr, hl.A.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->a_colidx, hl.A.colidx, stream));
+                ARAP_CUDA(upload_vector(d->a_val, hl.A.val, stream));
+                ARAP_CUDA(d->b.ensure((size_t)d->n));
+            }
+            ARAP_CUDA(upload_vector(d->inv_diag, hl.inv_diag, stream));
+            if (l + 1 < H.levels.size()) {
+                ARAP_CUDA(upload_vector(d->p_rowptr, hl.P.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->p_colidx, hl.P.colidx, stream));
+                ARAP_CUDA(upload_vector(d->p_val, hl.P.val, stream));
+                ARAP_CUDA(upload_vector(d->r_rowptr, hl.R.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->r_colidx, hl.R.colidx, stream));
+                ARAP_CUDA(upload_vector(d->r_val, hl.R.val, stream));
+                ARAP_CUDA(d->r.ensure((size_t)d->n));
+            }
+            ARAP_CUDA(d->x.ensure((size_t)d->n));
+            ARAP_CUDA(d->x2.ensure((size_t)d->n));
+            d->xp = d->x.ptr;
+            d->x2p = d->x2.ptr;
+            mg.push_back(std::move(d));
+        }
+        mg_dense = !H.coarse_inv.empty();
+        if (mg_dense) ARAP_CUDA(upload_vector(mg_coarse_inv, H.coarse_inv, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
+        stats.mg_levels = (int)mg.size();
+        stats.mg_operator_complexity = H.operator_complexity;
+        stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return ARAP_OK;
+    }
+
+    // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
+    void vcycle() {
+        const int V = n_vertices;
+        const int L = (int)mg.size();
+        MgLevelDev &m0 = *mg[0];
+        Vec3d *z = m0.x2.ptr;
+        if (L == 1) {
+            if (mg_dense) {
+                LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (V + kWarpsPerBlock - 1) / kWarpsPerBlock, V, mg_coarse_inv.ptr,
+                       cg_r.ptr, z, cg.ptr);
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+            } else {
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+            }
+            return;
+        }
+        // down
+        for (int l = 0; l + 1 < L; ++l) {
+            MgLevelDev &f = *mg[l], &c = *mg[l + 1];
+            if (l == 0)
+                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr,
+                       rest4.ptr, cg_r.ptr, f.xp, f.r.ptr, cg.ptr);
+            else
+                LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel, grid_for((size_t)f.n), f.n, f.a_rowptr.ptr, f.a_colidx.ptr,
+                       f.a_val.ptr, f.b.ptr, f.xp, f.r.ptr, cg.ptr);
+            LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel, grid_for((size_t)c.n), c.n, f.r_rowptr.ptr, f.r_colidx.ptr,
+                   f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, c.omega, c.b.ptr, c.xp, cg.ptr);
+        }
+        // coarsest
+        MgLevelDev &cl = *mg[L - 1];
+        if (mg_dense) {
+            LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
+                   cl.b.ptr, cl.xp, cg.ptr);
+        }
+        // up
+        for (int l = L - 2; l >= 0; --l) {
+            MgLevelDev &f = *mg[l], &c = *mg[l + 1];
+            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)f.n), f.n, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+                   c.xp, f.xp, cg.ptr);
+            if (l == 0) {
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr,
+                       weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.xp, z, partials.ptr, counter.ptr, cg.ptr);
+            } else {
+                LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel, grid_for((size_t)f.n), f.n, f.a_rowptr.ptr, f.a_colidx.ptr,
+                       f.a_val.ptr, f.inv_diag.ptr, f.omega, f.b.ptr, f.xp, f.x2p, cg.ptr);
+                Vec3d *t = f.xp; f.xp = f.x2p; f.x2p = t;
+            }
+        }
+    }
+
+    void cg_iteration_jacobi() {
+        const int V = n_vertices, G = grid_for((size_t)V);
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+               partials.ptr, counter.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, G, V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
+               counter.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, G, V, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+    }
+
+    void cg_iteration_mg() {
+        const int V = n_vertices, G = grid_for((size_t)V);
+        MgLevelDev &m0 = *mg[0];
+        vcycle();
+        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G, V, m0.x2.ptr, cg_d.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+               partials.ptr, counter.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, G, V, inv_diag.ptr, m0.omega, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr,
+               m0.xp, partials.ptr, counter.ptr, cg.ptr);
+    }
+
     int global_step() {
         const int V = n_vertices, G = grid_for((size_t)V);
-        LAUNCH(ARAP_K_RHS_RESIDUAL, rhs_residual_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
-               inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg_x.ptr, partials.ptr, counter.ptr, cg.ptr);
+        if (use_mg) {
+            MgLevelDev &m0 = *mg[0];
+            m0.xp = m0.x.ptr;
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+                   quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.xp, partials.ptr, counter.ptr, cg.ptr);
+        } else {
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+                   quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+        }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
-        const int check = opt.cg_check_interval > 0 ? opt.cg_check_interval : 32;
+        int check = opt.cg_check_interval > 0 ? opt.cg_check_interval : 32;
+        if (use_mg && check > 4) check = 4;
         // Batches of `check` CG iterations are enqueued one batch ahead of the convergence poll, so
         // the device never idles waiting for the host; once converged the kernels return immediately.
         int issued = 0, slot = 0;
@@ -348,11 +510,7 @@ public:
         while (!done) {
             const int batch = (max_it - issued < check) ? (max_it - issued) : check;
             for (int it = 0; it < batch; ++it) {
-                LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
-                       partials.ptr, counter.ptr, cg.ptr);
-                LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, G, V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
-                       counter.ptr, cg.ptr);
-                LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, G, V, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+                if (use_mg) cg_iteration_mg(); else cg_iteration_jacobi();
             }
             issued += batch;
             ARAP_CUDA(cudaMemcpyAsync(&cg_host[slot], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));

@@ -218,12 +218,15 @@ struct CgScalars {
     int pad[2];
 };
 
-template <typename S>
+// MG = false: Jacobi-preconditioned start (d = z = D^-1 r, rho = r.z).
+// MG = true : multigrid start (d = 0, rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
+template <typename S, bool MG>
 __global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                               const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
                                                               const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
-                                                              const double *__restrict__ inv_diag, Vec3d *__restrict__ r_out,
-                                                              Vec3d *__restrict__ d_out, Vec3d *__restrict__ x_out,
+                                                              const double *__restrict__ inv_diag, double omega0,
+                                                              Vec3d *__restrict__ r_out, Vec3d *__restrict__ d_out,
+                                                              Vec3d *__restrict__ x_out, Vec3d *__restrict__ x0_out,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,11 +272,17 @@ __global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *
             red[4] = rhs0 * rhs0 + rhs1 * rhs1 + rhs2 * rhs2;
         }
         r_out[i] = r;
-        d_out[i] = z;
         x_out[i] = Vec3d{0, 0, 0};
+        if (MG) {
+            d_out[i] = Vec3d{0, 0, 0};
+            x0_out[i] = Vec3d{omega0 * z.x, omega0 * z.y, omega0 * z.z};
+        } else {
+            d_out[i] = z;
+        }
     }
     double total[5];
     if (grid_sum_last_block<5>(red, partials, counter, total)) {
+        if (MG) { total[0] = 0; total[1] = 0; total[2] = 0; }
         cg->rho[0] = total[0]; cg->rho[1] = total[1]; cg->rho[2] = total[2];
         cg->rr = total[3];
         cg->ref2 = total[4];
@@ -346,6 +355,27 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
         cg->rr = total[3];
         cg->iterations += 1;
         if (total[3] <= cg->tol2 * cg->ref2) cg->converged = 1;
+    }
+}
+
+// rho_new = r . z (per coordinate) and beta = rho_new / rho: used when the preconditioner's last kernel cannot fuse it.
+__global__ void __launch_bounds__(kBlock) cg_dot_rho_kernel(int n, const Vec3d *__restrict__ r, const Vec3d *__restrict__ z,
+                                                            double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                            CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[3] = {0, 0, 0};
+    if (i < n) {
+        const Vec3d ri = r[i], zi = z[i];
+        red[0] = ri.x * zi.x; red[1] = ri.y * zi.y; red[2] = ri.z * zi.z;
+    }
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
+            cg->rho[c] = total[c];
+        }
     }
 }
 

@@ -1,0 +1,211 @@
+// mg_kernels.cuh -- device side of the multigrid-preconditioned CG (global step, replaces the
+// reference's SimplicialLDLT::solve, arap.h:418-421). All vectors are Vec3d (three right-hand sides
+// at once, fp64). The fine level is matrix-free on the one-ring CSR; coarse levels are explicit CSR.
+//
+// One V(1,1)-cycle, damped Jacobi smoothing, applied to b_0 = r (the CG residual):
+//   x_l = omega_l D_l^-1 b_l ; r_l = b_l - A_l x_l ; b_{l+1} = R_l r_l ; ... ; x_L = A_L^-1 b_L (dense)
+//   x_l += P_l x_{l+1} ; x_l += omega_l D_l^-1 (b_l - A_l x_l)
+// HBM-bound row-gather kernels, one thread per row.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace arap {
+
+// ---- fine level (matrix-free): (A x)_i = sum_j w_ij (x_i - x_j) on free rows ---------------------------
+template <typename S>
+__device__ __forceinline__ Vec3d fine_apply_row(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                const S *__restrict__ weight, const Vec3d *__restrict__ x) {
+    const Vec3d xi = x[i];
+    Vec3d out = {0, 0, 0};
+    const int k0 = rowptr[i], k1 = rowptr[i + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int j = __ldg(&colidx[k]);
+        const double w = (double)__ldg(&weight[k]);
+        const Vec3d xj = x[j];
+        out.x += w * (xi.x - xj.x); out.y += w * (xi.y - xj.y); out.z += w * (xi.z - xj.z);
+    }
+    return out;
+}
+
+// r0 = b - A x0 on free rows (0 elsewhere)
+template <typename S>
+__global__ void __launch_bounds__(kBlock) mg_fine_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                  const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                                  const Vec3d *__restrict__ b, const Vec3d *__restrict__ x,
+                                                                  Vec3d *__restrict__ r, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec3d out = {0, 0, 0};
+    if (rest4[i].w != S(0)) {
+        const Vec3d ax = fine_apply_row<S>(i, rowptr, colidx, weight, x);
+        const Vec3d bi = b[i];
+        out.x = bi.x - ax.x; out.y = bi.y - ax.y; out.z = bi.z - ax.z;
+    }
+    r[i] = out;
+}
+
+// z = x + omega D^-1 (b - A x) on free rows; fused rho_new = b . z (b is the CG residual) -> beta.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                    const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                                    const double *__restrict__ inv_diag, double omega,
+                                                                    const Vec3d *__restrict__ b, const Vec3d *__restrict__ x,
+                                                                    Vec3d *__restrict__ z, double *__restrict__ partials,
+                                                                    unsigned *__restrict__ counter, CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[3] = {0, 0, 0};
+    if (i < n) {
+        Vec3d out = {0, 0, 0};
+        if (rest4[i].w != S(0)) {
+            const Vec3d ax = fine_apply_row<S>(i, rowptr, colidx, weight, x);
+            const Vec3d bi = b[i], xi = x[i];
+            const double s = omega * inv_diag[i];
+            out.x = xi.x + s * (bi.x - ax.x); out.y = xi.y + s * (bi.y - ax.y); out.z = xi.z + s * (bi.z - ax.z);
+            red[0] = bi.x * out.x; red[1] = bi.y * out.y; red[2] = bi.z * out.z;
+        }
+        z[i] = out;
+    }
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
+            cg->rho[c] = total[c];
+        }
+    }
+}
+
+// ---- generic CSR levels -------------------------------------------------------------------------------
+__device__ __forceinline__ Vec3d csr_apply_row(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                               const double *__restrict__ val, const Vec3d *__restrict__ x) {
+    Vec3d out = {0, 0, 0};
+    const int k0 = rowptr[i], k1 = rowptr[i + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int j = __ldg(&colidx[k]);
+        const double a = __ldg(&val[k]);
+        const Vec3d xj = x[j];
+        out.x += a * xj.x; out.y += a * xj.y; out.z += a * xj.z;
+    }
+    return out;
+}
+
+// r = b - A x
+__global__ void __launch_bounds__(kBlock) mg_csr_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                 const double *__restrict__ val, const Vec3d *__restrict__ b,
+                                                                 const Vec3d *__restrict__ x, Vec3d *__restrict__ r,
+                                                                 const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3d ax = csr_apply_row(i, rowptr, colidx, val, x);
+    const Vec3d bi = b[i];
+    r[i] = Vec3d{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z};
+}
+
+// b_c = R r_f ; x_c = omega_c D_c^-1 b_c   (restriction fused with the coarse level's pre-smoothing from a zero guess)
+__global__ void __launch_bounds__(kBlock) mg_restrict_presmooth_kernel(int nc, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                       const double *__restrict__ val, const Vec3d *__restrict__ r_fine,
+                                                                       const double *__restrict__ inv_diag_c, double omega_c,
+                                                                       Vec3d *__restrict__ b_c, Vec3d *__restrict__ x_c,
+                                                                       const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const Vec3d bc = csr_apply_row(i, rowptr, colidx, val, r_fine);
+    b_c[i] = bc;
+    const double s = omega_c * inv_diag_c[i];
+    x_c[i] = Vec3d{s * bc.x, s * bc.y, s * bc.z};
+}
+
+// x += P x_c
+__global__ void __launch_bounds__(kBlock) mg_prolong_add_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                const double *__restrict__ val, const Vec3d *__restrict__ x_c,
+                                                                Vec3d *__restrict__ x, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (rowptr[i] == rowptr[i + 1]) return;
+    const Vec3d c = csr_apply_row(i, rowptr, colidx, val, x_c);
+    Vec3d xi = x[i];
+    xi.x += c.x; xi.y += c.y; xi.z += c.z;
+    x[i] = xi;
+}
+
+// x_out = x + omega D^-1 (b - A x)
+__global__ void __launch_bounds__(kBlock) mg_csr_postsmooth_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                   const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                                   double omega, const Vec3d *__restrict__ b, const Vec3d *__restrict__ x,
+                                                                   Vec3d *__restrict__ x_out, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3d ax = csr_apply_row(i, rowptr, colidx, val, x);
+    const Vec3d bi = b[i], xi = x[i];
+    const double s = omega * inv_diag[i];
+    x_out[i] = Vec3d{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z)};
+}
+
+// coarsest level: x = A^-1 b with the dense inverse; one warp per row.
+__global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, const double *__restrict__ inv, const Vec3d *__restrict__ b,
+                                                                Vec3d *__restrict__ x, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int c = lane; c < n; c += 32) {
+        const double a = inv[(size_t)row * n + c];
+        const Vec3d bc = b[c];
+        s0 += a * bc.x; s1 += a * bc.y; s2 += a * bc.z;
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) x[row] = Vec3d{s0, s1, s2};
+}
+
+// ---- CG pieces for a general preconditioner -------------------------------------------------------------
+// x += alpha d ; r -= alpha Ad ; x0 = omega_0 D^-1 r (the V-cycle's pre-smoothed fine iterate) ; |r|^2 -> convergence
+__global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n, const double *__restrict__ inv_diag, double omega0,
+                                                              const Vec3d *__restrict__ d, const Vec3d *__restrict__ ad,
+                                                              Vec3d *__restrict__ x, Vec3d *__restrict__ r, Vec3d *__restrict__ x0,
+                                                              double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                              CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[1] = {0};
+    if (i < n) {
+        const double a0 = cg->alpha[0], a1 = cg->alpha[1], a2 = cg->alpha[2];
+        const Vec3d di = d[i], adi = ad[i];
+        Vec3d xi = x[i], ri = r[i];
+        xi.x += a0 * di.x; xi.y += a1 * di.y; xi.z += a2 * di.z;
+        ri.x -= a0 * adi.x; ri.y -= a1 * adi.y; ri.z -= a2 * adi.z;
+        x[i] = xi; r[i] = ri;
+        const double s = omega0 * inv_diag[i];
+        x0[i] = Vec3d{s * ri.x, s * ri.y, s * ri.z};
+        red[0] = ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
+    }
+    double total[1];
+    if (grid_sum_last_block<1>(red, partials, counter, total)) {
+        cg->rr = total[0];
+        cg->iterations += 1;
+        if (total[0] <= cg->tol2 * cg->ref2) cg->converged = 1;
+    }
+}
+
+// d = z + beta d
+__global__ void __launch_bounds__(kBlock) cg_direction_mg_kernel(int n, const Vec3d *__restrict__ z, Vec3d *__restrict__ d,
+                                                                 const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3d zi = z[i];
+    Vec3d di = d[i];
+    di.x = zi.x + cg->beta[0] * di.x;
+    di.y = zi.y + cg->beta[1] * di.y;
+    di.z = zi.z + cg->beta[2] * di.z;
+    d[i] = di;
+}
+
+}  // namespace arap
