@@ -88,6 +88,7 @@ public:
     // ---- profiling -------------------------------------------------------------------------------
     struct TimedLaunch { int id; cudaEvent_t start, stop; };
     void begin_launch(int id) {
+        if (capturing) { graph_counts[id] += 1; return; }     // replayed per graph launch, see launch_cg_graph()
         profile.launches[id] += 1;
         if (!profile_events) return;
         TimedLaunch t;
@@ -98,7 +99,7 @@ public:
         pending.push_back(t);
     }
     void end_launch() {
-        if (!profile_events) return;
+        if (capturing || !profile_events) return;
         cudaEventRecord(pending.back().stop, stream);
         if (pending.size() >= 4096) collect_profile();
     }
@@ -123,6 +124,8 @@ public:
     std::string last_error;
     arap_profile profile;
     bool profile_events = false;
+    bool capturing = false;
+    int64_t graph_counts[ARAP_K_COUNT_MAX] = {0};
     std::vector<TimedLaunch> pending;
     arap_solver_stats stats;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -141,9 +144,29 @@ struct MgLevelDev {
     double omega = 2.0 / 3.0;
     DeviceBuffer<int> a_rowptr, a_colidx, p_rowptr, p_colidx, r_rowptr, r_colidx;
     DeviceBuffer<double> a_val, p_val, r_val, inv_diag;
-    DeviceBuffer<Vec3d> b, x, x2, r;
-    Vec3d *xp = nullptr, *x2p = nullptr;      // ping-pong views of x / x2
+    DeviceBuffer<Vec3d> b, x, x2, r;          // x: iterate before post-smoothing, x2: the level's result
+    int a_lanes = 1, r_lanes = 1;             // threads per row for A and R kernels
 };
+
+static inline int pick_lanes(size_t nnz, size_t rows) {
+    const double avg = rows ? (double)nnz / (double)rows : 0.0;
+    if (avg < 4) return 1;
+    if (avg < 8) return 2;
+    if (avg < 16) return 4;
+    if (avg < 32) return 8;
+    if (avg < 64) return 16;
+    return 32;
+}
+
+#define ARAP_DISPATCH_LANES(lanes, CALL)                                   \
+    switch (lanes) {                                                       \
+        case 1: { constexpr int LN = 1; CALL; } break;                     \
+        case 2: { constexpr int LN = 2; CALL; } break;                     \
+        case 4: { constexpr int LN = 4; CALL; } break;                     \
+        case 8: { constexpr int LN = 8; CALL; } break;                     \
+        case 16: { constexpr int LN = 16; CALL; } break;                   \
+        default: { constexpr int LN = 32; CALL; } break;                   \
+    }
 
 template <typename T>
 static cudaError_t upload_vector(DeviceBuffer<T> &dst, const std::vector<T> &src, cudaStream_t stream) {
@@ -180,6 +203,9 @@ public:
     DeviceBuffer<double> mg_coarse_inv;
     bool mg_dense = false;
     bool use_mg = false;
+    cudaGraph_t cg_graph = nullptr;                // one CG iteration (preconditioner included), replayed per iteration
+    cudaGraphExec_t cg_graph_exec = nullptr;
+    bool have_warm_rotations = false;              // quat[] holds the previous iteration's R_i
 
     int nnz = 0;
     int n_free = 0;
@@ -187,8 +213,16 @@ public:
     CgScalars *cg_host = nullptr;                  // pinned mirror for convergence polls
     cudaEvent_t poll_event[2] = {nullptr, nullptr};
 
+    void destroy_cg_graph() {
+        if (cg_graph_exec) cudaGraphExecDestroy(cg_graph_exec);
+        if (cg_graph) cudaGraphDestroy(cg_graph);
+        cg_graph_exec = nullptr;
+        cg_graph = nullptr;
+    }
+
     ~Engine() override {
         collect_profile();
+        destroy_cg_graph();
         if (cg_host) cudaFreeHost(cg_host);
         for (auto &e : poll_event) if (e) cudaEventDestroy(e);
         if (timer_start) cudaEventDestroy(timer_start);
@@ -359,6 +393,8 @@ public:
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        { int rc = build_cg_graph(); if (rc) return rc; }
+        have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
         return ARAP_OK;
@@ -405,8 +441,8 @@ public:
             }
             ARAP_CUDA(d->x.ensure((size_t)d->n));
             ARAP_CUDA(d->x2.ensure((size_t)d->n));
-            d->xp = d->x.ptr;
-            d->x2p = d->x2.ptr;
+            d->a_lanes = pick_lanes(hl.A.colidx.size(), (size_t)hl.A.n_rows);
+            d->r_lanes = pick_lanes(hl.R.colidx.size(), (size_t)hl.R.n_rows);
             mg.push_back(std::move(d));
         }
         mg_dense = !H.coarse_inv.empty();
@@ -419,6 +455,8 @@ public:
     }
 
     // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
+    // Buffer roles are fixed (no pointer swapping) so that the launch sequence can be captured in a CUDA graph:
+    // on every level x = iterate before post-smoothing, x2 = the level's result; level 0's result is z = mg[0]->x2.
     void vcycle() {
         const int V = n_vertices;
         const int L = (int)mg.size();
@@ -430,40 +468,48 @@ public:
                        cg_r.ptr, z, cg.ptr);
                 LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+                ARAP_DISPATCH_LANES(1, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)V * LN), V,
+                                              m0.a_rowptr.ptr, m0.a_colidx.ptr, m0.a_val.ptr, m0.inv_diag.ptr, 0.0, cg_r.ptr, m0.x.ptr, z, cg.ptr));
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             }
             return;
         }
         // down
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
-            if (l == 0)
+            if (l == 0) {
                 LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr,
-                       rest4.ptr, cg_r.ptr, f.xp, f.r.ptr, cg.ptr);
-            else
-                LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel, grid_for((size_t)f.n), f.n, f.a_rowptr.ptr, f.a_colidx.ptr,
-                       f.a_val.ptr, f.b.ptr, f.xp, f.r.ptr, cg.ptr);
-            LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel, grid_for((size_t)c.n), c.n, f.r_rowptr.ptr, f.r_colidx.ptr,
-                   f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, c.omega, c.b.ptr, c.xp, cg.ptr);
+                       rest4.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
+            } else {
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.b.ptr, f.x.ptr, f.r.ptr, cg.ptr));
+            }
+            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+                                                  f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, c.omega, c.b.ptr,
+                                                  c.x.ptr, cg.ptr));
         }
-        // coarsest
+        // coarsest: exact dense solve, or one more damped-Jacobi step when the level is too large for a dense inverse
         MgLevelDev &cl = *mg[L - 1];
         if (mg_dense) {
             LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
-                   cl.b.ptr, cl.xp, cg.ptr);
+                   cl.b.ptr, cl.x2.ptr, cg.ptr);
+        } else {
+            ARAP_DISPATCH_LANES(cl.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)cl.n * LN), cl.n,
+                                                   cl.a_rowptr.ptr, cl.a_colidx.ptr, cl.a_val.ptr, cl.inv_diag.ptr, cl.omega, cl.b.ptr,
+                                                   cl.x.ptr, cl.x2.ptr, cg.ptr));
         }
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)f.n), f.n, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
-                   c.xp, f.xp, cg.ptr);
+                   c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
                 LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr,
-                       weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.xp, z, partials.ptr, counter.ptr, cg.ptr);
+                       weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel, grid_for((size_t)f.n), f.n, f.a_rowptr.ptr, f.a_colidx.ptr,
-                       f.a_val.ptr, f.inv_diag.ptr, f.omega, f.b.ptr, f.xp, f.x2p, cg.ptr);
-                Vec3d *t = f.xp; f.xp = f.x2p; f.x2p = t;
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, f.omega, f.b.ptr,
+                                                      f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
     }
@@ -479,39 +525,68 @@ public:
 
     void cg_iteration_mg() {
         const int V = n_vertices, G = grid_for((size_t)V);
+        const int n3 = 3 * V, G3 = grid_for(((size_t)n3 + 1) / 2);
         MgLevelDev &m0 = *mg[0];
         vcycle();
-        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G, V, m0.x2.ptr, cg_d.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const double *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
         LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
                partials.ptr, counter.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, G, V, inv_diag.ptr, m0.omega, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr,
-               m0.xp, partials.ptr, counter.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, G3, n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
+               (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (double *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+    }
+
+    // Capture one CG iteration into a CUDA graph: ~20 small launches collapse into one graph launch.
+    int build_cg_graph() {
+        destroy_cg_graph();
+        std::memset(graph_counts, 0, sizeof(graph_counts));
+        ARAP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+        if (use_mg) cg_iteration_mg(); else cg_iteration_jacobi();
+        capturing = false;
+        cudaError_t e = cudaStreamEndCapture(stream, &cg_graph);
+        if (e != cudaSuccess) { cg_graph = nullptr; return fail(ARAP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+        ARAP_CUDA(cudaGraphInstantiate(&cg_graph_exec, cg_graph, 0));
+        return ARAP_OK;
+    }
+
+    inline int issue_cg_iteration() {
+        if (cg_graph_exec && !profile_events) {
+            for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) profile.launches[k] += graph_counts[k];
+            ARAP_CUDA(cudaGraphLaunch(cg_graph_exec, stream));
+        } else if (use_mg) {
+            cg_iteration_mg();
+        } else {
+            cg_iteration_jacobi();
+        }
+        return ARAP_OK;
     }
 
     int global_step() {
         const int V = n_vertices, G = grid_for((size_t)V);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            m0.xp = m0.x.ptr;
             LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.xp, partials.ptr, counter.ptr, cg.ptr);
+                   quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
         } else {
             LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
         int check = opt.cg_check_interval > 0 ? opt.cg_check_interval : 32;
-        if (use_mg && check > 4) check = 4;
-        // Batches of `check` CG iterations are enqueued one batch ahead of the convergence poll, so
-        // the device never idles waiting for the host; once converged the kernels return immediately.
+        if (use_mg) check = 1;
+        // The iteration count of a warm-started solve is very close to the previous global step's, so
+        // that many iterations (minus a margin) are enqueued blind; after that, batches of `check`
+        // iterations are enqueued one batch ahead of the convergence poll so the device never idles
+        // waiting for the host. Once converged every kernel returns immediately.
         int issued = 0, slot = 0;
         bool have_poll[2] = {false, false};
         bool done = false;
+        int blind = stats.last_cg_iterations - (use_mg ? 1 : check);
+        if (blind > max_it) blind = max_it;
+        for (; issued < blind; ++issued) { int rc = issue_cg_iteration(); if (rc) return rc; }
         while (!done) {
             const int batch = (max_it - issued < check) ? (max_it - issued) : check;
-            for (int it = 0; it < batch; ++it) {
-                if (use_mg) cg_iteration_mg(); else cg_iteration_jacobi();
-            }
+            for (int it = 0; it < batch; ++it) { int rc = issue_cg_iteration(); if (rc) return rc; }
             issued += batch;
             ARAP_CUDA(cudaMemcpyAsync(&cg_host[slot], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
             ARAP_CUDA(cudaEventRecord(poll_event[slot], stream));
@@ -541,7 +616,10 @@ public:
         if (!prepared) return fail(ARAP_ERR_INVALID, "iterate: arap_prepare has not succeeded");
         const int V = n_vertices, G = grid_for((size_t)V);
         for (int it = 0; it < n; ++it) {
-            LAUNCH(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
+            // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the warm
+            // kernel certifies convergence to the SVD's rotation per vertex and falls back to the Jacobi SVD otherwise.
+            LAUNCH(ARAP_K_LOCAL_STEP, (local_step_kernel<S, true>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
+            have_warm_rotations = true;
             int rc = global_step();
             if (rc) return rc;
         }

@@ -172,29 +172,55 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const S *__re
 // =================================================================================================
 // Local step (reference arap.h:354-384): S_i = sum_j w_ij (p_i-p_j)(p'_i-p'_j)^T, R_i from its SVD.
 // =================================================================================================
-template <typename S>
+// Neighbours are gathered in chunks of kGather<S> so that all index loads, then all position gathers
+// of a chunk are in flight together (memory-level parallelism) before the arithmetic starts.
+template <typename S> struct GatherChunk;
+template <> struct GatherChunk<float> { static constexpr int value = 6; };
+template <> struct GatherChunk<double> { static constexpr int value = 3; };
+
+// WARM = true : R_i from the previous iteration seeds a Newton iteration (see arap_math.cuh); Jacobi SVD fallback.
+// WARM = false: always the Jacobi SVD (used when there is no previous rotation worth trusting).
+template <typename S, bool WARM>
 __global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                             const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
                                                             const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat) {
+    constexpr int CH = GatherChunk<S>::value;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Vec4T<S> pi = load4<S>(&rest4[i]);
-    const Vec4T<S> qi = load4<S>(&cur4[i]);
     const int k0 = rowptr[i], k1 = rowptr[i + 1];
+    const Vec4T<S> pi = load4<S>(&rest4[i]);
+    const Vec4T<S> ci = load4<S>(&cur4[i]);
+    Vec4T<S> qprev;
+    if (WARM) qprev = load4<S>(&quat[i]);
     S cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = k0; k < k1; ++k) {
-        const int j = __ldg(&colidx[k]);
-        const S w = __ldg(&weight[k]);
-        const Vec4T<S> pj = load4<S>(&rest4[j]);
-        const Vec4T<S> qj = load4<S>(&cur4[j]);
-        const S ex = w * (pi.x - pj.x), ey = w * (pi.y - pj.y), ez = w * (pi.z - pj.z);
-        const S dx = qi.x - qj.x, dy = qi.y - qj.y, dz = qi.z - qj.z;
-        cov[0] += ex * dx; cov[1] += ex * dy; cov[2] += ex * dz;
-        cov[3] += ey * dx; cov[4] += ey * dy; cov[5] += ey * dz;
-        cov[6] += ez * dx; cov[7] += ez * dy; cov[8] += ez * dz;
+    for (int k = k0; k < k1; k += CH) {
+        int j[CH];
+        S w[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const bool valid = k + u < k1;
+            j[u] = valid ? __ldg(&colidx[k + u]) : i;
+            w[u] = valid ? __ldg(&weight[k + u]) : S(0);
+        }
+        Vec4T<S> pj[CH], cj[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const S ex = w[u] * (pi.x - pj[u].x), ey = w[u] * (pi.y - pj[u].y), ez = w[u] * (pi.z - pj[u].z);
+            const S dx = ci.x - cj[u].x, dy = ci.y - cj[u].y, dz = ci.z - cj[u].z;
+            cov[0] += ex * dx; cov[1] += ex * dy; cov[2] += ex * dz;
+            cov[3] += ey * dx; cov[4] += ey * dy; cov[5] += ey * dz;
+            cov[6] += ez * dx; cov[7] += ez * dy; cov[8] += ez * dz;
+        }
     }
     S q[4];
-    rotation_from_covariance<S>(cov, q);
+    if (WARM) {
+        const S qp[4] = {qprev.x, qprev.y, qprev.z, qprev.w};
+        rotation_from_covariance_warm<S>(cov, qp, q);
+    } else {
+        rotation_from_covariance<S>(cov, q);
+    }
     store4<S>(&quat[i], q[0], q[1], q[2], q[3]);
 }
 
@@ -240,24 +266,34 @@ __global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *
             double rot_j[3] = {0, 0, 0};     // sum_j (w/2) R_j e_ij
             double se[3] = {0, 0, 0};        // sum_j (w/2) e_ij
             double lap[3] = {0, 0, 0};       // sum_j w (p'_i - p'_j)
+            constexpr int CH = GatherChunk<S>::value;
             const int k0 = rowptr[i], k1 = rowptr[i + 1];
-            for (int k = k0; k < k1; ++k) {
-                const int j = __ldg(&colidx[k]);
-                const S w = __ldg(&weight[k]);
-                const Vec4T<S> pj = load4<S>(&rest4[j]);
-                const Vec4T<S> cj = load4<S>(&cur4[j]);
-                const Vec4T<S> qj = load4<S>(&quat[j]);
-                const S hw = S(0.5) * w;
-                const S ex = hw * (pi.x - pj.x), ey = hw * (pi.y - pj.y), ez = hw * (pi.z - pj.z);
-                S rj[9];
-                quat_to_matrix<S>(qj.x, qj.y, qj.z, qj.w, rj);     // quat stored as (w,x,y,z) in (.x,.y,.z,.w)
-                rot_j[0] += (double)(rj[0] * ex + rj[1] * ey + rj[2] * ez);
-                rot_j[1] += (double)(rj[3] * ex + rj[4] * ey + rj[5] * ez);
-                rot_j[2] += (double)(rj[6] * ex + rj[7] * ey + rj[8] * ez);
-                se[0] += (double)ex; se[1] += (double)ey; se[2] += (double)ez;
-                lap[0] += (double)w * ((double)ci.x - (double)cj.x);
-                lap[1] += (double)w * ((double)ci.y - (double)cj.y);
-                lap[2] += (double)w * ((double)ci.z - (double)cj.z);
+            for (int k = k0; k < k1; k += CH) {
+                int j[CH];
+                S w[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const bool valid = k + u < k1;
+                    j[u] = valid ? __ldg(&colidx[k + u]) : i;
+                    w[u] = valid ? __ldg(&weight[k + u]) : S(0);
+                }
+                Vec4T<S> pj[CH], cj[CH], qj[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); qj[u] = load4<S>(&quat[j[u]]); }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const S hw = S(0.5) * w[u];
+                    const S ex = hw * (pi.x - pj[u].x), ey = hw * (pi.y - pj[u].y), ez = hw * (pi.z - pj[u].z);
+                    S rj[9];
+                    quat_to_matrix<S>(qj[u].x, qj[u].y, qj[u].z, qj[u].w, rj);     // quat stored as (w,x,y,z) in (.x,.y,.z,.w)
+                    rot_j[0] += (double)(rj[0] * ex + rj[1] * ey + rj[2] * ez);
+                    rot_j[1] += (double)(rj[3] * ex + rj[4] * ey + rj[5] * ez);
+                    rot_j[2] += (double)(rj[6] * ex + rj[7] * ey + rj[8] * ez);
+                    se[0] += (double)ex; se[1] += (double)ey; se[2] += (double)ez;
+                    lap[0] += (double)w[u] * ((double)ci.x - (double)cj[u].x);
+                    lap[1] += (double)w[u] * ((double)ci.y - (double)cj[u].y);
+                    lap[2] += (double)w[u] * ((double)ci.z - (double)cj[u].z);
+                }
             }
             double ri[9];
             quat_to_matrix<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, ri);

@@ -79,48 +79,64 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
 }
 
 // ---- generic CSR levels -------------------------------------------------------------------------------
-__device__ __forceinline__ Vec3d csr_apply_row(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+// LANES (a power of two <= 32) consecutive threads share one row and reduce with shuffles, so that
+// rows of ~10-25 entries (coarse operators, restriction) still spread over enough threads to fill the GPU.
+template <int LANES>
+__device__ __forceinline__ Vec3d csr_apply_row(int row, bool row_valid, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                const double *__restrict__ val, const Vec3d *__restrict__ x) {
     Vec3d out = {0, 0, 0};
-    const int k0 = rowptr[i], k1 = rowptr[i + 1];
-    for (int k = k0; k < k1; ++k) {
-        const int j = __ldg(&colidx[k]);
-        const double a = __ldg(&val[k]);
-        const Vec3d xj = x[j];
-        out.x += a * xj.x; out.y += a * xj.y; out.z += a * xj.z;
+    const int sub = threadIdx.x & (LANES - 1);
+    if (row_valid) {
+        const int k0 = rowptr[row], k1 = rowptr[row + 1];
+        for (int k = k0 + sub; k < k1; k += LANES) {
+            const int j = __ldg(&colidx[k]);
+            const double a = __ldg(&val[k]);
+            const Vec3d xj = x[j];
+            out.x += a * xj.x; out.y += a * xj.y; out.z += a * xj.z;
+        }
     }
-    return out;
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        out.x += __shfl_down_sync(0xffffffffu, out.x, o, LANES);
+        out.y += __shfl_down_sync(0xffffffffu, out.y, o, LANES);
+        out.z += __shfl_down_sync(0xffffffffu, out.z, o, LANES);
+    }
+    return out;     // complete in the row's lane 0
 }
 
 // r = b - A x
+template <int LANES>
 __global__ void __launch_bounds__(kBlock) mg_csr_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                  const double *__restrict__ val, const Vec3d *__restrict__ b,
                                                                  const Vec3d *__restrict__ x, Vec3d *__restrict__ r,
                                                                  const CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Vec3d ax = csr_apply_row(i, rowptr, colidx, val, x);
-    const Vec3d bi = b[i];
-    r[i] = Vec3d{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z};
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const Vec3d ax = csr_apply_row<LANES>(i, i < n, rowptr, colidx, val, x);
+    if (i < n && (threadIdx.x & (LANES - 1)) == 0) {
+        const Vec3d bi = b[i];
+        r[i] = Vec3d{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z};
+    }
 }
 
 // b_c = R r_f ; x_c = omega_c D_c^-1 b_c   (restriction fused with the coarse level's pre-smoothing from a zero guess)
+template <int LANES>
 __global__ void __launch_bounds__(kBlock) mg_restrict_presmooth_kernel(int nc, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                        const double *__restrict__ val, const Vec3d *__restrict__ r_fine,
                                                                        const double *__restrict__ inv_diag_c, double omega_c,
                                                                        Vec3d *__restrict__ b_c, Vec3d *__restrict__ x_c,
                                                                        const CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nc) return;
-    const Vec3d bc = csr_apply_row(i, rowptr, colidx, val, r_fine);
-    b_c[i] = bc;
-    const double s = omega_c * inv_diag_c[i];
-    x_c[i] = Vec3d{s * bc.x, s * bc.y, s * bc.z};
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const Vec3d bc = csr_apply_row<LANES>(i, i < nc, rowptr, colidx, val, r_fine);
+    if (i < nc && (threadIdx.x & (LANES - 1)) == 0) {
+        b_c[i] = bc;
+        const double s = omega_c * inv_diag_c[i];
+        x_c[i] = Vec3d{s * bc.x, s * bc.y, s * bc.z};
+    }
 }
 
-// x += P x_c
+// x += P x_c   (P rows hold ~1-4 entries: one thread per row)
 __global__ void __launch_bounds__(kBlock) mg_prolong_add_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                 const double *__restrict__ val, const Vec3d *__restrict__ x_c,
                                                                 Vec3d *__restrict__ x, const CgScalars *__restrict__ cg) {
@@ -128,24 +144,26 @@ __global__ void __launch_bounds__(kBlock) mg_prolong_add_kernel(int n, const int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (rowptr[i] == rowptr[i + 1]) return;
-    const Vec3d c = csr_apply_row(i, rowptr, colidx, val, x_c);
+    const Vec3d c = csr_apply_row<1>(i, true, rowptr, colidx, val, x_c);
     Vec3d xi = x[i];
     xi.x += c.x; xi.y += c.y; xi.z += c.z;
     x[i] = xi;
 }
 
 // x_out = x + omega D^-1 (b - A x)
+template <int LANES>
 __global__ void __launch_bounds__(kBlock) mg_csr_postsmooth_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                    const double *__restrict__ val, const double *__restrict__ inv_diag,
                                                                    double omega, const Vec3d *__restrict__ b, const Vec3d *__restrict__ x,
                                                                    Vec3d *__restrict__ x_out, const CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Vec3d ax = csr_apply_row(i, rowptr, colidx, val, x);
-    const Vec3d bi = b[i], xi = x[i];
-    const double s = omega * inv_diag[i];
-    x_out[i] = Vec3d{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z)};
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const Vec3d ax = csr_apply_row<LANES>(i, i < n, rowptr, colidx, val, x);
+    if (i < n && (threadIdx.x & (LANES - 1)) == 0) {
+        const Vec3d bi = b[i], xi = x[i];
+        const double s = omega * inv_diag[i];
+        x_out[i] = Vec3d{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z)};
+    }
 }
 
 // coarsest level: x = A^-1 b with the dense inverse; one warp per row.
@@ -165,26 +183,43 @@ __global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, const dou
     if (lane == 0) x[row] = Vec3d{s0, s1, s2};
 }
 
+__device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
+
 // ---- CG pieces for a general preconditioner -------------------------------------------------------------
+// The CG vectors are (x,y,z) triples, i.e. flat arrays of 3V doubles. The update and direction kernels are
+// purely element-wise, so they stream those flat arrays with one coalesced 16-byte access per thread and array
+// (element e belongs to vertex e/3, coordinate e%3) instead of three strided 8-byte accesses per vertex.
+//
 // x += alpha d ; r -= alpha Ad ; x0 = omega_0 D^-1 r (the V-cycle's pre-smoothed fine iterate) ; |r|^2 -> convergence
-__global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n, const double *__restrict__ inv_diag, double omega0,
-                                                              const Vec3d *__restrict__ d, const Vec3d *__restrict__ ad,
-                                                              Vec3d *__restrict__ x, Vec3d *__restrict__ r, Vec3d *__restrict__ x0,
+__global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n3, const double *__restrict__ inv_diag, double omega0,
+                                                              const double *__restrict__ d, const double *__restrict__ ad,
+                                                              double *__restrict__ x, double *__restrict__ r, double *__restrict__ x0,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     double red[1] = {0};
-    if (i < n) {
-        const double a0 = cg->alpha[0], a1 = cg->alpha[1], a2 = cg->alpha[2];
-        const Vec3d di = d[i], adi = ad[i];
-        Vec3d xi = x[i], ri = r[i];
-        xi.x += a0 * di.x; xi.y += a1 * di.y; xi.z += a2 * di.z;
-        ri.x -= a0 * adi.x; ri.y -= a1 * adi.y; ri.z -= a2 * adi.z;
-        x[i] = xi; r[i] = ri;
-        const double s = omega0 * inv_diag[i];
-        x0[i] = Vec3d{s * ri.x, s * ri.y, s * ri.z};
-        red[0] = ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
+    if (e < n3) {
+        const double al0 = cg->alpha[0], al1 = cg->alpha[1], al2 = cg->alpha[2];
+        if (e + 1 < n3) {
+            const double2 dv = *reinterpret_cast<const double2 *>(d + e), av = *reinterpret_cast<const double2 *>(ad + e);
+            double2 xv = *reinterpret_cast<const double2 *>(x + e), rv = *reinterpret_cast<const double2 *>(r + e);
+            const int c0 = e % 3, c1 = (e + 1) % 3;
+            const double a0 = pick3(c0, al0, al1, al2), a1 = pick3(c1, al0, al1, al2);
+            xv.x += a0 * dv.x; xv.y += a1 * dv.y;
+            rv.x -= a0 * av.x; rv.y -= a1 * av.y;
+            *reinterpret_cast<double2 *>(x + e) = xv;
+            *reinterpret_cast<double2 *>(r + e) = rv;
+            const double s0 = omega0 * inv_diag[e / 3], s1 = omega0 * inv_diag[(e + 1) / 3];
+            *reinterpret_cast<double2 *>(x0 + e) = make_double2(s0 * rv.x, s1 * rv.y);
+            red[0] = rv.x * rv.x + rv.y * rv.y;
+        } else {
+            const double a0 = pick3(e % 3, al0, al1, al2);
+            const double xv = x[e] + a0 * d[e], rv = r[e] - a0 * ad[e];
+            x[e] = xv; r[e] = rv;
+            x0[e] = omega0 * inv_diag[e / 3] * rv;
+            red[0] = rv * rv;
+        }
     }
     double total[1];
     if (grid_sum_last_block<1>(red, partials, counter, total)) {
@@ -195,17 +230,21 @@ __global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n, const doubl
 }
 
 // d = z + beta d
-__global__ void __launch_bounds__(kBlock) cg_direction_mg_kernel(int n, const Vec3d *__restrict__ z, Vec3d *__restrict__ d,
+__global__ void __launch_bounds__(kBlock) cg_direction_mg_kernel(int n3, const double *__restrict__ z, double *__restrict__ d,
                                                                  const CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Vec3d zi = z[i];
-    Vec3d di = d[i];
-    di.x = zi.x + cg->beta[0] * di.x;
-    di.y = zi.y + cg->beta[1] * di.y;
-    di.z = zi.z + cg->beta[2] * di.z;
-    d[i] = di;
+    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (e >= n3) return;
+    const double b0 = cg->beta[0], b1 = cg->beta[1], b2 = cg->beta[2];
+    if (e + 1 < n3) {
+        const double2 zv = *reinterpret_cast<const double2 *>(z + e);
+        double2 dv = *reinterpret_cast<const double2 *>(d + e);
+        dv.x = zv.x + pick3(e % 3, b0, b1, b2) * dv.x;
+        dv.y = zv.y + pick3((e + 1) % 3, b0, b1, b2) * dv.y;
+        *reinterpret_cast<double2 *>(d + e) = dv;
+    } else {
+        d[e] = z[e] + pick3(e % 3, b0, b1, b2) * d[e];
+    }
 }
 
 }  // namespace arap
