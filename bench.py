@@ -381,7 +381,7 @@ def main():
 
 
 def arap_tolerance(args):
-    return args.cg_tol if args.cg_tol > 0 else 1e-10
+    return args.cg_tol if args.cg_tol > 0 else 1e-7
 
 
 if __name__ == "__main__":

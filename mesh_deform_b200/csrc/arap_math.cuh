@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define ARAP_HD __host__ __device__ __forceinline__
+#define ARAP_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define ARAP_HD inline
+#define ARAP_HD_NOINLINE inline
 #endif
 
 namespace arap {

@@ -388,7 +388,7 @@ public:
         if (use_mg) { int rc = setup_multigrid(); if (rc) return rc; }
         CgScalars init;
         std::memset(&init, 0, sizeof(init));
-        const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : 1e-10;
+        const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : 1e-7;
         init.tol2 = tol * tol;
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
@@ -703,7 +703,7 @@ void arap_default_options(arap_options *opt) {
     opt->device = -1;
     opt->solver = ARAP_SOLVER_AUTO;
     opt->max_cg_iterations = 20000;
-    opt->cg_tolerance = 1e-10;
+    opt->cg_tolerance = 1e-7;
     opt->cg_check_interval = 32;
     opt->profile = 0;
 }

@@ -32,6 +32,25 @@ template <> __device__ __forceinline__ void store4<double>(Vec4T<double> *p, dou
     reinterpret_cast<double2 *>(p)[1] = make_double2(z, w);
 }
 
+// ---- scheduling fences -----------------------------------------------------------------------------
+// ptxas interleaves gathers with the arithmetic that consumes them to save registers, which leaves only
+// a few loads in flight per thread. An empty asm that "modifies" every gathered value pins all loads of
+// a chunk BEFORE it and all arithmetic AFTER it: the whole chunk's gathers are then outstanding together.
+__device__ __forceinline__ void pin_loaded(Vec3d (&a)[6]) {
+    asm volatile("" : "+d"(a[0].x), "+d"(a[0].y), "+d"(a[0].z), "+d"(a[1].x), "+d"(a[1].y), "+d"(a[1].z),
+                      "+d"(a[2].x), "+d"(a[2].y), "+d"(a[2].z), "+d"(a[3].x), "+d"(a[3].y), "+d"(a[3].z),
+                      "+d"(a[4].x), "+d"(a[4].y), "+d"(a[4].z), "+d"(a[5].x), "+d"(a[5].y), "+d"(a[5].z));
+}
+__device__ __forceinline__ void pin_loaded(Vec4T<double> (&a)[3]) {
+    asm volatile("" : "+d"(a[0].x), "+d"(a[0].y), "+d"(a[0].z), "+d"(a[0].w), "+d"(a[1].x), "+d"(a[1].y), "+d"(a[1].z), "+d"(a[1].w),
+                      "+d"(a[2].x), "+d"(a[2].y), "+d"(a[2].z), "+d"(a[2].w));
+}
+__device__ __forceinline__ void pin_loaded(Vec4T<float> (&a)[6]) {
+    asm volatile("" : "+f"(a[0].x), "+f"(a[0].y), "+f"(a[0].z), "+f"(a[0].w), "+f"(a[1].x), "+f"(a[1].y), "+f"(a[1].z), "+f"(a[1].w),
+                      "+f"(a[2].x), "+f"(a[2].y), "+f"(a[2].z), "+f"(a[2].w), "+f"(a[3].x), "+f"(a[3].y), "+f"(a[3].z), "+f"(a[3].w),
+                      "+f"(a[4].x), "+f"(a[4].y), "+f"(a[4].z), "+f"(a[4].w), "+f"(a[5].x), "+f"(a[5].y), "+f"(a[5].z), "+f"(a[5].w));
+}
+
 // =================================================================================================
 // Setup path: cotan weights + CSR (reference arap.h:182-239), free map (:261-272), constraints (:277-281)
 // =================================================================================================
@@ -205,6 +224,8 @@ __global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__
         Vec4T<S> pj[CH], cj[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); }
+        pin_loaded(pj);
+        pin_loaded(cj);
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             const S ex = w[u] * (pi.x - pj[u].x), ey = w[u] * (pi.y - pj[u].y), ez = w[u] * (pi.z - pj[u].z);
@@ -247,7 +268,7 @@ struct CgScalars {
 // MG = false: Jacobi-preconditioned start (d = z = D^-1 r, rho = r.z).
 // MG = true : multigrid start (d = 0, rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
 template <typename S, bool MG>
-__global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+__global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                               const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
                                                               const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
                                                               const double *__restrict__ inv_diag, double omega0,
@@ -280,6 +301,9 @@ __global__ void __launch_bounds__(kBlock) rhs_residual_kernel(int n, const int *
                 Vec4T<S> pj[CH], cj[CH], qj[CH];
 #pragma unroll
                 for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); qj[u] = load4<S>(&quat[j[u]]); }
+                pin_loaded(pj);
+                pin_loaded(cj);
+                pin_loaded(qj);
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const S hw = S(0.5) * w[u];
@@ -344,13 +368,26 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
     if (i < n) {
         Vec3d out = {0, 0, 0};
         if (rest4[i].w != S(0)) {
-            const Vec3d di = d[i];
+            constexpr int CH = 6;
             const int k0 = rowptr[i], k1 = rowptr[i + 1];
-            for (int k = k0; k < k1; ++k) {
-                const int j = __ldg(&colidx[k]);
-                const double w = (double)__ldg(&weight[k]);
-                const Vec3d dj = d[j];
-                out.x += w * (di.x - dj.x); out.y += w * (di.y - dj.y); out.z += w * (di.z - dj.z);
+            const Vec3d di = d[i];
+            for (int k = k0; k < k1; k += CH) {
+                int j[CH];
+                double w[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const bool valid = k + u < k1;
+                    j[u] = valid ? __ldg(&colidx[k + u]) : i;
+                    w[u] = valid ? (double)__ldg(&weight[k + u]) : 0.0;
+                }
+                Vec3d dj[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) dj[u] = d[j[u]];
+                pin_loaded(dj);
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    out.x += w[u] * (di.x - dj[u].x); out.y += w[u] * (di.y - dj[u].y); out.z += w[u] * (di.z - dj[u].z);
+                }
             }
             red[0] = di.x * out.x; red[1] = di.y * out.y; red[2] = di.z * out.z;
         }

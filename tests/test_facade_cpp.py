@@ -1,0 +1,84 @@
+"""The C++ header API (inc/deform/*.h) over the C ABI: restated reference tests compiled with g++.
+test_trajectory is host-only and runs here; test_cotan and demo_bar need the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bbox_diag
+from oracle import oracle as O
+from mesh_deform_b200 import meshgen as G
+
+CPP = os.path.join(ROOT, "tests", "cpp")
+
+
+@pytest.fixture(scope="module")
+def cpp_build():
+    subprocess.check_call(["make", "-s", "-C", CPP, "all"])
+    return CPP
+
+
+def test_trajectory_cpp_matches_reference_test_and_oracle(cpp_build, trajectory_golden):
+    out = subprocess.run([os.path.join(cpp_build, "test_trajectory")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr          # reference tests/test_trajectory.cpp:37-38 pins
+    assert "ALL PASSED" in out.stdout
+    samples = [list(map(float, l.split()[1:])) for l in out.stdout.splitlines() if l.startswith("SAMPLE")]
+    samples = np.array(samples)
+    assert samples.shape == (33, 17)
+    assert np.allclose(samples[:, 0], trajectory_golden["u"])
+    got = samples[:, 1:].reshape(-1, 4, 4)
+    assert np.abs(got - trajectory_golden["samples"]).max() < 1e-12      # interior values: facade == oracle
+    # DeformationUtil arithmetic against the oracle's restatement of deformation_util.h:48-57
+    rows = {k: [] for k in ("HANDLE", "ORIGIN", "T")}
+    for l in out.stdout.splitlines():
+        tag = l.split()[0] if l.split() else ""
+        if tag in rows:
+            rows[tag].append(list(map(float, l.split()[1:])))
+    origin, t = np.array(rows["ORIGIN"]), np.array(rows["T"])
+    handles = np.array(rows["HANDLE"])
+    pts = np.array([[1.0 + i, 2.0, -0.5 * i] for i in handles[:, 0]])
+    assert np.abs(O.handle_targets(origin, t, pts) - handles[:, 1:]).max() < 1e-13
+
+
+def test_headers_compile_standalone(cpp_build, tmp_path):
+    """Every public header is self-contained and the mesh concept is exactly the reference's five members."""
+    for hdr in ("deform/arap.h", "deform/trajectory.h", "deform/deformation_util.h", "deform/simple_mesh.h"):
+        src = tmp_path / "t.cpp"
+        src.write_text(f"#include <{hdr}>\nint main() {{ return 0; }}\n")
+        subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-I", os.path.join(ROOT, "inc"), "-I",
+                               os.path.join(ROOT, "include"), str(src)])
+
+
+@pytest.mark.gpu
+def test_cotan_cpp_reference_test(cpp_build):
+    out = subprocess.run([os.path.join(cpp_build, "test_cotan")], capture_output=True, text=True)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_demo_bar_cpp_matches_oracle(cpp_build, meshes, golden, tmp_path):
+    """reference examples/deform_bar.cpp's workload through the C++ facade (float mesh, double precision)."""
+    P, F = meshes["bar"]
+    obj = tmp_path / "bar.obj"
+    with open(obj, "w") as fh:
+        for p in P:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for f in F:
+            fh.write("f %d %d %d\n" % tuple(f + 1))
+    con = tmp_path / "constraints.txt"
+    with open(con, "w") as fh:
+        for i, t in zip(golden["bar_idx"], golden["bar_tgt"]):
+            fh.write("%d %.17g %.17g %.17g\n" % (i, t[0], t[1], t[2]))
+    out = subprocess.run([os.path.join(cpp_build, "demo_bar"), str(obj), str(con), "10"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    pos = np.array([list(map(float, l.split()[1:])) for l in out.stdout.splitlines() if l.startswith("V ")])
+    energy = float([l for l in out.stdout.splitlines() if l.startswith("ENERGY")][0].split()[1])
+    # the same protocol in the oracle: float mesh, double solver (deform_bar.cpp:38)
+    mesh = P.astype(np.float32)
+    o = O.ArapOracle(mesh, F, np.float64)
+    for i, t in zip(golden["bar_idx"], golden["bar_tgt"]):
+        o.setConstraint(int(i), t)
+    assert o.deform(10)
+    assert np.abs(pos - mesh).max() <= 1e-5 * bbox_diag(P)
+    assert abs(energy - o.energy()) <= 1e-6 * o.energy()
