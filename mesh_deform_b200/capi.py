@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarap_b200.so")
+LIB_PATH = os.environ.get("ARAP_B200_LIB") or os.path.join(_HERE, "libarap_b200.so")   # override: kernel-variant experiments
 
 ARAP_OK = 0
 ARAP_UNCONSTRAINED = 1

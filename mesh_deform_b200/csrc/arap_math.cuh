@@ -233,7 +233,7 @@ template <> struct NewtonTol<float> {
     static constexpr float det_min = 1e-4f;
 };
 template <> struct NewtonTol<double> {
-    static constexpr double step2 = 1e-13;
+    static constexpr double step2 = 1e-10;
     static constexpr double det_min = 1e-9;
 };
 
@@ -259,8 +259,9 @@ ARAP_HD S refined_rcp(S x) {
 }
 
 // c: covariance scaled so that max|c| = 1. q: in = warm start (unit quaternion w,x,y,z), out = result.
+// step2_accept: stop once |omega|^2 of the step just taken is below it (the remaining error is ~|omega|^2).
 template <typename S>
-ARAP_HD bool rotation_newton(const S c[9], S q[4], int max_steps) {
+ARAP_HD bool rotation_newton(const S c[9], S q[4], int max_steps, S step2_accept) {
     for (int it = 0; it < max_steps; ++it) {
         S r[9];
         quat_to_matrix<S>(q[0], q[1], q[2], q[3], r);
@@ -290,9 +291,20 @@ ARAP_HD bool rotation_newton(const S c[9], S q[4], int max_steps) {
         q[0] = nw * inv_n; q[1] = nx * inv_n; q[2] = ny * inv_n; q[3] = nz * inv_n;
         const S step2 = S(4) * (ox * ox + oy * oy + oz * oz);
         if (!(step2 < S(4))) return false;          // |omega| >= 2 rad (or NaN): not in the Newton basin
-        if (step2 < NewtonTol<S>::step2) return true;
+        if (step2 < step2_accept) return true;
     }
     return false;
+}
+
+// float: plain fp32 Newton.
+ARAP_HD bool rotation_newton_certified(const float c[9], float q[4]) {
+    return rotation_newton<float>(c, q, 6, NewtonTol<float>::step2);
+}
+// double: plain fp64 Newton, accepted once |omega| < 1e-5 on the step just taken (remaining error ~1e-10 rad).
+// (A mixed variant -- fp32 approach, fp64 polish -- measured slower: the kernel is bound by the latency of
+// the serial chain per thread, and the extra fp32 steps lengthen it.)
+ARAP_HD bool rotation_newton_certified(const double c[9], double q[4]) {
+    return rotation_newton<double>(c, q, 6, NewtonTol<double>::step2);
 }
 
 // Local step kernel body: warm-started Newton, Jacobi SVD fallback. q_prev/q_out may alias.
@@ -305,7 +317,7 @@ ARAP_HD void rotation_from_covariance_warm(const S cov[9], const S q_prev[4], S 
         S c[9];
         for (int i = 0; i < 9; ++i) c[i] = cov[i] * inv_scale;
         S q[4] = {q_prev[0], q_prev[1], q_prev[2], q_prev[3]};
-        if (rotation_newton<S>(c, q, 6)) {
+        if (rotation_newton_certified(c, q)) {
             q_out[0] = q[0]; q_out[1] = q[1]; q_out[2] = q[2]; q_out[3] = q[3];
             return;
         }

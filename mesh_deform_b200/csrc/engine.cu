@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <new>
 #include <string>
@@ -45,6 +46,12 @@ struct Status {
     } while (0)
 
 static inline int grid_for(size_t n) { return (int)((n + kBlock - 1) / kBlock); }
+// Kernels that end in a grid-wide reduction run as persistent grid-stride kernels: exactly as many CTAs
+// as fit on the GPU at once (occupancy API, per kernel), so the number of per-block partials -- and the tail
+// in which the last CTA sums them -- stays small. Measured (profiles/r01_d_variants.txt): 10 % per CG iteration.
+#ifndef ARAP_PERSISTENT_CTAS_PER_SM
+#define ARAP_PERSISTENT_CTAS_PER_SM 0      /* 0 = ask the occupancy API per kernel */
+#endif
 
 template <typename T>
 struct DeviceBuffer {
@@ -117,6 +124,24 @@ public:
 
     int n_vertices = 0, n_faces = 0;
     int device = 0;
+    int sm_count = 148;
+    std::map<const void *, int> resident_ctas;     // per kernel: CTAs of kBlock threads resident per SM
+    template <typename K>
+    int reduce_grid(K kernel, size_t n) {
+        int per_sm = ARAP_PERSISTENT_CTAS_PER_SM;
+        if (per_sm <= 0) {
+            const void *key = (const void *)kernel;
+            auto it = resident_ctas.find(key);
+            if (it == resident_ctas.end()) {
+                int occ = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ <= 0) occ = 4;
+                it = resident_ctas.emplace(key, occ).first;
+            }
+            per_sm = it->second;
+        }
+        const int full = grid_for(n), cap = sm_count * per_sm;
+        return full < cap ? (full > 0 ? full : 1) : cap;
+    }
     cudaStream_t stream = nullptr;
     arap_options opt;
     bool dirty = true;
@@ -246,6 +271,7 @@ public:
         } else {
             ARAP_CUDA(cudaGetDevice(&device));
         }
+        ARAP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
         ARAP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         ARAP_CUDA(cudaEventCreate(&timer_start));
         ARAP_CUDA(cudaEventCreate(&timer_stop));
@@ -466,11 +492,11 @@ public:
             if (mg_dense) {
                 LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (V + kWarpsPerBlock - 1) / kWarpsPerBlock, V, mg_coarse_inv.ptr,
                        cg_r.ptr, z, cg.ptr);
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(1, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)V * LN), V,
                                               m0.a_rowptr.ptr, m0.a_colidx.ptr, m0.a_val.ptr, m0.inv_diag.ptr, 0.0, cg_r.ptr, m0.x.ptr, z, cg.ptr));
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, grid_for((size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             }
             return;
         }
@@ -504,7 +530,7 @@ public:
             LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)f.n), f.n, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr,
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr,
                        weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
@@ -516,9 +542,9 @@ public:
 
     void cg_iteration_jacobi() {
         const int V = n_vertices, G = grid_for((size_t)V);
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
                partials.ptr, counter.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, G, V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
+        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)V), V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
                counter.ptr, cg.ptr);
         LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, G, V, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
     }
@@ -529,9 +555,9 @@ public:
         MgLevelDev &m0 = *mg[0];
         vcycle();
         LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const double *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
                partials.ptr, counter.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, G3, n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
+        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
                (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (double *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
     }
 
@@ -565,10 +591,10 @@ public:
         const int V = n_vertices, G = grid_for((size_t)V);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
         } else {
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
@@ -674,7 +700,7 @@ public:
     int energy(double *e) override {
         if (!quat.ptr || !rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
         const int V = n_vertices;
-        LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+        LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, reduce_grid(energy_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
                partials.ptr, counter.ptr, energy_dev.ptr);
         ARAP_CUDA(cudaMemcpyAsync(e, energy_dev.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));

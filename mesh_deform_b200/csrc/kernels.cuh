@@ -32,23 +32,35 @@ template <> __device__ __forceinline__ void store4<double>(Vec4T<double> *p, dou
     reinterpret_cast<double2 *>(p)[1] = make_double2(z, w);
 }
 
-// ---- scheduling fences -----------------------------------------------------------------------------
-// ptxas interleaves gathers with the arithmetic that consumes them to save registers, which leaves only
-// a few loads in flight per thread. An empty asm that "modifies" every gathered value pins all loads of
-// a chunk BEFORE it and all arithmetic AFTER it: the whole chunk's gathers are then outstanding together.
-__device__ __forceinline__ void pin_loaded(Vec3d (&a)[6]) {
-    asm volatile("" : "+d"(a[0].x), "+d"(a[0].y), "+d"(a[0].z), "+d"(a[1].x), "+d"(a[1].y), "+d"(a[1].z),
-                      "+d"(a[2].x), "+d"(a[2].y), "+d"(a[2].z), "+d"(a[3].x), "+d"(a[3].y), "+d"(a[3].z),
-                      "+d"(a[4].x), "+d"(a[4].y), "+d"(a[4].z), "+d"(a[5].x), "+d"(a[5].y), "+d"(a[5].z));
+// ---- load-batching gates ---------------------------------------------------------------------------
+// ptxas interleaves each gather with the arithmetic that consumes it (to shorten live ranges), which
+// leaves only one neighbour's loads in flight per thread.
+// `0 * x` cannot be folded under IEEE rules (x could be NaN/Inf), so adding gate = 0 * (sum of one word
+// of every gathered value) to the chunk's weights makes every product depend on ALL gathers of the
+// chunk: the loads are then issued back to back and a whole chunk is in flight. Numerically a no-op
+// (w + 0.0 == w) for finite data. Measured on B200 (profiles/r01_d_variants.txt): batching 2 neighbours
+// is the sweet spot for the SpMV-like kernels (40 registers, full occupancy); batching 6 costs 78
+// registers and is 15 % SLOWER, and the local step / RHS kernels are best without a gate at all.
+template <int N>
+__device__ __forceinline__ double gather_gate(const Vec3d (&a)[N]) {
+    double s = a[0].z;
+#pragma unroll
+    for (int u = 1; u < N; ++u) s += a[u].z;
+    return 0.0 * s;
 }
-__device__ __forceinline__ void pin_loaded(Vec4T<double> (&a)[3]) {
-    asm volatile("" : "+d"(a[0].x), "+d"(a[0].y), "+d"(a[0].z), "+d"(a[0].w), "+d"(a[1].x), "+d"(a[1].y), "+d"(a[1].z), "+d"(a[1].w),
-                      "+d"(a[2].x), "+d"(a[2].y), "+d"(a[2].z), "+d"(a[2].w));
+template <int N>
+__device__ __forceinline__ double gather_gate(const Vec4T<double> (&a)[N]) {   // two 16-byte loads per element
+    double s = a[0].x + a[0].z;
+#pragma unroll
+    for (int u = 1; u < N; ++u) s += a[u].x + a[u].z;
+    return 0.0 * s;
 }
-__device__ __forceinline__ void pin_loaded(Vec4T<float> (&a)[6]) {
-    asm volatile("" : "+f"(a[0].x), "+f"(a[0].y), "+f"(a[0].z), "+f"(a[0].w), "+f"(a[1].x), "+f"(a[1].y), "+f"(a[1].z), "+f"(a[1].w),
-                      "+f"(a[2].x), "+f"(a[2].y), "+f"(a[2].z), "+f"(a[2].w), "+f"(a[3].x), "+f"(a[3].y), "+f"(a[3].z), "+f"(a[3].w),
-                      "+f"(a[4].x), "+f"(a[4].y), "+f"(a[4].z), "+f"(a[4].w), "+f"(a[5].x), "+f"(a[5].y), "+f"(a[5].z), "+f"(a[5].w));
+template <int N>
+__device__ __forceinline__ float gather_gate(const Vec4T<float> (&a)[N]) {     // one 16-byte load per element
+    float s = a[0].x;
+#pragma unroll
+    for (int u = 1; u < N; ++u) s += a[u].x;
+    return 0.0f * s;
 }
 
 // =================================================================================================
@@ -193,9 +205,22 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const S *__re
 // =================================================================================================
 // Neighbours are gathered in chunks of kGather<S> so that all index loads, then all position gathers
 // of a chunk are in flight together (memory-level parallelism) before the arithmetic starts.
+#ifndef ARAP_LOCAL_CHUNK_F64
+#define ARAP_LOCAL_CHUNK_F64 3
+#endif
+#ifndef ARAP_RHS_CHUNK_F64
+#define ARAP_RHS_CHUNK_F64 3
+#endif
+#ifndef ARAP_SPMV_CHUNK
+#define ARAP_SPMV_CHUNK 2
+#endif
 template <typename S> struct GatherChunk;
 template <> struct GatherChunk<float> { static constexpr int value = 6; };
-template <> struct GatherChunk<double> { static constexpr int value = 3; };
+template <> struct GatherChunk<double> { static constexpr int value = ARAP_LOCAL_CHUNK_F64; };
+template <typename S> struct RhsChunk;
+template <> struct RhsChunk<float> { static constexpr int value = 4; };
+template <> struct RhsChunk<double> { static constexpr int value = ARAP_RHS_CHUNK_F64; };
+constexpr int kSpmvChunk = ARAP_SPMV_CHUNK;
 
 // WARM = true : R_i from the previous iteration seeds a Newton iteration (see arap_math.cuh); Jacobi SVD fallback.
 // WARM = false: always the Jacobi SVD (used when there is no previous rotation worth trusting).
@@ -224,8 +249,6 @@ __global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__
         Vec4T<S> pj[CH], cj[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); }
-        pin_loaded(pj);
-        pin_loaded(cj);
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             const S ex = w[u] * (pi.x - pj[u].x), ey = w[u] * (pi.y - pj[u].y), ez = w[u] * (pi.z - pj[u].z);
@@ -267,6 +290,7 @@ struct CgScalars {
 
 // MG = false: Jacobi-preconditioned start (d = z = D^-1 r, rho = r.z).
 // MG = true : multigrid start (d = 0, rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
+// (A variant with 8 lanes per vertex and a shuffle reduction of the nine partial sums measured 4x slower: 383 us.)
 template <typename S, bool MG>
 __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                               const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
@@ -276,9 +300,8 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                                                               Vec3d *__restrict__ x_out, Vec3d *__restrict__ x0_out,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[5] = {0, 0, 0, 0, 0};   // rho x,y,z ; rr ; ref2
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec4T<S> pi = load4<S>(&rest4[i]);
         Vec3d r = {0, 0, 0}, z = {0, 0, 0};
         if (pi.w != S(0)) {
@@ -287,7 +310,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
             double rot_j[3] = {0, 0, 0};     // sum_j (w/2) R_j e_ij
             double se[3] = {0, 0, 0};        // sum_j (w/2) e_ij
             double lap[3] = {0, 0, 0};       // sum_j w (p'_i - p'_j)
-            constexpr int CH = GatherChunk<S>::value;
+            constexpr int CH = RhsChunk<S>::value;
             const int k0 = rowptr[i], k1 = rowptr[i + 1];
             for (int k = k0; k < k1; k += CH) {
                 int j[CH];
@@ -301,9 +324,6 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                 Vec4T<S> pj[CH], cj[CH], qj[CH];
 #pragma unroll
                 for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); qj[u] = load4<S>(&quat[j[u]]); }
-                pin_loaded(pj);
-                pin_loaded(cj);
-                pin_loaded(qj);
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const S hw = S(0.5) * w[u];
@@ -327,9 +347,9 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
             r.x = rhs0 - lap[0]; r.y = rhs1 - lap[1]; r.z = rhs2 - lap[2];
             const double idg = inv_diag[i];
             z.x = r.x * idg; z.y = r.y * idg; z.z = r.z * idg;
-            red[0] = r.x * z.x; red[1] = r.y * z.y; red[2] = r.z * z.z;
-            red[3] = r.x * r.x + r.y * r.y + r.z * r.z;
-            red[4] = rhs0 * rhs0 + rhs1 * rhs1 + rhs2 * rhs2;
+            red[0] += r.x * z.x; red[1] += r.y * z.y; red[2] += r.z * z.z;
+            red[3] += r.x * r.x + r.y * r.y + r.z * r.z;
+            red[4] += rhs0 * rhs0 + rhs1 * rhs1 + rhs2 * rhs2;
         }
         r_out[i] = r;
         x_out[i] = Vec3d{0, 0, 0};
@@ -363,12 +383,11 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
                                                          double *__restrict__ partials, unsigned *__restrict__ counter,
                                                          CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[3] = {0, 0, 0};
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Vec3d out = {0, 0, 0};
         if (rest4[i].w != S(0)) {
-            constexpr int CH = 6;
+            constexpr int CH = kSpmvChunk;
             const int k0 = rowptr[i], k1 = rowptr[i + 1];
             const Vec3d di = d[i];
             for (int k = k0; k < k1; k += CH) {
@@ -383,13 +402,15 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
                 Vec3d dj[CH];
 #pragma unroll
                 for (int u = 0; u < CH; ++u) dj[u] = d[j[u]];
-                pin_loaded(dj);
+                const double gate = gather_gate(dj);
+#pragma unroll
+                for (int u = 0; u < CH; ++u) w[u] += gate;
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     out.x += w[u] * (di.x - dj[u].x); out.y += w[u] * (di.y - dj[u].y); out.z += w[u] * (di.z - dj[u].z);
                 }
             }
-            red[0] = di.x * out.x; red[1] = di.y * out.y; red[2] = di.z * out.z;
+            red[0] += di.x * out.x; red[1] += di.y * out.y; red[2] += di.z * out.z;
         }
         ad[i] = out;
     }
@@ -405,9 +426,8 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
                                                            double *__restrict__ partials, unsigned *__restrict__ counter,
                                                            CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0, 0, 0, 0};
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double a0 = cg->alpha[0], a1 = cg->alpha[1], a2 = cg->alpha[2];
         const Vec3d di = d[i], adi = ad[i];
         Vec3d xi = x[i], ri = r[i];
@@ -415,8 +435,8 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
         ri.x -= a0 * adi.x; ri.y -= a1 * adi.y; ri.z -= a2 * adi.z;
         x[i] = xi; r[i] = ri;
         const double idg = inv_diag[i];
-        red[0] = ri.x * ri.x * idg; red[1] = ri.y * ri.y * idg; red[2] = ri.z * ri.z * idg;
-        red[3] = ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
+        red[0] += ri.x * ri.x * idg; red[1] += ri.y * ri.y * idg; red[2] += ri.z * ri.z * idg;
+        red[3] += ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
     }
     double total[4];
     if (grid_sum_last_block<4>(red, partials, counter, total)) {
@@ -436,11 +456,10 @@ __global__ void __launch_bounds__(kBlock) cg_dot_rho_kernel(int n, const Vec3d *
                                                             double *__restrict__ partials, unsigned *__restrict__ counter,
                                                             CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[3] = {0, 0, 0};
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec3d ri = r[i], zi = z[i];
-        red[0] = ri.x * zi.x; red[1] = ri.y * zi.y; red[2] = ri.z * zi.z;
+        red[0] += ri.x * zi.x; red[1] += ri.y * zi.y; red[2] += ri.z * zi.z;
     }
     double total[3];
     if (grid_sum_last_block<3>(red, partials, counter, total)) {
@@ -488,9 +507,8 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(int n, const int *__rest
                                                         const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
                                                         double *__restrict__ partials, unsigned *__restrict__ counter,
                                                         double *__restrict__ energy_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[1] = {0};
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec4T<S> pi = load4<S>(&rest4[i]);
         const Vec4T<S> ci = load4<S>(&cur4[i]);
         const Vec4T<S> qi = load4<S>(&quat[i]);
@@ -507,7 +525,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(int n, const int *__rest
             const double dz = (double)ci.z - (double)cj.z - (ri[6] * ex + ri[7] * ey + ri[8] * ez);
             e += (double)weight[k] * (dx * dx + dy * dy + dz * dz);
         }
-        red[0] = e;
+        red[0] += e;
     }
     double total[1];
     if (grid_sum_last_block<1>(red, partials, counter, total)) *energy_out = total[0];

@@ -18,7 +18,7 @@ namespace arap {
 template <typename S>
 __device__ __forceinline__ Vec3d fine_apply_row(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                 const S *__restrict__ weight, const Vec3d *__restrict__ x) {
-    constexpr int CH = 6;
+    constexpr int CH = kSpmvChunk;
     const int k0 = rowptr[i], k1 = rowptr[i + 1];
     const Vec3d xi = x[i];
     Vec3d out = {0, 0, 0};
@@ -34,7 +34,9 @@ __device__ __forceinline__ Vec3d fine_apply_row(int i, const int *__restrict__ r
         Vec3d xj[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) xj[u] = x[j[u]];
-        pin_loaded(xj);
+        const double gate = gather_gate(xj);
+#pragma unroll
+        for (int u = 0; u < CH; ++u) w[u] += gate;
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             out.x += w[u] * (xi.x - xj[u].x); out.y += w[u] * (xi.y - xj[u].y); out.z += w[u] * (xi.z - xj[u].z);
@@ -70,16 +72,15 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
                                                                     Vec3d *__restrict__ z, double *__restrict__ partials,
                                                                     unsigned *__restrict__ counter, CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[3] = {0, 0, 0};
-    if (i < n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Vec3d out = {0, 0, 0};
         if (rest4[i].w != S(0)) {
             const Vec3d ax = fine_apply_row<S>(i, rowptr, colidx, weight, x);
             const Vec3d bi = b[i], xi = x[i];
             const double s = omega * inv_diag[i];
             out.x = xi.x + s * (bi.x - ax.x); out.y = xi.y + s * (bi.y - ax.y); out.z = xi.z + s * (bi.z - ax.z);
-            red[0] = bi.x * out.x; red[1] = bi.y * out.y; red[2] = bi.z * out.z;
+            red[0] += bi.x * out.x; red[1] += bi.y * out.y; red[2] += bi.z * out.z;
         }
         z[i] = out;
     }
@@ -212,10 +213,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n3, const doub
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     double red[1] = {0};
-    if (e < n3) {
-        const double al0 = cg->alpha[0], al1 = cg->alpha[1], al2 = cg->alpha[2];
+    const double al0 = cg->alpha[0], al1 = cg->alpha[1], al2 = cg->alpha[2];
+    for (int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x); e < n3; e += 2 * gridDim.x * blockDim.x) {
         if (e + 1 < n3) {
             const double2 dv = *reinterpret_cast<const double2 *>(d + e), av = *reinterpret_cast<const double2 *>(ad + e);
             double2 xv = *reinterpret_cast<const double2 *>(x + e), rv = *reinterpret_cast<const double2 *>(r + e);
@@ -227,13 +227,13 @@ __global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n3, const doub
             *reinterpret_cast<double2 *>(r + e) = rv;
             const double s0 = omega0 * inv_diag[e / 3], s1 = omega0 * inv_diag[(e + 1) / 3];
             *reinterpret_cast<double2 *>(x0 + e) = make_double2(s0 * rv.x, s1 * rv.y);
-            red[0] = rv.x * rv.x + rv.y * rv.y;
+            red[0] += rv.x * rv.x + rv.y * rv.y;
         } else {
             const double a0 = pick3(e % 3, al0, al1, al2);
             const double xv = x[e] + a0 * d[e], rv = r[e] - a0 * ad[e];
             x[e] = xv; r[e] = rv;
             x0[e] = omega0 * inv_diag[e / 3] * rv;
-            red[0] = rv * rv;
+            red[0] += rv * rv;
         }
     }
     double total[1];
