@@ -60,8 +60,9 @@ typedef struct arap_options {
     int32_t device;             /* CUDA device ordinal, -1 = current device */
     int32_t solver;             /* ARAP_SOLVER_* */
     int32_t max_cg_iterations;  /* per global step; <= 0 -> default */
-    double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> default 1e-7
-                                 * (measured: 1e-7 keeps positions within ~2e-9 x bbox diagonal of a direct solve) */
+    double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> per-solver default:
+                                 * 1e-6 with the multigrid preconditioner (measured: positions within ~2e-8 x bbox diagonal of a
+                                 * direct solve after 20 iterations), 1e-9 with plain Jacobi */
     int32_t cg_check_interval;  /* CG iterations between convergence polls; <= 0 -> default */
     int32_t profile;            /* != 0: time every kernel launch with CUDA events (see arap_profile_*) */
 } arap_options;
@@ -144,6 +145,24 @@ const char *arap_kernel_name(int32_t kernel_id);
 int arap_timer_start(arap_handle *h);
 int arap_timer_stop(arap_handle *h, double *milliseconds);
 int arap_synchronize(arap_handle *h);
+
+/* ---- batches of independent deformations of ONE mesh (BASELINE.json configs[3]) ------------------------------
+ * K members share topology, rest pose and the SET of constrained vertices; only the targets differ (one pose
+ * per key frame). Replaces the "fresh mesh copy + fresh solver per pose" loop of the reference's
+ * examples/deform_example.cpp:37-53. All members advance together in one set of kernel launches: the batch is
+ * solved as one block-diagonal system (the members' one-rings never touch), so every kernel of the single-mesh
+ * path is reused unchanged. Results are per member, laid out [member][vertex][xyz]. */
+typedef struct arap_batch arap_batch;
+int arap_batch_create(const int32_t *faces, int32_t n_faces, int32_t n_vertices, int32_t batch_size, int32_t precision_bytes,
+                      const arap_options *opt, arap_batch **out);
+void arap_batch_destroy(arap_batch *b);
+/* n constrained vertices (the same in every member); xyz: batch_size x n x 3 targets. */
+int arap_batch_set_constraints(arap_batch *b, int32_t n, const int32_t *vertex_idx, const void *xyz, int32_t xyz_scalar_bytes);
+int arap_batch_prepare(arap_batch *b, const void *rest_xyz /* V x 3, shared */, int32_t rest_scalar_bytes);
+int arap_batch_iterate(arap_batch *b, int32_t n_iterations);
+int arap_batch_get_positions(arap_batch *b, void *out_xyz /* batch_size x V x 3 */, int32_t out_scalar_bytes);
+/* The underlying handle (statistics, profiling, timers, total energy over all members). */
+arap_handle *arap_batch_handle(arap_batch *b);
 
 /* Page-locked host memory for mesh buffers handed to arap_deform / arap_prepare / arap_get_positions
  * (optional: pageable memory works too, pinned memory makes the copies run at full PCIe rate). */

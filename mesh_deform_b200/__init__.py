@@ -6,4 +6,4 @@ This Python package is only a ctypes binding of that C ABI (used by tests and be
 synthetic workload generators. There is no CPU fallback anywhere in the package.
 """
 from . import capi, meshgen  # noqa: F401
-from .capi import AsRigidAsPossibleDeformation, ArapError, EngineMissingError  # noqa: F401
+from .capi import AsRigidAsPossibleDeformation, ArapError, BatchDeformation, EngineMissingError  # noqa: F401

@@ -31,7 +31,8 @@ EXPORTED_SYMBOLS = (
     "arap_get_free_map", "arap_get_rotations", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
     "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
-    "arap_abi_version",
+    "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
+    "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle",
 )
 
 
@@ -94,6 +95,15 @@ def lib():
     L.arap_timer_start.argtypes = [vp]
     L.arap_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.arap_synchronize.argtypes = [vp]
+    L.arap_batch_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(Options), C.POINTER(vp)]
+    L.arap_batch_destroy.argtypes = [vp]
+    L.arap_batch_destroy.restype = None
+    L.arap_batch_set_constraints.argtypes = [vp, i32, vp, vp, i32]
+    L.arap_batch_prepare.argtypes = [vp, vp, i32]
+    L.arap_batch_iterate.argtypes = [vp, i32]
+    L.arap_batch_get_positions.argtypes = [vp, vp, i32]
+    L.arap_batch_handle.argtypes = [vp]
+    L.arap_batch_handle.restype = vp
     L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.arap_host_free.argtypes = [vp]
     L.arap_last_error.argtypes = [vp]
@@ -274,3 +284,72 @@ class AsRigidAsPossibleDeformation:
 
     def synchronize(self):
         self._check(lib().arap_synchronize(self._h))
+
+
+class BatchDeformation:
+    """K independent deformations of one mesh advanced together (C ABI arap_batch_*): same topology, rest pose and
+    constrained vertex set, per-member targets -- BASELINE.json configs[3] (one member per trajectory key frame)."""
+
+    def __init__(self, rest_positions, faces, batch_size, precision=np.float64, **options):
+        self.rest = np.ascontiguousarray(rest_positions, dtype=np.float64)
+        self.faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+        self.real = np.dtype(precision)
+        self.nV, self.K = self.rest.shape[0], int(batch_size)
+        opt = default_options()
+        for k, v in options.items():
+            setattr(opt, k, v)
+        self._b = C.c_void_p()
+        rc = lib().arap_batch_create(_ptr(self.faces), self.faces.shape[0], self.nV, self.K, self.real.itemsize, C.byref(opt),
+                                     C.byref(self._b))
+        if rc != ARAP_OK:
+            self._b = None
+            raise ArapError(rc, lib().arap_create_error().decode())
+        self._h = C.c_void_p(lib().arap_batch_handle(self._b))
+
+    def close(self):
+        if getattr(self, "_b", None):
+            lib().arap_batch_destroy(self._b)
+            self._b = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ArapError(rc, lib().arap_last_error(self._h).decode())
+        return rc
+
+    def setConstraints(self, indices, targets):
+        """indices: (n,), targets: (K, n, 3)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        tgt = np.ascontiguousarray(targets, dtype=np.float64)
+        assert tgt.shape == (self.K, idx.size, 3)
+        self._check(lib().arap_batch_set_constraints(self._b, idx.size, _ptr(idx), _ptr(tgt), 8))
+
+    def prepare(self):
+        return self._check(lib().arap_batch_prepare(self._b, _ptr(self.rest), 8))
+
+    def iterate(self, n):
+        return self._check(lib().arap_batch_iterate(self._b, int(n)))
+
+    def positions(self, dtype=np.float64):
+        out = np.zeros((self.K, self.nV, 3), dtype)
+        self._check(lib().arap_batch_get_positions(self._b, _ptr(out), out.dtype.itemsize))
+        return out
+
+    def total_energy(self):
+        e = C.c_double()
+        self._check(lib().arap_energy(self._h, C.byref(e)))
+        return e.value
+
+    def solver_stats(self):
+        s = SolverStats()
+        self._check(lib().arap_get_solver_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in SolverStats._fields_}
+
+    def timer_start(self):
+        self._check(lib().arap_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(lib().arap_timer_stop(self._h, C.byref(ms)))
+        return ms.value

@@ -41,7 +41,7 @@ def test_library_is_sm100a_only():
 def test_default_options_and_argument_validation():
     from mesh_deform_b200 import capi
     o = capi.default_options()
-    assert o.struct_size == C.sizeof(capi.Options) and o.device == -1 and o.cg_tolerance > 0
+    assert o.struct_size == C.sizeof(capi.Options) and o.device == -1 and o.cg_tolerance == 0
     lib = capi.lib()
     h = C.c_void_p()
     faces = np.array([[0, 1, 5]], np.int32)     # vertex 5 out of range for V = 3

@@ -251,3 +251,49 @@ def test_midsize_grid_parity_mg():
     de = abs(a.energy() - o.energy()) / o.energy()
     print("grid", n, "err/diag", err, "rel dE", de, a.solver_stats())
     assert err <= POS_TOL and de <= E_TOL
+
+
+def sphere_trajectory():
+    """BASELINE.json configs[3] / SURVEY.md section 8d config 4: poses from the SE(3) trajectory through the key poses of
+    reference examples/deform_trajectory.cpp:66-69 with the translations scaled by 0.25."""
+    def T(t=(0, 0, 0), R=np.eye(3)):
+        M = np.eye(4)
+        M[:3, :3] = R
+        M[:3, 3] = t
+        return M
+    traj = O.TrajectorySE3Oracle()
+    prev = np.eye(4)
+    traj.addKeyPose(prev)
+    prev = prev @ T((0.25, 0, 0))
+    traj.addKeyPose(prev)
+    prev = prev @ T((0.5, 0, 0))
+    traj.addKeyPose(prev)
+    prev = prev @ T(R=G.rot_x(np.pi / 2))
+    traj.addKeyPose(prev)
+    return traj
+
+
+def test_batch_of_sphere_deformations_matches_oracle(meshes):
+    P, F = meshes["sphere"]
+    K = 6
+    handles = np.sort(np.unique(F[(F == G.SPHERE_HANDLE).any(1)]))          # v32 and its one-ring
+    idx = np.concatenate([[G.SPHERE_ANCHOR], handles]).astype(np.int32)
+    traj = sphere_trajectory()
+    origin = traj(0.0)
+    targets = np.zeros((K, idx.size, 3))
+    for k in range(K):
+        pose = traj(k / (K - 1))
+        targets[k, 0] = P[G.SPHERE_ANCHOR]
+        targets[k, 1:] = O.handle_targets(origin, pose, P[handles])
+    b = capi.BatchDeformation(P, F, K, np.float64)
+    b.setConstraints(idx, targets)
+    assert b.prepare() == capi.ARAP_OK
+    b.iterate(10)
+    pos = b.positions()
+    diag = bbox_diag(P)
+    for k in range(K):
+        mesh = P.copy()
+        o = O.ArapOracle(mesh, F, np.float64)
+        constrain(o, idx, targets[k])
+        assert o.deform(10)
+        assert np.abs(pos[k] - mesh).max() <= POS_TOL * diag, k
