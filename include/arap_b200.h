@@ -130,7 +130,7 @@ enum {
     ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC,
     ARAP_K_MG_FINE_RESIDUAL, ARAP_K_MG_FINE_POSTSMOOTH, ARAP_K_MG_CSR_RESIDUAL, ARAP_K_MG_RESTRICT, ARAP_K_MG_PROLONG,
     ARAP_K_MG_CSR_POSTSMOOTH, ARAP_K_MG_DENSE_SOLVE, ARAP_K_CG_UPDATE_MG, ARAP_K_CG_DIRECTION_MG, ARAP_K_CG_DOT,
-    ARAP_K_COUNT_MAX = 32
+    ARAP_K_HALO_PACK, ARAP_K_CG_FINALIZE, ARAP_K_COUNT_MAX = 32
 };
 typedef struct arap_profile {
     int64_t launches[ARAP_K_COUNT_MAX];
@@ -163,6 +163,27 @@ int arap_batch_iterate(arap_batch *b, int32_t n_iterations);
 int arap_batch_get_positions(arap_batch *b, void *out_xyz /* batch_size x V x 3 */, int32_t out_scalar_bytes);
 /* The underlying handle (statistics, profiling, timers, total energy over all members). */
 arap_handle *arap_batch_handle(arap_batch *b);
+
+/* ---- one mesh partitioned over several GPUs (BASELINE.json configs[4]) ------------------------------------------
+ * Every rank creates an ordinary handle for ITS local mesh: the vertices it owns first (local indices
+ * [0, n_owned)), then its halo (one-ring neighbours owned by other ranks, grouped by owner), and every face that
+ * touches an owned vertex. arap_attach_partition (before arap_prepare) tells the engine who owns what; from then on
+ * arap_prepare / arap_iterate / arap_get_positions work as usual on the local mesh, exchanging the halo of p', R and
+ * the CG direction and all-reducing the CG's dot products through the chosen transport. The reference has no
+ * counterpart (single-threaded CPU code); the partition itself is made by the caller (mesh_deform_b200/partition.py). */
+enum { ARAP_TRANSPORT_NCCL = 0,        /* one process per GPU; id = the 128 bytes from arap_comm_unique_id, broadcast by the caller */
+       ARAP_TRANSPORT_IN_PROCESS = 1   /* several partitions on one GPU, one host thread per partition; id = an int32 group key */ };
+typedef struct arap_partition_plan {
+    int32_t n_owned;                /* owned vertices come first in the local numbering */
+    int32_t n_neighbors;
+    const int32_t *neighbor_rank;   /* [n_neighbors] */
+    const int32_t *send_offset;     /* [n_neighbors + 1] into send_index */
+    const int32_t *send_index;      /* owned local indices to send, grouped by neighbour, in the receiver's halo order */
+    const int32_t *recv_offset;     /* [n_neighbors + 1]: halo from neighbour k = local indices n_owned + recv_offset[k] ... */
+} arap_partition_plan;
+int arap_comm_unique_id(void *out_bytes, int32_t capacity /* >= 128 */);
+int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32_t rank, int32_t world_size, int32_t transport,
+                          const void *id, int32_t id_bytes);
 
 /* Page-locked host memory for mesh buffers handed to arap_deform / arap_prepare / arap_get_positions
  * (optional: pageable memory works too, pinned memory makes the copies run at full PCIe rate). */

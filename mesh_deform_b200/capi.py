@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = (
     "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
     "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
-    "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle",
+    "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle", "arap_comm_unique_id", "arap_attach_partition",
 )
 
 
@@ -46,6 +46,14 @@ class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
                 ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
                 ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double)]
+
+
+class PartitionPlan(C.Structure):
+    _fields_ = [("n_owned", C.c_int32), ("n_neighbors", C.c_int32), ("neighbor_rank", C.c_void_p), ("send_offset", C.c_void_p),
+                ("send_index", C.c_void_p), ("recv_offset", C.c_void_p)]
+
+
+TRANSPORT_NCCL, TRANSPORT_IN_PROCESS = 0, 1
 
 
 class Profile(C.Structure):
@@ -104,6 +112,8 @@ def lib():
     L.arap_batch_get_positions.argtypes = [vp, vp, i32]
     L.arap_batch_handle.argtypes = [vp]
     L.arap_batch_handle.restype = vp
+    L.arap_comm_unique_id.argtypes = [vp, i32]
+    L.arap_attach_partition.argtypes = [vp, C.POINTER(PartitionPlan), i32, i32, i32, vp, i32]
     L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.arap_host_free.argtypes = [vp]
     L.arap_last_error.argtypes = [vp]
@@ -353,3 +363,80 @@ class BatchDeformation:
         ms = C.c_double()
         self._check(lib().arap_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (call on rank 0, broadcast to the other ranks, e.g. with torch.distributed)."""
+    buf = np.zeros(128, np.uint8)
+    rc = lib().arap_comm_unique_id(_ptr(buf), 128)
+    if rc != ARAP_OK:
+        raise ArapError(rc, lib().arap_create_error().decode())
+    return buf
+
+
+class PartitionedDeformation:
+    """One rank's share of a mesh partitioned over several GPUs (C ABI arap_attach_partition).
+
+    positions/faces are the GLOBAL mesh (every rank holds it on the host); `owner` maps vertex -> rank
+    (mesh_deform_b200.partition.strip_owner). transport: TRANSPORT_NCCL (one process per GPU, comm_id = the broadcast
+    128-byte unique id) or TRANSPORT_IN_PROCESS (several partitions on one GPU driven by one host thread each,
+    comm_id = an int group key) -- the latter is how the single-GPU test tier runs the very same solver code path.
+    """
+
+    def __init__(self, positions, faces, owner, rank, world, transport, comm_id, precision=np.float64, **options):
+        from . import partition as part_mod
+        self.part = part_mod.build_local_part(faces, owner, rank, world)
+        self.global_rest = np.asarray(positions, dtype=np.float64)
+        self.local_mesh = np.ascontiguousarray(self.global_rest[self.part.local_to_global], dtype=np.dtype(precision))
+        self.arap = AsRigidAsPossibleDeformation(self.local_mesh, self.part.faces, precision, **options)
+        pl = self.part
+        self._keep = [np.ascontiguousarray(a, dtype=np.int32) for a in (pl.neighbor_rank, pl.send_offset, pl.send_index, pl.recv_offset)]
+        plan = PartitionPlan(pl.n_owned, int(pl.neighbor_rank.size), *[a.ctypes.data for a in self._keep])
+        if transport == TRANSPORT_NCCL:
+            ident = np.ascontiguousarray(comm_id, dtype=np.uint8)
+        else:
+            ident = np.array([int(comm_id)], np.int32)
+        self.arap._check(lib().arap_attach_partition(self.arap._h, C.byref(plan), rank, world, transport, _ptr(ident), ident.nbytes))
+
+    def setConstraints(self, global_indices, targets):
+        from . import partition as part_mod
+        idx, tgt = part_mod.local_constraints(self.part, global_indices, targets)
+        if idx.size:
+            self.arap.setConstraints(idx, tgt)
+
+    def prepare(self):
+        return self.arap.prepare()
+
+    def iterate(self, n):
+        return self.arap.iterate(n)
+
+    def owned_positions(self, dtype=np.float64):
+        """(global vertex ids, positions) of the vertices this rank owns."""
+        return self.part.owned_global, self.arap.positions(dtype)[:self.part.n_owned]
+
+    def local_energy(self):
+        return self.arap.energy()
+
+    def solver_stats(self):
+        return self.arap.solver_stats()
+
+
+def run_partitions_in_process(workers):
+    """Run one callable per partition concurrently (one host thread each; ctypes releases the GIL inside the C ABI).
+    Exceptions are re-raised. Used with TRANSPORT_IN_PROCESS."""
+    import threading
+    errors = [None] * len(workers)
+
+    def wrap(k, fn):
+        try:
+            fn()
+        except BaseException as exc:      # noqa: BLE001
+            errors[k] = exc
+    threads = [threading.Thread(target=wrap, args=(k, fn)) for k, fn in enumerate(workers)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_setup.h"
+#include "partition.cuh"
 
 #include <cuda_runtime.h>
 
@@ -28,7 +29,7 @@ static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
     "cg_update", "cg_direction", "apply_update", "energy", "misc",
     "mg_fine_residual", "mg_fine_postsmooth", "mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add",
-    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot"};
+    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize"};
 
 static thread_local std::string g_create_error;
 
@@ -85,6 +86,7 @@ public:
     virtual int get_free_map(int *free_idx, int *n_free) = 0;
     virtual int get_rotations(void *rot9) = 0;
     virtual int energy(double *e) = 0;
+    virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
 
     int fail(int code, const std::string &msg) {
         last_error = msg;
@@ -228,6 +230,12 @@ public:
     DeviceBuffer<double> mg_coarse_inv;
     bool mg_dense = false;
     bool use_mg = false;
+    // partitioned mode (partition.cuh): rows [0, n_rows) are owned, [n_rows, n_vertices) is the halo
+    int n_rows = 0;
+    HaloPlan plan;
+    DeviceBuffer<int> send_index_dev;
+    DeviceBuffer<unsigned char> halo_sendbuf;
+    std::unique_ptr<Transport> transport;
     cudaGraph_t cg_graph = nullptr;                // one CG iteration (preconditioner included), replayed per iteration
     cudaGraphExec_t cg_graph_exec = nullptr;
     bool have_warm_rotations = false;              // quat[] holds the previous iteration's R_i
@@ -404,12 +412,15 @@ public:
                    rowptr.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr);
         ARAP_CUDA(cudaGetLastError());
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        if (n_free == V) return ARAP_UNCONSTRAINED;                      // arap.h:113-114: stays dirty, nothing solved
+        n_rows = transport ? plan.n_owned : V;
+        if (n_free == V && !transport) return ARAP_UNCONSTRAINED;        // arap.h:113-114: stays dirty, nothing solved
         // ---- setupLinearSystem (arap.h:292-340): matrix-free L, nothing to factor; allocate the CG vectors
         ARAP_CUDA(cg_r.ensure((size_t)V));
         ARAP_CUDA(cg_d.ensure((size_t)V));
         ARAP_CUDA(cg_ad.ensure((size_t)V));
         ARAP_CUDA(cg_x.ensure((size_t)V));
+        for (Vec3d *vec : {cg_r.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr})                                  // halo slots must start finite
+            ARAP_CUDA(cudaMemsetAsync(vec, 0, sizeof(Vec3d) * (size_t)(V > 0 ? V : 1), stream));
         use_mg = (opt.solver != ARAP_SOLVER_PCG_JACOBI);
         if (use_mg) { int rc = setup_multigrid(); if (rc) return rc; }
         CgScalars init;
@@ -418,13 +429,73 @@ public:
         // positions within ~2e-8 x bbox diagonal of a direct solve, measured); plain Jacobi needs a much smaller one.
         const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : (use_mg ? 1e-6 : 1e-9);
         init.tol2 = tol * tol;
+        init.distributed = transport ? 1 : 0;
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        { int rc = build_cg_graph(); if (rc) return rc; }
+        if (transport) destroy_cg_graph();                                // collectives are issued from the host between kernels
+        else { int rc = build_cg_graph(); if (rc) return rc; }
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
+        return ARAP_OK;
+    }
+
+    // ---- partitioned mode ----------------------------------------------------------------------------------------
+    int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) override {
+        if (!p || p->n_owned < 0 || p->n_owned > n_vertices || p->n_neighbors < 0 || world <= 0 || rank < 0 || rank >= world)
+            return fail(ARAP_ERR_INVALID, "attach_partition: bad arguments");
+        plan = HaloPlan();
+        plan.n_owned = p->n_owned;
+        plan.neighbor_rank.assign(p->neighbor_rank, p->neighbor_rank + p->n_neighbors);
+        plan.send_offset.assign(p->send_offset, p->send_offset + p->n_neighbors + 1);
+        plan.recv_offset.assign(p->recv_offset, p->recv_offset + p->n_neighbors + 1);
+        plan.send_index.assign(p->send_index, p->send_index + plan.send_offset.back());
+        if (plan.n_owned + plan.n_halo() != n_vertices) return fail(ARAP_ERR_INVALID, "attach_partition: n_owned + halo != local vertex count");
+        for (int v : plan.send_index) if (v < 0 || v >= plan.n_owned) return fail(ARAP_ERR_INVALID, "attach_partition: send index is not an owned vertex");
+        ARAP_CUDA(upload_vector(send_index_dev, plan.send_index, stream));
+        ARAP_CUDA(halo_sendbuf.ensure((size_t)(plan.n_send() > 0 ? plan.n_send() : 1) * 32));
+        if (kind == ARAP_TRANSPORT_NCCL) {
+            if (!id || id_bytes < 128) return fail(ARAP_ERR_INVALID, "attach_partition: NCCL needs the 128-byte unique id");
+            std::unique_ptr<NcclTransport> t(new NcclTransport());
+            if (t->init(rank, world, id)) return fail(ARAP_ERR_CUDA, t->error);
+            transport = std::move(t);
+        } else if (kind == ARAP_TRANSPORT_IN_PROCESS) {
+            if (!id || id_bytes < 4) return fail(ARAP_ERR_INVALID, "attach_partition: in-process transport needs an int32 group key");
+            std::unique_ptr<LocalTransport> t(new LocalTransport());
+            if (t->init(rank, world, *(const int32_t *)id)) return fail(ARAP_ERR_INVALID, t->error);
+            transport = std::move(t);
+        } else {
+            return fail(ARAP_ERR_INVALID, "attach_partition: unknown transport");
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        dirty = true;
+        prepared = false;
+        return ARAP_OK;
+    }
+
+    // refresh the halo slots of a per-vertex array from their owners (no-op on a single GPU)
+    int exchange_halo(void *array, size_t elem_bytes) {
+        if (!transport) return ARAP_OK;
+        const int words = (int)(elem_bytes / 8), n = plan.n_send();
+        if (n > 0) {
+            begin_launch(ARAP_K_HALO_PACK);
+            halo_pack_kernel<<<(n * words + 255) / 256, 256, 0, stream>>>(n, words, send_index_dev.ptr, (const unsigned long long *)array,
+                                                                          (unsigned long long *)halo_sendbuf.ptr);
+            end_launch();
+        }
+        if (transport->exchange(stream, plan, (const char *)halo_sendbuf.ptr, (char *)array, elem_bytes)) return fail(ARAP_ERR_CUDA, transport->error);
+        return ARAP_OK;
+    }
+
+    // partitioned mode: sum the stage's partial sums over the ranks, then finish the stage (alpha / beta / convergence)
+    int reduce_stage(int stage, int n_values) {
+        if (!transport) return ARAP_OK;
+        double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
+        if (transport->allreduce_sum(stream, red, n_values)) return fail(ARAP_ERR_CUDA, transport->error);
+        begin_launch(ARAP_K_CG_FINALIZE);
+        cg_finalize_kernel<<<1, 1, 0, stream>>>(cg.ptr, stage);
+        end_launch();
         return ARAP_OK;
     }
 
@@ -442,6 +513,7 @@ public:
         }
         if (V > 0) ARAP_CUDA(cudaMemcpyAsync(h_con.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        for (int v = n_rows; v < V; ++v) h_con[(size_t)v] = 1;      // partitioned mode: block-Jacobi across ranks, halo = Dirichlet
         MgHierarchyHost H;
         MgSetupOptions mo;
         mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H);
@@ -469,6 +541,8 @@ public:
             }
             ARAP_CUDA(d->x.ensure((size_t)d->n));
             ARAP_CUDA(d->x2.ensure((size_t)d->n));
+            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(Vec3d) * (size_t)(d->n > 0 ? d->n : 1), stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(Vec3d) * (size_t)(d->n > 0 ? d->n : 1), stream));
             d->a_lanes = pick_lanes(hl.A.colidx.size(), (size_t)hl.A.n_rows);
             d->r_lanes = pick_lanes(hl.R.colidx.size(), (size_t)hl.R.n_rows);
             mg.push_back(std::move(d));
@@ -485,28 +559,27 @@ public:
     // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
     // Buffer roles are fixed (no pointer swapping) so that the launch sequence can be captured in a CUDA graph:
     // on every level x = iterate before post-smoothing, x2 = the level's result; level 0's result is z = mg[0]->x2.
-    void vcycle() {
-        const int V = n_vertices;
+    int vcycle() {
+        const int R = n_rows;                 // owned rows (== n_vertices on a single GPU)
         const int L = (int)mg.size();
         MgLevelDev &m0 = *mg[0];
         Vec3d *z = m0.x2.ptr;
         if (L == 1) {
             if (mg_dense) {
-                LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (V + kWarpsPerBlock - 1) / kWarpsPerBlock, V, mg_coarse_inv.ptr,
+                LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (m0.n + kWarpsPerBlock - 1) / kWarpsPerBlock, m0.n, mg_coarse_inv.ptr,
                        cg_r.ptr, z, cg.ptr);
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                ARAP_DISPATCH_LANES(1, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)V * LN), V,
+                ARAP_DISPATCH_LANES(1, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)m0.n * LN), m0.n,
                                               m0.a_rowptr.ptr, m0.a_colidx.ptr, m0.a_val.ptr, m0.inv_diag.ptr, 0.0, cg_r.ptr, m0.x.ptr, z, cg.ptr));
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)V), V, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             }
-            return;
+            LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+            return reduce_stage(CG_STAGE_RHO, 3);
         }
         // down
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr,
+                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr,
                        rest4.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
@@ -529,10 +602,11 @@ public:
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
-            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)f.n), f.n, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+            const int rows = (l == 0) ? R : f.n;
+            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr,
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr,
                        weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
@@ -540,27 +614,35 @@ public:
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
+        return reduce_stage(CG_STAGE_RHO, 3);
     }
 
-    void cg_iteration_jacobi() {
-        const int V = n_vertices, G = grid_for((size_t)V);
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+    int cg_iteration_jacobi() {
+        const int R = n_rows;
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
                partials.ptr, counter.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)V), V, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
+        { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
+        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)R), R, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
                counter.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, G, V, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+        { int rc = reduce_stage(CG_STAGE_UPDATE_JACOBI, 4); if (rc) return rc; }
+        LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, grid_for((size_t)R), R, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+        return ARAP_OK;
     }
 
-    void cg_iteration_mg() {
-        const int V = n_vertices, G = grid_for((size_t)V);
-        const int n3 = 3 * V, G3 = grid_for(((size_t)n3 + 1) / 2);
+    int cg_iteration_mg() {
+        const int R = n_rows;
+        const int n3 = 3 * R, G3 = grid_for(((size_t)n3 + 1) / 2);
         MgLevelDev &m0 = *mg[0];
-        vcycle();
+        { int rc = vcycle(); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const double *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
+        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
                partials.ptr, counter.ptr, cg.ptr);
+        { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
                (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (double *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+        return reduce_stage(CG_STAGE_UPDATE_MG, 1);
     }
 
     // Capture one CG iteration into a CUDA graph: ~20 small launches collapse into one graph launch.
@@ -569,10 +651,10 @@ public:
         std::memset(graph_counts, 0, sizeof(graph_counts));
         ARAP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         capturing = true;
-        if (use_mg) cg_iteration_mg(); else cg_iteration_jacobi();
+        const int rc_body = use_mg ? cg_iteration_mg() : cg_iteration_jacobi();
         capturing = false;
         cudaError_t e = cudaStreamEndCapture(stream, &cg_graph);
-        if (e != cudaSuccess) { cg_graph = nullptr; return fail(ARAP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+        if (e != cudaSuccess || rc_body) { cg_graph = nullptr; return fail(ARAP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
         ARAP_CUDA(cudaGraphInstantiate(&cg_graph_exec, cg_graph, 0));
         return ARAP_OK;
     }
@@ -582,22 +664,24 @@ public:
             for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) profile.launches[k] += graph_counts[k];
             ARAP_CUDA(cudaGraphLaunch(cg_graph_exec, stream));
         } else if (use_mg) {
-            cg_iteration_mg();
+            return cg_iteration_mg();
         } else {
-            cg_iteration_jacobi();
+            return cg_iteration_jacobi();
         }
         return ARAP_OK;
     }
 
     int global_step() {
-        const int V = n_vertices, G = grid_for((size_t)V);
+        const int R = n_rows, G = grid_for((size_t)R);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+            { int rc = reduce_stage(CG_STAGE_START_MG, 5); if (rc) return rc; }
         } else {
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+            { int rc = reduce_stage(CG_STAGE_START_JACOBI, 5); if (rc) return rc; }
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
         int check = opt.cg_check_interval > 0 ? opt.cg_check_interval : 32;
@@ -627,7 +711,8 @@ public:
             if (issued >= max_it || batch == 0) done = true;
             slot ^= 1;
         }
-        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, V, rest4.ptr, cg_x.ptr, cur4.ptr);
+        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, R, rest4.ptr, cg_x.ptr, cur4.ptr);
+        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
         ARAP_CUDA(cudaGetLastError());
@@ -642,12 +727,12 @@ public:
 
     int iterate(int n) override {
         if (!prepared) return fail(ARAP_ERR_INVALID, "iterate: arap_prepare has not succeeded");
-        const int V = n_vertices, G = grid_for((size_t)V);
+        const int R = n_rows, G = grid_for((size_t)R);
         for (int it = 0; it < n; ++it) {
             // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the warm
             // kernel certifies convergence to the SVD's rotation per vertex and falls back to the Jacobi SVD otherwise.
-            LAUNCH(ARAP_K_LOCAL_STEP, (local_step_kernel<S, true>), G, V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
-            have_warm_rotations = true;
+            LAUNCH(ARAP_K_LOCAL_STEP, (local_step_kernel<S, true>), G, R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
+            { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
             int rc = global_step();
             if (rc) return rc;
         }
@@ -701,7 +786,7 @@ public:
     }
     int energy(double *e) override {
         if (!quat.ptr || !rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
-        const int V = n_vertices;
+        const int V = prepared ? n_rows : n_vertices;      // partitioned mode: this rank's share (owned rows)
         LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, reduce_grid(energy_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
                partials.ptr, counter.ptr, energy_dev.ptr);
         ARAP_CUDA(cudaMemcpyAsync(e, energy_dev.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -966,6 +1051,23 @@ int arap_batch_iterate(arap_batch *b, int32_t n_iterations) { return b ? arap_it
 
 int arap_batch_get_positions(arap_batch *b, void *out_xyz, int32_t out_scalar_bytes) {
     return b ? arap_get_positions(b->handle, out_xyz, out_scalar_bytes) : ARAP_ERR_INVALID;
+}
+
+int arap_comm_unique_id(void *out_bytes, int32_t capacity) {
+    if (!out_bytes || capacity < 128) return ARAP_ERR_INVALID;
+    std::string err;
+    arap::NcclApi *api = arap::NcclApi::get(&err);
+    if (!api) { arap::g_create_error = err; return ARAP_ERR_CUDA; }
+    arap::NcclApi::UniqueId id;
+    if (api->GetUniqueId(&id) != 0) return ARAP_ERR_CUDA;
+    std::memcpy(out_bytes, &id, 128);
+    return ARAP_OK;
+}
+
+int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32_t rank, int32_t world_size, int32_t transport,
+                          const void *id, int32_t id_bytes) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->attach_partition(plan, rank, world_size, transport, id, id_bytes);
 }
 
 int arap_host_alloc(size_t bytes, void **out) {

@@ -283,10 +283,67 @@ struct CgScalars {
     double rr;           // |r|^2 over the three coordinates
     double ref2;         // |rhs|^2 over the three coordinates
     double tol2;         // tolerance^2
+    double red[8];       // partitioned mode: this rank's partial sums, all-reduced in place before cg_finalize_kernel
     int converged;
     int iterations;
-    int pad[2];
+    int distributed;     // != 0: reduction kernels only deposit their sums in red[]; cg_finalize_kernel finishes the stage
+    int pad;
 };
+
+// What each grid-wide reduction of the CG turns into. On one GPU the last CTA of the reducing kernel calls this
+// directly; in partitioned mode the sums first go through an all-reduce over the ranks (see partition.cuh).
+enum CgStage { CG_STAGE_START_JACOBI = 0, CG_STAGE_START_MG, CG_STAGE_ALPHA, CG_STAGE_UPDATE_JACOBI, CG_STAGE_UPDATE_MG, CG_STAGE_RHO };
+
+__device__ __forceinline__ void cg_finalize(CgScalars *cg, int stage, const double *t) {
+    switch (stage) {
+        case CG_STAGE_START_JACOBI:      // t = rho x,y,z ; |r|^2 ; |rhs|^2
+        case CG_STAGE_START_MG:
+            for (int c = 0; c < 3; ++c) cg->rho[c] = (stage == CG_STAGE_START_MG) ? 0.0 : t[c];
+            cg->rr = t[3];
+            cg->ref2 = t[4];
+            cg->iterations = 0;
+            cg->converged = (t[3] <= cg->tol2 * t[4]) ? 1 : 0;
+            break;
+        case CG_STAGE_ALPHA:             // t = d.Ad per coordinate
+            for (int c = 0; c < 3; ++c) cg->alpha[c] = (t[c] > 0.0) ? cg->rho[c] / t[c] : 0.0;
+            break;
+        case CG_STAGE_UPDATE_JACOBI:     // t = r.D^-1 r per coordinate ; |r|^2
+            for (int c = 0; c < 3; ++c) {
+                cg->beta[c] = (cg->rho[c] > 0.0) ? t[c] / cg->rho[c] : 0.0;
+                cg->rho[c] = t[c];
+            }
+            cg->rr = t[3];
+            cg->iterations += 1;
+            if (t[3] <= cg->tol2 * cg->ref2) cg->converged = 1;
+            break;
+        case CG_STAGE_UPDATE_MG:         // t = |r|^2
+            cg->rr = t[0];
+            cg->iterations += 1;
+            if (t[0] <= cg->tol2 * cg->ref2) cg->converged = 1;
+            break;
+        case CG_STAGE_RHO:               // t = r.z per coordinate
+            for (int c = 0; c < 3; ++c) {
+                cg->beta[c] = (cg->rho[c] > 0.0) ? t[c] / cg->rho[c] : 0.0;
+                cg->rho[c] = t[c];
+            }
+            break;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void cg_finish_reduction(CgScalars *cg, int stage, const double (&total)[N]) {
+    if (cg->distributed) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) cg->red[c] = total[c];
+    } else {
+        cg_finalize(cg, stage, total);
+    }
+}
+
+__global__ void cg_finalize_kernel(CgScalars *cg, int stage) {
+    if (cg->converged && stage != CG_STAGE_START_JACOBI && stage != CG_STAGE_START_MG) return;
+    cg_finalize(cg, stage, cg->red);
+}
 
 // MG = false: Jacobi-preconditioned start (d = z = D^-1 r, rho = r.z).
 // MG = true : multigrid start (d = 0, rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
@@ -361,14 +418,8 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
         }
     }
     double total[5];
-    if (grid_sum_last_block<5>(red, partials, counter, total)) {
-        if (MG) { total[0] = 0; total[1] = 0; total[2] = 0; }
-        cg->rho[0] = total[0]; cg->rho[1] = total[1]; cg->rho[2] = total[2];
-        cg->rr = total[3];
-        cg->ref2 = total[4];
-        cg->iterations = 0;
-        cg->converged = (total[3] <= cg->tol2 * total[4]) ? 1 : 0;
-    }
+    if (grid_sum_last_block<5>(red, partials, counter, total))
+        cg_finish_reduction<5>(cg, MG ? CG_STAGE_START_MG : CG_STAGE_START_JACOBI, total);
 }
 
 // =================================================================================================
@@ -415,10 +466,7 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
         ad[i] = out;
     }
     double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cg->alpha[c] = (total[c] > 0.0) ? cg->rho[c] / total[c] : 0.0;
-    }
+    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_ALPHA, total);
 }
 
 __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *__restrict__ inv_diag, const Vec3d *__restrict__ d,
@@ -439,16 +487,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
         red[3] += ri.x * ri.x + ri.y * ri.y + ri.z * ri.z;
     }
     double total[4];
-    if (grid_sum_last_block<4>(red, partials, counter, total)) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
-            cg->rho[c] = total[c];
-        }
-        cg->rr = total[3];
-        cg->iterations += 1;
-        if (total[3] <= cg->tol2 * cg->ref2) cg->converged = 1;
-    }
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_UPDATE_JACOBI, total);
 }
 
 // rho_new = r . z (per coordinate) and beta = rho_new / rho: used when the preconditioner's last kernel cannot fuse it.
@@ -462,13 +501,7 @@ __global__ void __launch_bounds__(kBlock) cg_dot_rho_kernel(int n, const Vec3d *
         red[0] += ri.x * zi.x; red[1] += ri.y * zi.y; red[2] += ri.z * zi.z;
     }
     double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
-            cg->rho[c] = total[c];
-        }
-    }
+    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_RHO, total);
 }
 
 // d = z + beta d. Launched after cg_update; skipped (like everything else) once converged.

@@ -85,13 +85,7 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
         z[i] = out;
     }
     double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cg->beta[c] = (cg->rho[c] > 0.0) ? total[c] / cg->rho[c] : 0.0;
-            cg->rho[c] = total[c];
-        }
-    }
+    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_RHO, total);
 }
 
 // ---- generic CSR levels -------------------------------------------------------------------------------
@@ -237,11 +231,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n3, const doub
         }
     }
     double total[1];
-    if (grid_sum_last_block<1>(red, partials, counter, total)) {
-        cg->rr = total[0];
-        cg->iterations += 1;
-        if (total[0] <= cg->tol2 * cg->ref2) cg->converged = 1;
-    }
+    if (grid_sum_last_block<1>(red, partials, counter, total)) cg_finish_reduction<1>(cg, CG_STAGE_UPDATE_MG, total);
 }
 
 // d = z + beta d

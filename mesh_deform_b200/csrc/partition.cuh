@@ -1,0 +1,222 @@
+// partition.cuh -- one mesh partitioned over several GPUs (BASELINE.json configs[4]).
+//
+// Each rank owns a contiguous block of local vertex indices [0, n_owned) followed by its halo: the one-ring
+// neighbours of owned vertices that another rank owns, grouped by owner. All row-parallel kernels run on the owned
+// rows only. Three things cross ranks, all through the Transport below:
+//   * halo exchange of p' (after every global step), of R as quaternions (after every local step) and of the CG
+//     search direction (every CG iteration): pack kernel -> point-to-point send/recv into the halo slots;
+//   * all-reduce of the CG's 1-5 partial sums per reduction stage;
+//   * nothing else: the multigrid preconditioner is applied per rank on its owned block (block-Jacobi across ranks).
+// Transports: NCCL over NVLink (one process per GPU; the library is dlopen'ed so single-GPU use needs no NCCL),
+// and an in-process transport (several partitions of one mesh on ONE GPU, one host thread per partition) that the
+// single-GPU test tier uses to exercise exactly the same solver code path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <condition_variable>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace arap {
+
+struct HaloPlan {
+    int n_owned = 0;
+    std::vector<int> neighbor_rank;   // ranks this rank exchanges with
+    std::vector<int> send_offset;     // [n_neighbors + 1] into send_index
+    std::vector<int> send_index;      // owned local indices, grouped by neighbour, in the neighbour's halo order
+    std::vector<int> recv_offset;     // [n_neighbors + 1]: halo from neighbour k sits at local n_owned + recv_offset[k] ...
+    int n_send() const { return send_offset.empty() ? 0 : send_offset.back(); }
+    int n_halo() const { return recv_offset.empty() ? 0 : recv_offset.back(); }
+};
+
+// sendbuf[k] = array[send_index[k]] in 8-byte words (element sizes are 16, 24 or 32 bytes)
+__global__ void __launch_bounds__(256) halo_pack_kernel(int n_send, int words_per_elem, const int *__restrict__ send_index,
+                                                        const unsigned long long *__restrict__ array, unsigned long long *__restrict__ sendbuf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_send * words_per_elem) return;
+    const int k = t / words_per_elem, w = t - k * words_per_elem;
+    sendbuf[t] = array[(size_t)send_index[k] * words_per_elem + w];
+}
+
+class Transport {
+public:
+    virtual ~Transport() {}
+    // sendbuf: packed device buffer (plan.send_offset layout, elem_bytes per entry); array: device base of the local array
+    virtual int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) = 0;
+    virtual int allreduce_sum(cudaStream_t stream, double *dev, int n) = 0;
+    std::string error;
+};
+
+// ---- NCCL (dlopen'ed) --------------------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void *Comm;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void *lib = nullptr;
+
+    static NcclApi *get(std::string *err) {
+        static NcclApi api;
+        static bool tried = false;
+        static std::string load_error;
+        if (!tried) {
+            tried = true;
+            const char *env = getenv("ARAP_NCCL_LIB");
+            const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+            for (const char *n : names) {
+                if (!n) continue;
+                api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+                if (api.lib) break;
+            }
+            if (!api.lib) load_error = "cannot dlopen libnccl.so.2 (set ARAP_NCCL_LIB)";
+            else {
+#define ARAP_NCCL_SYM(field, name)                                                     \
+    *(void **)(&api.field) = dlsym(api.lib, name);                                     \
+    if (!api.field) load_error = std::string("libnccl lacks ") + name;
+                ARAP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+                ARAP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+                ARAP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+                ARAP_NCCL_SYM(GroupStart, "ncclGroupStart")
+                ARAP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+                ARAP_NCCL_SYM(Send, "ncclSend")
+                ARAP_NCCL_SYM(Recv, "ncclRecv")
+                ARAP_NCCL_SYM(AllReduce, "ncclAllReduce")
+                ARAP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef ARAP_NCCL_SYM
+            }
+        }
+        if (!load_error.empty()) { if (err) *err = load_error; return nullptr; }
+        return &api;
+    }
+};
+
+class NcclTransport : public Transport {
+public:
+    NcclApi *api = nullptr;
+    NcclApi::Comm comm = nullptr;
+    int init(int rank, int world, const void *unique_id) {
+        api = NcclApi::get(&error);
+        if (!api) return -1;
+        NcclApi::UniqueId id;
+        memcpy(&id, unique_id, sizeof(id));
+        const int rc = api->CommInitRank(&comm, world, id, rank);
+        if (rc != 0) { error = std::string("ncclCommInitRank: ") + api->GetErrorString(rc); return -1; }
+        return 0;
+    }
+    ~NcclTransport() override { if (api && comm) api->CommDestroy(comm); }
+    int check(int rc, const char *what) {
+        if (rc == 0) return 0;
+        error = std::string(what) + ": " + api->GetErrorString(rc);
+        return -1;
+    }
+    int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) override {
+        if (plan.neighbor_rank.empty()) return 0;
+        if (check(api->GroupStart(), "ncclGroupStart")) return -1;
+        for (size_t k = 0; k < plan.neighbor_rank.size(); ++k) {
+            const size_t ns = (size_t)(plan.send_offset[k + 1] - plan.send_offset[k]) * elem_bytes;
+            const size_t nr = (size_t)(plan.recv_offset[k + 1] - plan.recv_offset[k]) * elem_bytes;
+            if (ns && check(api->Send(sendbuf + (size_t)plan.send_offset[k] * elem_bytes, ns, /*ncclChar*/ 0, plan.neighbor_rank[k], comm, stream), "ncclSend")) return -1;
+            if (nr && check(api->Recv(array + ((size_t)plan.n_owned + plan.recv_offset[k]) * elem_bytes, nr, 0, plan.neighbor_rank[k], comm, stream), "ncclRecv")) return -1;
+        }
+        return check(api->GroupEnd(), "ncclGroupEnd");
+    }
+    int allreduce_sum(cudaStream_t stream, double *dev, int n) override {
+        return check(api->AllReduce(dev, dev, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
+    }
+};
+
+// ---- in-process transport: P partitions on one GPU, one host thread each ------------------------------------------------
+struct LocalGroup {
+    int world = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    long generation = 0;
+    std::vector<const char *> sendbuf;
+    std::vector<const HaloPlan *> plan;
+    std::vector<std::vector<double>> values;
+
+    void barrier() {
+        std::unique_lock<std::mutex> lock(mu);
+        const long gen = generation;
+        if (++arrived == world) { arrived = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lock, [&] { return generation != gen; });
+    }
+    static std::shared_ptr<LocalGroup> get(int key, int world) {
+        static std::mutex reg_mu;
+        static std::map<int, std::weak_ptr<LocalGroup>> registry;
+        std::lock_guard<std::mutex> lock(reg_mu);
+        std::shared_ptr<LocalGroup> g = registry[key].lock();
+        if (!g) {
+            g = std::make_shared<LocalGroup>();
+            g->world = world;
+            g->sendbuf.assign((size_t)world, nullptr);
+            g->plan.assign((size_t)world, nullptr);
+            g->values.assign((size_t)world, std::vector<double>());
+            registry[key] = g;
+        }
+        return g;
+    }
+};
+
+class LocalTransport : public Transport {
+public:
+    std::shared_ptr<LocalGroup> group;
+    int rank = 0;
+    int init(int rank_, int world, int key) {
+        rank = rank_;
+        group = LocalGroup::get(key, world);
+        if (group->world != world) { error = "in-process group: world size mismatch"; return -1; }
+        return 0;
+    }
+    int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) override {
+        if (cudaStreamSynchronize(stream) != cudaSuccess) { error = "sync before exchange"; return -1; }
+        group->sendbuf[(size_t)rank] = sendbuf;
+        group->plan[(size_t)rank] = &plan;
+        group->barrier();
+        for (size_t k = 0; k < plan.neighbor_rank.size(); ++k) {
+            const int peer = plan.neighbor_rank[k];
+            const HaloPlan *pp = group->plan[(size_t)peer];
+            size_t slot = pp->neighbor_rank.size();
+            for (size_t q = 0; q < pp->neighbor_rank.size(); ++q) if (pp->neighbor_rank[q] == rank) slot = q;
+            if (slot == pp->neighbor_rank.size()) { error = "in-process exchange: asymmetric neighbour lists"; return -1; }
+            const size_t n = (size_t)(plan.recv_offset[k + 1] - plan.recv_offset[k]);
+            if ((size_t)(pp->send_offset[slot + 1] - pp->send_offset[slot]) != n) { error = "in-process exchange: send/recv counts differ"; return -1; }
+            if (n && cudaMemcpyAsync(array + ((size_t)plan.n_owned + plan.recv_offset[k]) * elem_bytes,
+                                     group->sendbuf[(size_t)peer] + (size_t)pp->send_offset[slot] * elem_bytes, n * elem_bytes,
+                                     cudaMemcpyDeviceToDevice, stream) != cudaSuccess) { error = "in-process exchange: copy failed"; return -1; }
+        }
+        if (cudaStreamSynchronize(stream) != cudaSuccess) { error = "sync after exchange"; return -1; }
+        group->barrier();      // nobody repacks its send buffer before every reader is done
+        return 0;
+    }
+    int allreduce_sum(cudaStream_t stream, double *dev, int n) override {
+        std::vector<double> mine((size_t)n);
+        if (cudaMemcpyAsync(mine.data(), dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess) { error = "in-process allreduce: D2H failed"; return -1; }
+        group->values[(size_t)rank] = mine;
+        group->barrier();
+        std::vector<double> sum((size_t)n, 0.0);
+        for (int r = 0; r < group->world; ++r)                 // fixed rank order: every partition gets identical bits
+            for (int c = 0; c < n; ++c) sum[(size_t)c] += group->values[(size_t)r][(size_t)c];
+        if (cudaMemcpyAsync(dev, sum.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess) { error = "in-process allreduce: H2D failed"; return -1; }
+        group->barrier();
+        return 0;
+    }
+};
+
+}  // namespace arap

@@ -297,3 +297,42 @@ def test_batch_of_sphere_deformations_matches_oracle(meshes):
         constrain(o, idx, targets[k])
         assert o.deform(10)
         assert np.abs(pos[k] - mesh).max() <= POS_TOL * diag, k
+
+
+@pytest.mark.parametrize("solver", ["mg", "jacobi"])
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_partitioned_mesh_in_process_matches_oracle(world, solver):
+    """BASELINE.json configs[4] in small: the plane.obj-topology grid with 2+2 constraint columns, partitioned into
+    `world` strips that run concurrently on ONE GPU (in-process transport: same solver code path as NCCL, copies
+    instead of NVLink). Result must match the unpartitioned CPU oracle."""
+    from mesh_deform_b200 import partition as PT
+    nx, nz, iters = 64, 48, 4
+    P, F = G.grid_plane(nx, nz)
+    idx, tgt = G.grid_constraints(nx, nz, P)
+    owner = PT.strip_owner(P, world)
+    key = 1000 + 10 * world + (0 if solver == "mg" else 1)
+    parts = [capi.PartitionedDeformation(P, F, owner, r, world, capi.TRANSPORT_IN_PROCESS, key, np.float64, solver=SOLVERS[solver])
+             for r in range(world)]
+
+    def work(p):
+        def run():
+            p.setConstraints(idx, tgt)
+            assert p.prepare() == capi.ARAP_OK
+            p.iterate(iters)
+        return run
+    capi.run_partitions_in_process([work(p) for p in parts])
+    pos = np.zeros_like(P)
+    for p in parts:
+        gid, xyz = p.owned_positions()
+        pos[gid] = xyz
+    energy = sum(p.local_energy() for p in parts)
+    omesh = P.copy()
+    o = O.ArapOracle(omesh, F, np.float64)
+    constrain(o, idx, tgt)
+    assert o.deform(iters)
+    err = np.abs(pos - omesh).max() / bbox_diag(P)
+    de = abs(energy - o.energy()) / o.energy()
+    print("partitioned", world, solver, "err/diag", err, "rel dE", de, [p.solver_stats()["last_cg_iterations"] for p in parts])
+    assert err <= POS_TOL and de <= E_TOL
+    its = {p.solver_stats()["cg_iterations_total"] for p in parts}
+    assert len(its) == 1                      # every rank took exactly the same control path
