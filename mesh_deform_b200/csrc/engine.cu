@@ -230,6 +230,11 @@ public:
     DeviceBuffer<double> mg_coarse_inv;
     bool mg_dense = false;
     bool use_mg = false;
+    std::vector<unsigned char> mg_mask;            // constrained(+halo) mask the hierarchy was built for
+    int mg_nnz = -1;
+    double mg_complexity = 0;
+    bool mg_stale = false, mg_fresh = false;
+    int mg_fresh_iterations = 0;                   // CG iterations of the first global step after a fresh setup
     // partitioned mode (partition.cuh): rows [0, n_rows) are owned, [n_rows, n_vertices) is the halo
     int n_rows = 0;
     HaloPlan plan;
@@ -422,7 +427,33 @@ public:
         for (Vec3d *vec : {cg_r.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr})                                  // halo slots must start finite
             ARAP_CUDA(cudaMemsetAsync(vec, 0, sizeof(Vec3d) * (size_t)(V > 0 ? V : 1), stream));
         use_mg = (opt.solver != ARAP_SOLVER_PCG_JACOBI);
-        if (use_mg) { int rc = setup_multigrid(); if (rc) return rc; }
+        if (use_mg) {
+            // The hierarchy is only a preconditioner: the operator CG sees is always the exact, freshly weighted one.
+            // The reference's dirty protocol re-weights the mesh on every constraint change (every frame in its demos,
+            // arap.h:84,102-120), but as long as the SET of constrained vertices is the same the old hierarchy still
+            // preconditions the new system well, so it is kept (saves the host setup, ~0.6 s at 1M vertices) until the
+            // CG needs noticeably more iterations than right after the last fresh setup.
+            std::vector<unsigned char> mask((size_t)V);
+            if (V > 0) ARAP_CUDA(cudaMemcpyAsync(mask.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaStreamSynchronize(stream));
+            for (int v = n_rows; v < V; ++v) mask[(size_t)v] = 1;
+            const bool reusable = !mg.empty() && !mg_stale && mask == mg_mask && nnz == mg_nnz && getenv("ARAP_MG_ALWAYS_REBUILD") == nullptr;
+            if (reusable) {
+                stats.mg_levels = (int)mg.size();
+                stats.mg_operator_complexity = mg_complexity;
+                stats.setup_host_ms = 0.0;
+                mg_fresh = false;
+            } else {
+                int rc = setup_multigrid();
+                if (rc) return rc;
+                mg_mask.swap(mask);
+                mg_nnz = nnz;
+                mg_complexity = stats.mg_operator_complexity;
+                mg_stale = false;
+                mg_fresh = true;
+                mg_fresh_iterations = 0;
+            }
+        }
         CgScalars init;
         std::memset(&init, 0, sizeof(init));
         // default tolerance: with the multigrid preconditioner the residual tracks the error closely (1e-6 keeps
@@ -720,6 +751,10 @@ public:
         stats.cg_iterations_total += cg_host[0].iterations;
         stats.last_cg_iterations = cg_host[0].iterations;
         stats.last_converged = cg_host[0].converged;
+        if (use_mg) {
+            if (mg_fresh && mg_fresh_iterations == 0) mg_fresh_iterations = cg_host[0].iterations > 0 ? cg_host[0].iterations : 1;
+            else if (!mg_fresh && mg_fresh_iterations > 0 && cg_host[0].iterations > (3 * mg_fresh_iterations) / 2 + 3) mg_stale = true;
+        }
         stats.last_relative_residual = cg_host[0].ref2 > 0 ? sqrt(cg_host[0].rr / cg_host[0].ref2) : 0.0;
         if (!(cg_host[0].rr == cg_host[0].rr)) return fail(ARAP_ERR_SOLVER, "global step: CG residual is NaN");
         return ARAP_OK;
