@@ -358,8 +358,9 @@ def test_hierarchy_reuse_across_dirty_cycles_keeps_parity():
         assert np.abs(mesh - omesh).max() <= POS_TOL * bbox_diag(P)
     assert setups[0] > 0 and all(s == 0 for s in setups[1:])      # one fresh setup, then reuse
     # a NEW constrained vertex changes the mask -> fresh hierarchy
-    a.setConstraint(0, P[0])
-    o.setConstraint(0, P[0])
+    new = int(np.setdiff1d(np.arange(len(P)), idx)[0])
+    a.setConstraint(new, mesh[new].copy())
+    o.setConstraint(new, omesh[new].copy())
     assert a.deform(2) and o.deform(2)
     assert a.solver_stats()["setup_host_ms"] > 0
     assert np.abs(mesh - omesh).max() <= POS_TOL * bbox_diag(P)
