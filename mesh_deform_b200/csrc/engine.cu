@@ -129,14 +129,14 @@ public:
     int sm_count = 148;
     std::map<const void *, int> resident_ctas;     // per kernel: CTAs of kBlock threads resident per SM
     template <typename K>
-    int reduce_grid(K kernel, size_t n) {
+    int reduce_grid(K kernel, size_t n, size_t dyn_smem = 0) {
         int per_sm = ARAP_PERSISTENT_CTAS_PER_SM;
         if (per_sm <= 0) {
             const void *key = (const void *)kernel;
             auto it = resident_ctas.find(key);
             if (it == resident_ctas.end()) {
                 int occ = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ <= 0) occ = 4;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, dyn_smem) != cudaSuccess || occ <= 0) occ = 4;
                 it = resident_ctas.emplace(key, occ).first;
             }
             per_sm = it->second;
@@ -395,8 +395,8 @@ public:
         { int rc = exclusive_scan(unique_count.ptr, V, rowptr.ptr); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&nnz, rowptr.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        ARAP_CUDA(colidx.ensure((size_t)nnz));
-        ARAP_CUDA(weight.ensure((size_t)nnz));
+        ARAP_CUDA(colidx.ensure((size_t)nnz + 4));      // + 4: TMA bulk copies round a tile's span up to 16 bytes
+        ARAP_CUDA(weight.ensure((size_t)nnz + 4));
         if (V > 0)
             LAUNCH(ARAP_K_CSR_COMPACT, csr_compact_kernel<S>, grid_for((size_t)V), V, raw_rowptr.ptr, raw_col.ptr, raw_val.ptr,
                    rowptr.ptr, colidx.ptr, weight.ptr);
@@ -648,11 +648,25 @@ public:
         return reduce_stage(CG_STAGE_RHO, 3);
     }
 
+    bool use_tma = getenv("ARAP_TMA") != nullptr && atoi(getenv("ARAP_TMA")) != 0;
+    void launch_spmv() {
+        const int R = n_rows;
+        if (use_tma) {
+            const size_t smem = tma_spmv_smem_bytes<S>();
+            begin_launch(ARAP_K_CG_SPMV);
+            cg_spmv_tma_kernel<S><<<reduce_grid(cg_spmv_tma_kernel<S>, (size_t)R, smem), kBlock, smem, stream>>>(
+                R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
+            end_launch();
+        } else {
+            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr,
+                   cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
+        }
+    }
+
     int cg_iteration_jacobi() {
         const int R = n_rows;
         { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
-               partials.ptr, counter.ptr, cg.ptr);
+        launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)R), R, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
                counter.ptr, cg.ptr);
@@ -668,8 +682,7 @@ public:
         { int rc = vcycle(); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const double *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
         { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr,
-               partials.ptr, counter.ptr, cg.ptr);
+        launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
                (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (double *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);

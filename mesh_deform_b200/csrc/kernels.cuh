@@ -10,6 +10,7 @@
 
 #include "arap_math.cuh"
 #include "device_utils.cuh"
+#include "tma_stage.cuh"
 
 namespace arap {
 
@@ -464,6 +465,85 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
             red[0] += di.x * out.x; red[1] += di.y * out.y; red[2] += di.z * out.z;
         }
         ad[i] = out;
+    }
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_ALPHA, total);
+}
+
+// ---- TMA-staged variant of cg_spmv ---------------------------------------------------------------------------------
+// Same arithmetic as cg_spmv_kernel. The CTA walks row tiles of kBlock rows; the tile's contiguous colidx / weight spans
+// are bulk-copied (cp.async.bulk + mbarrier, see tma_stage.cuh) into one of two shared-memory stages while the
+// previous tile is being processed. Tiles whose span does not fit a stage (very high valence) read the CSR from global.
+constexpr int kTmaStageEntries = 1792;      // per stage: 7 entries per row on average; 2 stages x 1792 x (4 + 8) B = 43 KB
+template <typename S>
+constexpr size_t tma_spmv_smem_bytes() { return 2 * (size_t)kTmaStageEntries * (sizeof(int) + sizeof(S)) + 64; }
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock) cg_spmv_tma_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                             const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                             const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
+                                                             double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                             CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    extern __shared__ __align__(16) unsigned char tma_smem[];
+    S *const s_w0 = reinterpret_cast<S *>(tma_smem);                                                       // [2][kTmaStageEntries]
+    int *const s_c0 = reinterpret_cast<int *>(tma_smem + 2 * (size_t)kTmaStageEntries * sizeof(S));        // [2][kTmaStageEntries]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tma_smem + 2 * (size_t)kTmaStageEntries * (sizeof(int) + sizeof(S)));
+    int *s_meta = reinterpret_cast<int *>(bar + 2);          // [stage][2]: first staged entry (k0a), staged flag
+    const int n_tiles = (n + kBlock - 1) / kBlock;
+    if (threadIdx.x == 0) {
+        tma::mbar_init(&bar[0], 1);
+        tma::mbar_init(&bar[1], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int stage) {                  // one thread: start the bulk copies of `tile` into `stage`
+        const int r0 = tile * kBlock, r1 = min(n, r0 + kBlock);
+        const int k0 = rowptr[r0], k1 = rowptr[r1];
+        const int k0a = k0 & ~3, cnt = ((k1 + 3) & ~3) - k0a;
+        const bool staged = cnt > 0 && cnt <= kTmaStageEntries;
+        s_meta[2 * stage] = k0a;
+        s_meta[2 * stage + 1] = staged ? 1 : 0;
+        if (staged) {
+            tma::mbar_arrive_expect_tx(&bar[stage], (uint32_t)cnt * (uint32_t)(sizeof(int) + sizeof(S)));
+            tma::bulk_g2s(s_c0 + stage * kTmaStageEntries, colidx + k0a, (uint32_t)cnt * (uint32_t)sizeof(int), &bar[stage]);
+            tma::bulk_g2s(s_w0 + stage * kTmaStageEntries, weight + k0a, (uint32_t)cnt * (uint32_t)sizeof(S), &bar[stage]);
+        } else {
+            tma::mbar_arrive_expect_tx(&bar[stage], 0u);
+        }
+    };
+    int stage = 0;
+    uint32_t phase_bits = 0u;                                // bit s = parity to wait for on stage s
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    __syncthreads();
+    double red[3] = {0, 0, 0};
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < n_tiles) issue(next, stage ^ 1);
+        tma::mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= 1u << stage;
+        const int k0a = s_meta[2 * stage];
+        const bool staged = s_meta[2 * stage + 1] != 0;
+        const int i = tile * kBlock + threadIdx.x;
+        if (i < n) {
+            Vec3d out = {0, 0, 0};
+            if (rest4[i].w != S(0)) {
+                const int ka = rowptr[i], kb = rowptr[i + 1];
+                const Vec3d di = d[i];
+                const int *cc = staged ? (s_c0 + stage * kTmaStageEntries - k0a) : colidx;      // both indexed by the global entry number
+                const S *ww = staged ? (s_w0 + stage * kTmaStageEntries - k0a) : weight;
+                for (int kk = ka; kk < kb; ++kk) {
+                    const int j = cc[kk];
+                    const double w = (double)ww[kk];
+                    const Vec3d dj = d[j];
+                    out.x += w * (di.x - dj.x); out.y += w * (di.y - dj.y); out.z += w * (di.z - dj.z);
+                }
+                red[0] += di.x * out.x; red[1] += di.y * out.y; red[2] += di.z * out.z;
+            }
+            ad[i] = out;
+        }
+        __syncthreads();        // everyone is done with this stage before the copy of tile + 2*grid lands in it
+        stage ^= 1;
     }
     double total[3];
     if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_ALPHA, total);
