@@ -233,7 +233,7 @@ template <> struct NewtonTol<float> {
     static constexpr float det_min = 1e-4f;
 };
 template <> struct NewtonTol<double> {
-    static constexpr double step2 = 1e-10;
+    static constexpr double step2 = 1e-8;       // |omega| < 1e-4 on the accepted step: remaining rotation error ~1e-8 rad
     static constexpr double det_min = 1e-9;
 };
 
@@ -300,11 +300,27 @@ ARAP_HD bool rotation_newton(const S c[9], S q[4], int max_steps, S step2_accept
 ARAP_HD bool rotation_newton_certified(const float c[9], float q[4]) {
     return rotation_newton<float>(c, q, 6, NewtonTol<float>::step2);
 }
-// double: plain fp64 Newton, accepted once |omega| < 1e-5 on the step just taken (remaining error ~1e-10 rad).
+// double: plain fp64 Newton, accepted once |omega| < 1e-4 on the step just taken (remaining error ~1e-8 rad, three
+// orders of magnitude inside the 1e-5 x bbox-diagonal parity bar; it does not accumulate: every iteration re-converges).
 // (A mixed variant -- fp32 approach, fp64 polish -- measured slower: the kernel is bound by the latency of
 // the serial chain per thread, and the extra fp32 steps lengthen it.)
 ARAP_HD bool rotation_newton_certified(const double c[9], double q[4]) {
     return rotation_newton<double>(c, q, 6, NewtonTol<double>::step2);
+}
+
+// Newton only: true if certified (q_out valid), false if the caller has to run the Jacobi SVD for this covariance.
+template <typename S>
+ARAP_HD bool rotation_from_covariance_newton_only(const S cov[9], const S q_prev[4], S q_out[4]) {
+    S scale = 0;
+    for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(cov[i]));
+    if (!(scale > S(0))) return false;
+    const S inv_scale = S(1) / scale;
+    S c[9];
+    for (int i = 0; i < 9; ++i) c[i] = cov[i] * inv_scale;
+    S q[4] = {q_prev[0], q_prev[1], q_prev[2], q_prev[3]};
+    if (!rotation_newton_certified(c, q)) return false;
+    q_out[0] = q[0]; q_out[1] = q[1]; q_out[2] = q[2]; q_out[3] = q[3];
+    return true;
 }
 
 // Local step kernel body: warm-started Newton, Jacobi SVD fallback. q_prev/q_out may alias.

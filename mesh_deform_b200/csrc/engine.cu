@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -29,7 +30,7 @@ static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
     "cg_update", "cg_direction", "apply_update", "energy", "misc",
     "mg_fine_residual", "mg_fine_postsmooth", "mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add",
-    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize"};
+    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize", "local_step_redo"};
 
 static thread_local std::string g_create_error;
 
@@ -213,6 +214,12 @@ public:
     DeviceBuffer<int> rowptr, colidx;              // _edgeWeights
     DeviceBuffer<S> weight;
     DeviceBuffer<int> free_idx;                    // _freeIdxMap
+    // internal (hot) order: perm[internal] = user index; the iteration kernels only ever see the hot CSR
+    DeviceBuffer<int> perm, iperm, hot_rowptr, hot_colidx;
+    DeviceBuffer<S> hot_weight;
+    bool have_perm = false;
+    std::vector<int> faces_host;                   // kept until the vertex order has been decided
+    std::vector<int> mg_visit_order;               // Morton sequence of internal indices: aggregation order of the fine level
     DeviceBuffer<Vec4T<S>> rest4, cur4, quat;      // _p, _pprime, _rotations
     DeviceBuffer<double> inv_diag;
     DeviceBuffer<Vec3d> cg_r, cg_d, cg_ad, cg_x;
@@ -220,6 +227,8 @@ public:
     DeviceBuffer<unsigned> counter;
     DeviceBuffer<CgScalars> cg;
     DeviceBuffer<double> energy_dev;
+    DeviceBuffer<int> redo_list, redo_count;       // local step: vertices that need the Jacobi SVD fallback
+    DeviceBuffer<unsigned> redo_done;
     // scratch for the CSR build
     DeviceBuffer<int> row_count, raw_rowptr, row_cursor, raw_col, unique_count, scan_tiles, flags;
     DeviceBuffer<S> raw_val;
@@ -268,7 +277,7 @@ public:
         if (stream) cudaStreamDestroy(stream);
     }
 
-    int init(const int *faces_host, int nf, int nv, const arap_options &o) {
+    int init(const int *faces_host_in, int nf, int nv, const arap_options &o) {
         opt = o;
         n_vertices = nv;
         n_faces = nf;
@@ -291,8 +300,9 @@ public:
         ARAP_CUDA(cudaEventCreateWithFlags(&poll_event[0], cudaEventDisableTiming));
         ARAP_CUDA(cudaEventCreateWithFlags(&poll_event[1], cudaEventDisableTiming));
         ARAP_CUDA(cudaMallocHost(&cg_host, 2 * sizeof(CgScalars)));
+        faces_host.assign(faces_host_in, faces_host_in + 3 * (size_t)nf);
         ARAP_CUDA(faces.ensure(3 * (size_t)nf));
-        ARAP_CUDA(cudaMemcpyAsync(faces.ptr, faces_host, sizeof(int) * 3 * (size_t)nf, cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaMemcpyAsync(faces.ptr, faces_host_in, sizeof(int) * 3 * (size_t)nf, cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(is_constrained.ensure((size_t)nv));
         ARAP_CUDA(target_xyz.ensure(3 * (size_t)nv));
         ARAP_CUDA(cudaMemsetAsync(is_constrained.ptr, 0, (size_t)(nv > 0 ? nv : 1), stream));
@@ -303,6 +313,11 @@ public:
         ARAP_CUDA(cg.ensure(1));
         ARAP_CUDA(cudaMemsetAsync(cg.ptr, 0, sizeof(CgScalars), stream));
         ARAP_CUDA(energy_dev.ensure(1));
+        ARAP_CUDA(redo_list.ensure((size_t)nv + 1));
+        ARAP_CUDA(redo_count.ensure(1));
+        ARAP_CUDA(redo_done.ensure(1));
+        ARAP_CUDA(cudaMemsetAsync(redo_count.ptr, 0, sizeof(int), stream));
+        ARAP_CUDA(cudaMemsetAsync(redo_done.ptr, 0, sizeof(unsigned), stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
         return ARAP_OK;
     }
@@ -395,8 +410,8 @@ public:
         { int rc = exclusive_scan(unique_count.ptr, V, rowptr.ptr); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&nnz, rowptr.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        ARAP_CUDA(colidx.ensure((size_t)nnz + 4));      // + 4: TMA bulk copies round a tile's span up to 16 bytes
-        ARAP_CUDA(weight.ensure((size_t)nnz + 4));
+        ARAP_CUDA(colidx.ensure((size_t)nnz));
+        ARAP_CUDA(weight.ensure((size_t)nnz));
         if (V > 0)
             LAUNCH(ARAP_K_CSR_COMPACT, csr_compact_kernel<S>, grid_for((size_t)V), V, raw_rowptr.ptr, raw_col.ptr, raw_val.ptr,
                    rowptr.ptr, colidx.ptr, weight.ptr);
@@ -407,17 +422,27 @@ public:
         { int rc = exclusive_scan(flags.ptr, V, row_count.ptr); if (rc) return rc; }   // row_count reused as the prefix array
         ARAP_CUDA(cudaMemcpyAsync(&n_free, row_count.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
         if (V > 0) LAUNCH(ARAP_K_MISC, free_map_kernel, grid_for((size_t)V), V, is_constrained.ptr, row_count.ptr, free_idx.ptr);
+        // ---- internal vertex order (once per handle) and the hot CSR in that order (every prepare: the weights changed)
+        n_rows = transport ? plan.n_owned : V;
+        if (!have_perm) { int rc = build_permutation(rest_host, scalar_bytes); if (rc) return rc; }
+        ARAP_CUDA(hot_rowptr.ensure((size_t)V + 1));
+        ARAP_CUDA(hot_colidx.ensure((size_t)nnz + 4));      // + 4: TMA bulk copies round a tile's span up to 16 bytes
+        ARAP_CUDA(hot_weight.ensure((size_t)nnz + 4));
+        if (V > 0) LAUNCH(ARAP_K_MISC, perm_row_count_kernel, grid_for((size_t)V), V, perm.ptr, rowptr.ptr, unique_count.ptr);
+        { int rc = exclusive_scan(unique_count.ptr, V, hot_rowptr.ptr); if (rc) return rc; }
+        if (V > 0)
+            LAUNCH(ARAP_K_MISC, perm_csr_fill_kernel<S>, grid_for((size_t)V), V, perm.ptr, iperm.ptr, rowptr.ptr, colidx.ptr, weight.ptr,
+                   hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr);
         // ---- initializeMeshGeometry / Rotations / Constraints into the solver layout (arap.h:162-168,246-249,277-281)
         ARAP_CUDA(rest4.ensure((size_t)V));
         ARAP_CUDA(cur4.ensure((size_t)V));
         ARAP_CUDA(quat.ensure((size_t)V));
         ARAP_CUDA(inv_diag.ensure((size_t)V));
         if (V > 0)
-            LAUNCH(ARAP_K_INIT_STATE, init_state_kernel<S>, grid_for((size_t)V), V, rest_xyz.ptr, is_constrained.ptr, target_xyz.ptr,
-                   rowptr.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr);
+            LAUNCH(ARAP_K_INIT_STATE, init_state_kernel<S>, grid_for((size_t)V), V, perm.ptr, rest_xyz.ptr, is_constrained.ptr, target_xyz.ptr,
+                   hot_rowptr.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr);
         ARAP_CUDA(cudaGetLastError());
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        n_rows = transport ? plan.n_owned : V;
         if (n_free == V && !transport) return ARAP_UNCONSTRAINED;        // arap.h:113-114: stays dirty, nothing solved
         // ---- setupLinearSystem (arap.h:292-340): matrix-free L, nothing to factor; allocate the CG vectors
         ARAP_CUDA(cg_r.ensure((size_t)V));
@@ -433,10 +458,9 @@ public:
             // arap.h:84,102-120), but as long as the SET of constrained vertices is the same the old hierarchy still
             // preconditions the new system well, so it is kept (saves the host setup, ~0.6 s at 1M vertices) until the
             // CG needs noticeably more iterations than right after the last fresh setup.
-            std::vector<unsigned char> mask((size_t)V);
+            std::vector<unsigned char> mask((size_t)V);      // user order is fine here: it is only compared with the previous one
             if (V > 0) ARAP_CUDA(cudaMemcpyAsync(mask.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
             ARAP_CUDA(cudaStreamSynchronize(stream));
-            for (int v = n_rows; v < V; ++v) mask[(size_t)v] = 1;
             const bool reusable = !mg.empty() && !mg_stale && mask == mg_mask && nnz == mg_nnz && getenv("ARAP_MG_ALWAYS_REBUILD") == nullptr;
             if (reusable) {
                 stats.mg_levels = (int)mg.size();
@@ -472,6 +496,83 @@ public:
         return ARAP_OK;
     }
 
+    // ---- internal vertex order --------------------------------------------------------------------------------------
+    // Morton (Z-curve) order of the rest pose: vertices that are close in space -- a vertex and its one-ring -- get close
+    // internal indices, so the gathers of a CTA mostly hit lines its own rows already pulled into L1. Computed once per
+    // handle on the host (the topology is fixed, arap.h:95; the geometry of later dirty cycles stays close). In
+    // partitioned mode only the owned block is reordered; the halo keeps the layout the exchange plan relies on.
+    int build_permutation(const void *rest_host, int scalar_bytes) {
+        const int V = n_vertices, owned = n_rows;
+        std::vector<int> h_perm((size_t)V);
+        for (int i = 0; i < V; ++i) h_perm[(size_t)i] = i;
+        const char *env = getenv("ARAP_REORDER");
+        if (!(env && atoi(env) == 0) && owned > 1) {
+            auto coord = [&](int v, int d) -> double {
+                return scalar_bytes == 4 ? (double)((const float *)rest_host)[3 * (size_t)v + d] : ((const double *)rest_host)[3 * (size_t)v + d];
+            };
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int v = 0; v < owned; ++v)
+                for (int d = 0; d < 3; ++d) { const double c = coord(v, d); if (c < lo[d]) lo[d] = c; if (c > hi[d]) hi[d] = c; }
+            double extent = 0;
+            for (int d = 0; d < 3; ++d) extent = std::max(extent, hi[d] - lo[d]);
+            const double scale = extent > 0 ? 2097151.0 / extent : 0.0;             // 21 bits per axis
+            auto spread = [](uint64_t x) -> uint64_t {                                // insert two zero bits between the 21 low bits
+                x &= 0x1fffffULL;
+                x = (x | x << 32) & 0x1f00000000ffffULL;
+                x = (x | x << 16) & 0x1f0000ff0000ffULL;
+                x = (x | x << 8) & 0x100f00f00f00f00fULL;
+                x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+                x = (x | x << 2) & 0x1249249249249249ULL;
+                return x;
+            };
+            std::vector<std::pair<uint64_t, int>> keyed((size_t)owned);
+            for (int v = 0; v < owned; ++v) {
+                uint64_t key = 0;
+                for (int d = 0; d < 3; ++d) key |= spread((uint64_t)((coord(v, d) - lo[d]) * scale)) << d;
+                keyed[(size_t)v] = {key, v};
+            }
+            std::sort(keyed.begin(), keyed.end());
+            // Renumber the memory layout only if it buys locality: count the mesh edges whose end points are within a
+            // few CTAs of each other, in the user's order and in Morton order. Generated / scanned-in-strips meshes are
+            // often already well ordered (the headline icosphere is: renumbering it made the gather kernels 15 % slower).
+            std::vector<int> rank_of((size_t)V);
+            for (int i = 0; i < V; ++i) rank_of[(size_t)i] = i;
+            for (int i = 0; i < owned; ++i) rank_of[(size_t)keyed[(size_t)i].second] = i;
+            long long near_user = 0, near_morton = 0;
+            const int window = 4 * kBlock;
+            for (size_t f = 0; f + 2 < faces_host.size(); f += 3)
+                for (int e = 0; e < 3; ++e) {
+                    const int a = faces_host[f + e], b = faces_host[f + (e + 1) % 3];
+                    if (a >= owned || b >= owned) continue;
+                    if (std::abs(a - b) <= window) ++near_user;
+                    if (std::abs(rank_of[(size_t)a] - rank_of[(size_t)b]) <= window) ++near_morton;
+                }
+            const bool force = env && atoi(env) == 2;
+            const bool renumber = force || (double)near_morton > 1.15 * (double)near_user;
+            mg_visit_order.resize((size_t)V);
+            for (int i = 0; i < V; ++i) mg_visit_order[(size_t)i] = i;
+            if (renumber) {
+                for (int i = 0; i < owned; ++i) h_perm[(size_t)i] = keyed[(size_t)i].second;       // internal order IS the Morton order
+            } else {
+                for (int i = 0; i < owned; ++i) mg_visit_order[(size_t)i] = keyed[(size_t)i].second; // identity layout, Morton visiting order
+            }
+        }
+        std::vector<int>().swap(faces_host);
+        ARAP_CUDA(upload_vector(perm, h_perm, stream));
+        ARAP_CUDA(iperm.ensure((size_t)V));
+        if (V > 0) LAUNCH(ARAP_K_MISC, invert_perm_kernel, grid_for((size_t)V), V, perm.ptr, iperm.ptr);
+        if (transport && plan.n_send() > 0) {                  // the exchange plan speaks user-local indices
+            std::vector<int> h_iperm((size_t)V);
+            for (int i = 0; i < V; ++i) h_iperm[(size_t)h_perm[(size_t)i]] = i;
+            std::vector<int> send((size_t)plan.n_send());
+            for (size_t k = 0; k < send.size(); ++k) send[k] = h_iperm[(size_t)plan.send_index[k]];
+            ARAP_CUDA(upload_vector(send_index_dev, send, stream));
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));              // h_perm dies at scope exit
+        have_perm = true;
+        return ARAP_OK;
+    }
+
     // ---- partitioned mode ----------------------------------------------------------------------------------------
     int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) override {
         if (!p || p->n_owned < 0 || p->n_owned > n_vertices || p->n_neighbors < 0 || world <= 0 || rank < 0 || rank >= world)
@@ -502,6 +603,7 @@ public:
         ARAP_CUDA(cudaStreamSynchronize(stream));
         dirty = true;
         prepared = false;
+        have_perm = false;
         return ARAP_OK;
     }
 
@@ -537,17 +639,24 @@ public:
         std::vector<int> h_rowptr((size_t)V + 1), h_colidx((size_t)nnz);
         std::vector<S> h_w((size_t)nnz);
         std::vector<unsigned char> h_con((size_t)V);
-        ARAP_CUDA(cudaMemcpyAsync(h_rowptr.data(), rowptr.ptr, sizeof(int) * ((size_t)V + 1), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaMemcpyAsync(h_rowptr.data(), hot_rowptr.ptr, sizeof(int) * ((size_t)V + 1), cudaMemcpyDeviceToHost, stream));
         if (nnz > 0) {
-            ARAP_CUDA(cudaMemcpyAsync(h_colidx.data(), colidx.ptr, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
-            ARAP_CUDA(cudaMemcpyAsync(h_w.data(), weight.ptr, sizeof(S) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h_colidx.data(), hot_colidx.ptr, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h_w.data(), hot_weight.ptr, sizeof(S) * (size_t)nnz, cudaMemcpyDeviceToHost, stream));
         }
-        if (V > 0) ARAP_CUDA(cudaMemcpyAsync(h_con.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
+        std::vector<unsigned char> h_con_user((size_t)V);
+        std::vector<int> h_perm((size_t)V);
+        if (V > 0) {
+            ARAP_CUDA(cudaMemcpyAsync(h_con_user.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h_perm.data(), perm.ptr, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, stream));
+        }
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        for (int v = 0; v < V; ++v) h_con[(size_t)v] = h_con_user[(size_t)h_perm[(size_t)v]];
         for (int v = n_rows; v < V; ++v) h_con[(size_t)v] = 1;      // partitioned mode: block-Jacobi across ranks, halo = Dirichlet
         MgHierarchyHost H;
         MgSetupOptions mo;
-        mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H);
+        mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H,
+                              (int)mg_visit_order.size() == V ? mg_visit_order.data() : nullptr);
         mg.clear();
         for (size_t l = 0; l < H.levels.size(); ++l) {
             const MgLevelHost &hl = H.levels[l];
@@ -610,7 +719,7 @@ public:
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr,
+                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
                        rest4.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
@@ -637,8 +746,8 @@ public:
             LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr,
-                       weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
+                       hot_weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, f.omega, f.b.ptr,
@@ -655,10 +764,10 @@ public:
             const size_t smem = tma_spmv_smem_bytes<S>();
             begin_launch(ARAP_K_CG_SPMV);
             cg_spmv_tma_kernel<S><<<reduce_grid(cg_spmv_tma_kernel<S>, (size_t)R, smem), kBlock, smem, stream>>>(
-                R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
+                R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
             end_launch();
         } else {
-            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr,
+            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr,
                    cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
         }
     }
@@ -719,11 +828,11 @@ public:
         const int R = n_rows, G = grid_for((size_t)R);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
             { int rc = reduce_stage(CG_STAGE_START_MG, 5); if (rc) return rc; }
         } else {
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr,
+            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
             { int rc = reduce_stage(CG_STAGE_START_JACOBI, 5); if (rc) return rc; }
         }
@@ -777,9 +886,12 @@ public:
         if (!prepared) return fail(ARAP_ERR_INVALID, "iterate: arap_prepare has not succeeded");
         const int R = n_rows, G = grid_for((size_t)R);
         for (int it = 0; it < n; ++it) {
-            // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the warm
-            // kernel certifies convergence to the SVD's rotation per vertex and falls back to the Jacobi SVD otherwise.
-            LAUNCH(ARAP_K_LOCAL_STEP, (local_step_kernel<S, true>), G, R, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr);
+            // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the hot kernel
+            // certifies convergence to the SVD's rotation per vertex and lists the vertices that need the Jacobi SVD.
+            LAUNCH(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+                   redo_list.ptr, redo_count.ptr);
+            LAUNCH(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                   quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
             { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
             int rc = global_step();
             if (rc) return rc;
@@ -795,8 +907,8 @@ public:
         const size_t bytes = (size_t)scalar_bytes * 3 * (size_t)V;
         ARAP_CUDA(staging.ensure(bytes));
         begin_launch(ARAP_K_MISC);
-        if (scalar_bytes == 4) export_positions_kernel<S, float><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, cur4.ptr, (float *)staging.ptr);
-        else export_positions_kernel<S, double><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, cur4.ptr, (double *)staging.ptr);
+        if (scalar_bytes == 4) export_positions_kernel<S, float><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, perm.ptr, cur4.ptr, (float *)staging.ptr);
+        else export_positions_kernel<S, double><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, perm.ptr, cur4.ptr, (double *)staging.ptr);
         end_launch();
         ARAP_CUDA(cudaMemcpyAsync(out, staging.ptr, bytes, cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
@@ -827,15 +939,15 @@ public:
         if (!quat.ptr) return fail(ARAP_ERR_INVALID, "get_rotations: call arap_prepare first");
         const int V = n_vertices;
         ARAP_CUDA(staging.ensure(sizeof(S) * 9 * (size_t)V));
-        LAUNCH(ARAP_K_MISC, export_rotations_kernel<S>, grid_for((size_t)V), V, quat.ptr, (S *)staging.ptr);
+        LAUNCH(ARAP_K_MISC, export_rotations_kernel<S>, grid_for((size_t)V), V, perm.ptr, quat.ptr, (S *)staging.ptr);
         ARAP_CUDA(cudaMemcpyAsync(rot9, staging.ptr, sizeof(S) * 9 * (size_t)V, cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
         return ARAP_OK;
     }
     int energy(double *e) override {
-        if (!quat.ptr || !rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
+        if (!quat.ptr || !hot_rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
         const int V = prepared ? n_rows : n_vertices;      // partitioned mode: this rank's share (owned rows)
-        LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, reduce_grid(energy_kernel<S>, (size_t)V), V, rowptr.ptr, colidx.ptr, weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+        LAUNCH(ARAP_K_ENERGY, energy_kernel<S>, reduce_grid(energy_kernel<S>, (size_t)V), V, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
                partials.ptr, counter.ptr, energy_dev.ptr);
         ARAP_CUDA(cudaMemcpyAsync(e, energy_dev.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));

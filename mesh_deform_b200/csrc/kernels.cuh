@@ -19,18 +19,20 @@ template <> __device__ __forceinline__ Vec4T<float> load4<float>(const Vec4T<flo
     const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
     return Vec4T<float>{v.x, v.y, v.z, v.w};
 }
+// sm_100 has 256-bit global loads/stores (SASS LDG.E.256 / STG.E.256): one request per 32-byte element, i.e. per
+// 32-byte sector, instead of two 128-bit requests that each touch the same sector -- halves the L1 request traffic of
+// the double-precision gathers, which is what bounds the local step and the RHS kernel (profiles/README.md).
 template <> __device__ __forceinline__ Vec4T<double> load4<double>(const Vec4T<double> *p) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    return Vec4T<double>{a.x, a.y, b.x, b.y};
+    Vec4T<double> r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
 }
 template <typename S> __device__ __forceinline__ void store4(Vec4T<S> *p, S x, S y, S z, S w);
 template <> __device__ __forceinline__ void store4<float>(Vec4T<float> *p, float x, float y, float z, float w) {
     *reinterpret_cast<float4 *>(p) = make_float4(x, y, z, w);
 }
 template <> __device__ __forceinline__ void store4<double>(Vec4T<double> *p, double x, double y, double z, double w) {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(x, y);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(z, w);
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
 }
 
 // ---- load-batching gates ---------------------------------------------------------------------------
@@ -50,10 +52,10 @@ __device__ __forceinline__ double gather_gate(const Vec3d (&a)[N]) {
     return 0.0 * s;
 }
 template <int N>
-__device__ __forceinline__ double gather_gate(const Vec4T<double> (&a)[N]) {   // two 16-byte loads per element
-    double s = a[0].x + a[0].z;
+__device__ __forceinline__ double gather_gate(const Vec4T<double> (&a)[N]) {   // one 32-byte load per element
+    double s = a[0].x;
 #pragma unroll
-    for (int u = 1; u < N; ++u) s += a[u].x + a[u].z;
+    for (int u = 1; u < N; ++u) s += a[u].x;
     return 0.0 * s;
 }
 template <int N>
@@ -182,18 +184,49 @@ __global__ void __launch_bounds__(kBlock) free_map_kernel(int n, const unsigned 
 
 // initializeMeshGeometry + initializeRotations + initializeConstraints (arap.h:162-168, 246-249, 277-281)
 // plus the Jacobi preconditioner 1 / L_ii = 1 / sum_j w_ij (the diagonal of arap.h:332).
+// Internal vertex order. The engine renumbers vertices once (Morton order of the rest pose, see engine.cu) so that a
+// CTA's rows and their one-ring neighbours sit close together in memory; perm[internal] = user index. Everything at the
+// C-ABI boundary (constraints, CSR export, positions, rotations) stays in the user's numbering.
+__global__ void __launch_bounds__(kBlock) invert_perm_kernel(int n, const int *__restrict__ perm, int *__restrict__ iperm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) iperm[perm[i]] = i;
+}
+__global__ void __launch_bounds__(kBlock) perm_row_count_kernel(int n, const int *__restrict__ perm, const int *__restrict__ rowptr_user,
+                                                                int *__restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int u = perm[i]; count[i] = rowptr_user[u + 1] - rowptr_user[u]; }
+}
 template <typename S>
-__global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const S *__restrict__ rest_xyz, const unsigned char *__restrict__ is_constrained,
+__global__ void __launch_bounds__(kBlock) perm_csr_fill_kernel(int n, const int *__restrict__ perm, const int *__restrict__ iperm,
+                                                               const int *__restrict__ rowptr_user, const int *__restrict__ colidx_user,
+                                                               const S *__restrict__ weight_user, const int *__restrict__ rowptr_hot,
+                                                               int *__restrict__ colidx_hot, S *__restrict__ weight_hot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int u = perm[i];
+    const int src = rowptr_user[u], len = rowptr_user[u + 1] - src, dst = rowptr_hot[i];
+    for (int k = 0; k < len; ++k) {                 // the user row's column order is kept, so every sum runs in the reference's order
+        colidx_hot[dst + k] = iperm[colidx_user[src + k]];
+        weight_hot[dst + k] = weight_user[src + k];
+    }
+}
+
+// initializeMeshGeometry + initializeRotations + initializeConstraints (arap.h:162-168, 246-249, 277-281) into the
+// solver layout (internal order), plus the Jacobi preconditioner 1 / L_ii = 1 / sum_j w_ij (the diagonal of arap.h:332).
+template <typename S>
+__global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__restrict__ perm, const S *__restrict__ rest_xyz,
+                                                            const unsigned char *__restrict__ is_constrained,
                                                             const S *__restrict__ target_xyz, const int *__restrict__ rowptr,
                                                             const S *__restrict__ weight, Vec4T<S> *__restrict__ rest4,
                                                             Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
                                                             double *__restrict__ inv_diag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const bool con = is_constrained[i] != 0;
-    const S x = rest_xyz[3 * (size_t)i], y = rest_xyz[3 * (size_t)i + 1], z = rest_xyz[3 * (size_t)i + 2];
+    const size_t u = (size_t)perm[i];
+    const bool con = is_constrained[u] != 0;
+    const S x = rest_xyz[3 * u], y = rest_xyz[3 * u + 1], z = rest_xyz[3 * u + 2];
     store4<S>(&rest4[i], x, y, z, con ? S(0) : S(1));
-    if (con) store4<S>(&cur4[i], target_xyz[3 * (size_t)i], target_xyz[3 * (size_t)i + 1], target_xyz[3 * (size_t)i + 2], S(0));
+    if (con) store4<S>(&cur4[i], target_xyz[3 * u], target_xyz[3 * u + 1], target_xyz[3 * u + 2], S(0));
     else store4<S>(&cur4[i], x, y, z, S(0));
     store4<S>(&quat[i], S(1), S(0), S(0), S(0));
     double diag = 0.0;
@@ -215,6 +248,15 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const S *__re
 #ifndef ARAP_SPMV_CHUNK
 #define ARAP_SPMV_CHUNK 2
 #endif
+#ifndef ARAP_LOCAL_GATE
+#define ARAP_LOCAL_GATE 0
+#endif
+#ifndef ARAP_RHS_GATE
+#define ARAP_RHS_GATE 0
+#endif
+#ifndef ARAP_LOCAL_MIN_BLOCKS
+#define ARAP_LOCAL_MIN_BLOCKS 1
+#endif
 template <typename S> struct GatherChunk;
 template <> struct GatherChunk<float> { static constexpr int value = 6; };
 template <> struct GatherChunk<double> { static constexpr int value = ARAP_LOCAL_CHUNK_F64; };
@@ -223,21 +265,17 @@ template <> struct RhsChunk<float> { static constexpr int value = 4; };
 template <> struct RhsChunk<double> { static constexpr int value = ARAP_RHS_CHUNK_F64; };
 constexpr int kSpmvChunk = ARAP_SPMV_CHUNK;
 
-// WARM = true : R_i from the previous iteration seeds a Newton iteration (see arap_math.cuh); Jacobi SVD fallback.
-// WARM = false: always the Jacobi SVD (used when there is no previous rotation worth trusting).
-template <typename S, bool WARM>
-__global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                                                            const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
-                                                            const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat) {
+// S_i of one vertex: neighbours gathered in chunks of GatherChunk<S> (index/weight loads, then position gathers, then FMAs).
+template <typename S>
+__device__ __forceinline__ void one_ring_covariance(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                    const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                    const Vec4T<S> *__restrict__ cur4, S cov[9]) {
     constexpr int CH = GatherChunk<S>::value;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const int k0 = rowptr[i], k1 = rowptr[i + 1];
     const Vec4T<S> pi = load4<S>(&rest4[i]);
     const Vec4T<S> ci = load4<S>(&cur4[i]);
-    Vec4T<S> qprev;
-    if (WARM) qprev = load4<S>(&quat[i]);
-    S cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) cov[c] = S(0);
     for (int k = k0; k < k1; k += CH) {
         int j[CH];
         S w[CH];
@@ -250,6 +288,13 @@ __global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__
         Vec4T<S> pj[CH], cj[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); }
+#if ARAP_LOCAL_GATE
+        {
+            const S gate = gather_gate(pj) + gather_gate(cj);
+#pragma unroll
+            for (int u = 0; u < CH; ++u) w[u] += gate;
+        }
+#endif
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             const S ex = w[u] * (pi.x - pj[u].x), ey = w[u] * (pi.y - pj[u].y), ez = w[u] * (pi.z - pj[u].z);
@@ -259,14 +304,64 @@ __global__ void __launch_bounds__(kBlock) local_step_kernel(int n, const int *__
             cov[6] += ez * dx; cov[7] += ez * dy; cov[8] += ez * dz;
         }
     }
-    S q[4];
-    if (WARM) {
-        const S qp[4] = {qprev.x, qprev.y, qprev.z, qprev.w};
-        rotation_from_covariance_warm<S>(cov, qp, q);
-    } else {
-        rotation_from_covariance<S>(cov, q);
+}
+
+// Local step, hot kernel: R_i from the previous iteration seeds a Newton iteration on SO(3) (see arap_math.cuh).
+// Vertices whose Newton iteration does not certify (far from the previous rotation, degenerate covariance) are appended
+// to `redo_list`; local_step_redo_kernel gives them the full Jacobi SVD. Keeping the SVD out of this kernel keeps its
+// register count -- and with it the occupancy of the 99.9 % case -- down.
+template <typename S>
+__global__ void __launch_bounds__(kBlock, ARAP_LOCAL_MIN_BLOCKS) local_step_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                            const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
+                                                            int *__restrict__ redo_list, int *__restrict__ redo_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S cov[9];
+#if defined(ARAP_DIAG_LOCAL) && ARAP_DIAG_LOCAL == 2          /* diagnostic build: no gathers, compute only */
+    {
+        const Vec4T<S> pi = load4<S>(&rest4[i]);
+        const Vec4T<S> ci = load4<S>(&cur4[i]);
+        cov[0] = pi.x + S(2); cov[1] = pi.y * S(0.1); cov[2] = pi.z * S(0.1); cov[3] = ci.y * S(0.1); cov[4] = ci.x + S(2.5);
+        cov[5] = ci.z * S(0.1); cov[6] = pi.z * S(0.05); cov[7] = ci.y * S(0.05); cov[8] = S(3) + pi.y;
     }
-    store4<S>(&quat[i], q[0], q[1], q[2], q[3]);
+#else
+    one_ring_covariance<S>(i, rowptr, colidx, weight, rest4, cur4, cov);
+#endif
+    const Vec4T<S> qprev = load4<S>(&quat[i]);
+    const S qp[4] = {qprev.x, qprev.y, qprev.z, qprev.w};
+    S q[4];
+#if defined(ARAP_DIAG_LOCAL) && ARAP_DIAG_LOCAL == 1          /* diagnostic build: gathers only, no rotation extraction */
+    store4<S>(&quat[i], cov[0] + cov[4] + cov[8] + qp[0], cov[1] + cov[2] + cov[3], cov[5] + cov[6], cov[7]);
+    (void)q; (void)redo_list; (void)redo_count;
+#else
+    if (rotation_from_covariance_newton_only<S>(cov, qp, q)) store4<S>(&quat[i], q[0], q[1], q[2], q[3]);
+    else redo_list[atomicAdd(redo_count, 1)] = i;
+#endif
+}
+
+// Jacobi SVD (reference arap.h:376-382) for the vertices the Newton kernel handed back. Grid-stride over the list.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) local_step_redo_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                 const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                                 const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
+                                                                 const int *__restrict__ redo_list, int *__restrict__ redo_count,
+                                                                 unsigned *__restrict__ done_counter) {
+    const int count = *redo_count;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const int i = redo_list[t];
+        S cov[9];
+        one_ring_covariance<S>(i, rowptr, colidx, weight, rest4, cur4, cov);
+        S q[4];
+        rotation_from_covariance<S>(cov, q);
+        store4<S>(&quat[i], q[0], q[1], q[2], q[3]);
+    }
+    // the last CTA to finish resets the list for the next local step
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) { *redo_count = 0; *done_counter = 0u; }
 }
 
 // =================================================================================================
@@ -382,6 +477,13 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                 Vec4T<S> pj[CH], cj[CH], qj[CH];
 #pragma unroll
                 for (int u = 0; u < CH; ++u) { pj[u] = load4<S>(&rest4[j[u]]); cj[u] = load4<S>(&cur4[j[u]]); qj[u] = load4<S>(&quat[j[u]]); }
+#if ARAP_RHS_GATE
+                {
+                    const S gate = gather_gate(pj) + gather_gate(cj) + gather_gate(qj);
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) w[u] += gate;
+                }
+#endif
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const S hw = S(0.5) * w[u];
@@ -644,24 +746,28 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(int n, const int *__rest
     if (grid_sum_last_block<1>(red, partials, counter, total)) *energy_out = total[0];
 }
 
-// ---- readout helpers ----------------------------------------------------------------------------
+// ---- readout helpers (internal order -> the user's numbering) -------------------------------------------------
 template <typename S, typename T>
-__global__ void __launch_bounds__(kBlock) export_positions_kernel(int n, const Vec4T<S> *__restrict__ cur4, T *__restrict__ out_xyz) {
+__global__ void __launch_bounds__(kBlock) export_positions_kernel(int n, const int *__restrict__ perm, const Vec4T<S> *__restrict__ cur4,
+                                                                  T *__restrict__ out_xyz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Vec4T<S> c = cur4[i];
-    out_xyz[3 * (size_t)i] = (T)c.x; out_xyz[3 * (size_t)i + 1] = (T)c.y; out_xyz[3 * (size_t)i + 2] = (T)c.z;
+    const size_t u = (size_t)perm[i];
+    out_xyz[3 * u] = (T)c.x; out_xyz[3 * u + 1] = (T)c.y; out_xyz[3 * u + 2] = (T)c.z;
 }
 
 template <typename S>
-__global__ void __launch_bounds__(kBlock) export_rotations_kernel(int n, const Vec4T<S> *__restrict__ quat, S *__restrict__ rot9) {
+__global__ void __launch_bounds__(kBlock) export_rotations_kernel(int n, const int *__restrict__ perm, const Vec4T<S> *__restrict__ quat,
+                                                                  S *__restrict__ rot9) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Vec4T<S> q = quat[i];
     S r[9];
     quat_to_matrix<S>(q.x, q.y, q.z, q.w, r);
+    const size_t u = (size_t)perm[i];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) rot9[9 * (size_t)i + k] = r[k];
+    for (int k = 0; k < 9; ++k) rot9[9 * u + k] = r[k];
 }
 
 }  // namespace arap

@@ -83,7 +83,7 @@ double estimate_rho(const HostCsr &A, const std::vector<double> &inv_diag) {
 
 // Greedy aggregation on the strength graph. agg[i] = aggregate id, or -1 if the row takes no part
 // in the coarse level (empty row, or no strong neighbour: Jacobi alone solves such rows).
-int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double theta, std::vector<int> &agg) {
+int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double theta, std::vector<int> &agg, const int *order) {
     const int n = A.n_rows;
     std::vector<unsigned char> strong((size_t)A.nnz(), 0);
     std::vector<unsigned char> has_strong((size_t)n, 0);
@@ -101,7 +101,8 @@ int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double thet
     for (int i = 0; i < n; ++i) if (!has_strong[i]) agg[i] = -1;
     int n_agg = 0;
     // pass 1: a vertex whose strong neighbourhood is untouched becomes a root
-    for (int i = 0; i < n; ++i) {
+    for (int t = 0; t < n; ++t) {
+        const int i = order ? order[t] : t;
         if (agg[i] != UNSET) continue;
         bool free_nbhd = true;
         for (int k = A.rowptr[i]; k < A.rowptr[i + 1] && free_nbhd; ++k)
@@ -124,7 +125,8 @@ int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double thet
     }
     for (int i = 0; i < n; ++i) if (agg[i] == UNSET && joined[i] != UNSET) agg[i] = joined[i];
     // pass 3: whatever is still unset forms new aggregates with its unset strong neighbours
-    for (int i = 0; i < n; ++i) {
+    for (int t = 0; t < n; ++t) {
+        const int i = order ? order[t] : t;
         if (agg[i] != UNSET) continue;
         agg[i] = n_agg;
         for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
@@ -257,7 +259,7 @@ bool dense_inverse(const HostCsr &A, std::vector<double> &inv) {
 
 template <typename S>
 void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *weight, const unsigned char *con,
-                        const MgSetupOptions &opt, MgHierarchyHost &out) {
+                        const MgSetupOptions &opt, MgHierarchyHost &out, const int *visit_order) {
     out.levels.clear();
     out.coarse_inv.clear();
     HostCsr A;
@@ -275,7 +277,7 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
         if (!last) {
             lvl.omega = 4.0 / (3.0 * estimate_rho(lvl.A, lvl.inv_diag));
             std::vector<int> agg;
-            const int n_agg = aggregate(lvl.A, lvl.inv_diag, opt.theta, agg);
+            const int n_agg = aggregate(lvl.A, lvl.inv_diag, opt.theta, agg, out.levels.empty() ? visit_order : nullptr);
             if (n_agg > 0 && n_agg < 0.8 * active) {
                 smoothed_prolongator(lvl.A, lvl.inv_diag, agg, n_agg, lvl.omega, lvl.P);
                 transpose(lvl.P, lvl.R);
@@ -299,8 +301,8 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
 }
 
 template void mg_build_hierarchy<float>(int, const int *, const int *, const float *, const unsigned char *,
-                                        const MgSetupOptions &, MgHierarchyHost &);
+                                        const MgSetupOptions &, MgHierarchyHost &, const int *);
 template void mg_build_hierarchy<double>(int, const int *, const int *, const double *, const unsigned char *,
-                                         const MgSetupOptions &, MgHierarchyHost &);
+                                         const MgSetupOptions &, MgHierarchyHost &, const int *);
 
 }  // namespace arap

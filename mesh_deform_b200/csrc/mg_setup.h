@@ -46,8 +46,12 @@ struct MgSetupOptions {
 };
 
 // w may be float or double (the handle precision); it is widened to double.
+// visit_order (optional, n_vertices entries): the order in which the greedy aggregation of the FINE level walks the
+// vertices. A spatially coherent order (Morton) gives compact, regular aggregates -- fewer CG iterations -- whatever
+// the memory order of the vertices is; coarse levels inherit it through the aggregate numbering.
 template <typename S>
 void mg_build_hierarchy(int n_vertices, const int *rowptr, const int *colidx, const S *weight,
-                        const unsigned char *is_constrained, const MgSetupOptions &opt, MgHierarchyHost &out);
+                        const unsigned char *is_constrained, const MgSetupOptions &opt, MgHierarchyHost &out,
+                        const int *visit_order = nullptr);
 
 }  // namespace arap

@@ -96,7 +96,7 @@ def test_first_local_step_rotations_match_oracle(meshes, golden):
     a.deform(1)
     o.deform(1)
     R, Ro = a.rotations(), o.rotations()
-    assert np.abs(R - Ro).max() < 1e-9
+    assert np.abs(R - Ro).max() < 1e-7          # Newton accepts at |omega| < 1e-4: remaining error ~1e-8
     assert np.abs(np.einsum("nij,nkj->nik", R, R) - np.eye(3)).max() < 1e-12
     assert np.abs(mesh - omesh).max() <= 1e-8 * bbox_diag(P)
 
