@@ -103,20 +103,22 @@ class ClockSampler:
 
 
 def algorithmic_bytes(V, nF, nnz, s):
-    """Per-launch algorithmic bytes (SURVEY.md section 8d / BASELINE.md section 3), s = sizeof(scalar)."""
+    """Per-launch algorithmic bytes (SURVEY.md section 8d / BASELINE.md section 3), s = sizeof(scalar).
+    Every array a kernel must touch is counted once; neighbour gathers are assumed to be served by cache."""
     d = nnz / V
     return {
-        "local_step": V * (15 * s + 4 + (4 + s) * d),
+        "local_step": V * (15 * s + 4 + (4 + s) * d),              # p, p' read, R written (as 9 scalars), CSR
         "rhs_residual": V * (18 * s + 8 + (4 + s) * d),
-        "cg_spmv": nF * ((s + 4) * (d + 1) + 4 + 6 * 8),          # CG vectors are always fp64
+        # matrix-free SpMV on the one-ring CSR, CG vectors fp64 (3 x 8 B per row), 1-byte row mask
+        "cg_spmv": nF * ((s + 4) * d + 4 + 1 + 2 * 24),
         "cg_update": nF * (6 * 24 + 8),
         "cg_direction": nF * (3 * 24 + 8),
         "apply_update": nF * (24 + 2 * 3 * s),
-        # multigrid-preconditioned path, fine level (coarse levels are < 20 % of the work and launch-bound)
-        "mg_fine_residual": nF * ((s + 4) * d + 4 + 8 + 3 * 24),
-        "mg_fine_postsmooth": nF * ((s + 4) * d + 4 + 8 + 8 + 3 * 24),
-        "cg_update_mg": nF * (7 * 24 + 8),
-        "cg_direction_mg": nF * (3 * 24),
+        # multigrid V-cycle, fine level: fp32 weights + float4 vectors, fp64 CG residual as right-hand side
+        "mg_fine_residual": nF * ((4 + 4) * d + 4 + 1 + 24 + 16 + 16),
+        "mg_fine_postsmooth": nF * ((4 + 4) * d + 4 + 1 + 8 + 24 + 16 + 16),
+        "cg_update_mg": nF * (6 * 24 + 8 + 16),
+        "cg_direction_mg": nF * (16 + 2 * 24),
     }
 
 

@@ -171,10 +171,20 @@ struct MgLevelDev {
     int n = 0;
     double omega = 2.0 / 3.0;
     DeviceBuffer<int> a_rowptr, a_colidx, p_rowptr, p_colidx, r_rowptr, r_colidx;
-    DeviceBuffer<double> a_val, p_val, r_val, inv_diag;
-    DeviceBuffer<Vec3d> b, x, x2, r;          // x: iterate before post-smoothing, x2: the level's result
+    DeviceBuffer<float> a_val, p_val, r_val, inv_diag;     // the V-cycle runs in fp32 (mg_kernels.cuh)
+    DeviceBuffer<MgVec> b, x, x2, r;          // x: iterate before post-smoothing, x2: the level's result
     int a_lanes = 1, r_lanes = 1;             // threads per row for A and R kernels
 };
+
+template <typename T>
+static cudaError_t upload_as_float(DeviceBuffer<float> &dst, const std::vector<T> &src, cudaStream_t stream, std::vector<float> &scratch) {
+    scratch.assign(src.begin(), src.end());
+    cudaError_t e = dst.ensure(scratch.size());
+    if (e != cudaSuccess || scratch.empty()) return e;
+    e = cudaMemcpyAsync(dst.ptr, scratch.data(), scratch.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream);      // scratch is reused by the next upload
+}
 
 static inline int pick_lanes(size_t nnz, size_t rows) {
     const double avg = rows ? (double)nnz / (double)rows : 0.0;
@@ -217,6 +227,8 @@ public:
     // internal (hot) order: perm[internal] = user index; the iteration kernels only ever see the hot CSR
     DeviceBuffer<int> perm, iperm, hot_rowptr, hot_colidx;
     DeviceBuffer<S> hot_weight;
+    DeviceBuffer<float> hot_weight_f32;            // fp32 copy for the multigrid preconditioner
+    DeviceBuffer<unsigned char> free_mask;         // 1 = free row (internal order)
     bool have_perm = false;
     std::vector<int> faces_host;                   // kept until the vertex order has been decided
     std::vector<int> mg_visit_order;               // Morton sequence of internal indices: aggregation order of the fine level
@@ -236,7 +248,7 @@ public:
     DeviceBuffer<unsigned char> staging;           // uploads / downloads in a foreign scalar type
 
     std::vector<std::unique_ptr<MgLevelDev>> mg;   // multigrid hierarchy (empty -> Jacobi preconditioner)
-    DeviceBuffer<double> mg_coarse_inv;
+    DeviceBuffer<float> mg_coarse_inv;
     bool mg_dense = false;
     bool use_mg = false;
     std::vector<unsigned char> mg_mask;            // constrained(+halo) mask the hierarchy was built for
@@ -428,11 +440,13 @@ public:
         ARAP_CUDA(hot_rowptr.ensure((size_t)V + 1));
         ARAP_CUDA(hot_colidx.ensure((size_t)nnz + 4));      // + 4: TMA bulk copies round a tile's span up to 16 bytes
         ARAP_CUDA(hot_weight.ensure((size_t)nnz + 4));
+        ARAP_CUDA(hot_weight_f32.ensure((size_t)nnz + 4));
+        ARAP_CUDA(free_mask.ensure((size_t)V + 1));
         if (V > 0) LAUNCH(ARAP_K_MISC, perm_row_count_kernel, grid_for((size_t)V), V, perm.ptr, rowptr.ptr, unique_count.ptr);
         { int rc = exclusive_scan(unique_count.ptr, V, hot_rowptr.ptr); if (rc) return rc; }
         if (V > 0)
             LAUNCH(ARAP_K_MISC, perm_csr_fill_kernel<S>, grid_for((size_t)V), V, perm.ptr, iperm.ptr, rowptr.ptr, colidx.ptr, weight.ptr,
-                   hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr);
+                   hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, hot_weight_f32.ptr);
         // ---- initializeMeshGeometry / Rotations / Constraints into the solver layout (arap.h:162-168,246-249,277-281)
         ARAP_CUDA(rest4.ensure((size_t)V));
         ARAP_CUDA(cur4.ensure((size_t)V));
@@ -440,7 +454,7 @@ public:
         ARAP_CUDA(inv_diag.ensure((size_t)V));
         if (V > 0)
             LAUNCH(ARAP_K_INIT_STATE, init_state_kernel<S>, grid_for((size_t)V), V, perm.ptr, rest_xyz.ptr, is_constrained.ptr, target_xyz.ptr,
-                   hot_rowptr.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr);
+                   hot_rowptr.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, free_mask.ptr);
         ARAP_CUDA(cudaGetLastError());
         ARAP_CUDA(cudaStreamSynchronize(stream));
         if (n_free == V && !transport) return ARAP_UNCONSTRAINED;        // arap.h:113-114: stays dirty, nothing solved
@@ -658,6 +672,7 @@ public:
         mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H,
                               (int)mg_visit_order.size() == V ? mg_visit_order.data() : nullptr);
         mg.clear();
+        std::vector<float> fscratch;
         for (size_t l = 0; l < H.levels.size(); ++l) {
             const MgLevelHost &hl = H.levels[l];
             std::unique_ptr<MgLevelDev> d(new MgLevelDev());
@@ -666,29 +681,29 @@ public:
             if (l > 0) {
                 ARAP_CUDA(upload_vector(d->a_rowptr, hl.A.rowptr, stream));
                 ARAP_CUDA(upload_vector(d->a_colidx, hl.A.colidx, stream));
-                ARAP_CUDA(upload_vector(d->a_val, hl.A.val, stream));
+                ARAP_CUDA(upload_as_float(d->a_val, hl.A.val, stream, fscratch));
                 ARAP_CUDA(d->b.ensure((size_t)d->n));
             }
-            ARAP_CUDA(upload_vector(d->inv_diag, hl.inv_diag, stream));
+            ARAP_CUDA(upload_as_float(d->inv_diag, hl.inv_diag, stream, fscratch));
             if (l + 1 < H.levels.size()) {
                 ARAP_CUDA(upload_vector(d->p_rowptr, hl.P.rowptr, stream));
                 ARAP_CUDA(upload_vector(d->p_colidx, hl.P.colidx, stream));
-                ARAP_CUDA(upload_vector(d->p_val, hl.P.val, stream));
+                ARAP_CUDA(upload_as_float(d->p_val, hl.P.val, stream, fscratch));
                 ARAP_CUDA(upload_vector(d->r_rowptr, hl.R.rowptr, stream));
                 ARAP_CUDA(upload_vector(d->r_colidx, hl.R.colidx, stream));
-                ARAP_CUDA(upload_vector(d->r_val, hl.R.val, stream));
+                ARAP_CUDA(upload_as_float(d->r_val, hl.R.val, stream, fscratch));
                 ARAP_CUDA(d->r.ensure((size_t)d->n));
             }
             ARAP_CUDA(d->x.ensure((size_t)d->n));
             ARAP_CUDA(d->x2.ensure((size_t)d->n));
-            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(Vec3d) * (size_t)(d->n > 0 ? d->n : 1), stream));
-            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(Vec3d) * (size_t)(d->n > 0 ? d->n : 1), stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)(d->n > 0 ? d->n : 1), stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)(d->n > 0 ? d->n : 1), stream));
             d->a_lanes = pick_lanes(hl.A.colidx.size(), (size_t)hl.A.n_rows);
             d->r_lanes = pick_lanes(hl.R.colidx.size(), (size_t)hl.R.n_rows);
             mg.push_back(std::move(d));
         }
         mg_dense = !H.coarse_inv.empty();
-        if (mg_dense) ARAP_CUDA(upload_vector(mg_coarse_inv, H.coarse_inv, stream));
+        if (mg_dense) ARAP_CUDA(upload_as_float(mg_coarse_inv, H.coarse_inv, stream, fscratch));
         ARAP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
         stats.mg_levels = (int)mg.size();
         stats.mg_operator_complexity = H.operator_complexity;
@@ -703,30 +718,31 @@ public:
         const int R = n_rows;                 // owned rows (== n_vertices on a single GPU)
         const int L = (int)mg.size();
         MgLevelDev &m0 = *mg[0];
-        Vec3d *z = m0.x2.ptr;
+        MgVec *z = m0.x2.ptr;
         if (L == 1) {
+            // tiny meshes: the whole system is the "coarsest level"; b = the fp64 CG residual converted to fp32
+            LAUNCH(ARAP_K_MISC, mg_to_float_kernel, grid_for((size_t)m0.n), m0.n, cg_r.ptr, m0.x.ptr);
             if (mg_dense) {
                 LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (m0.n + kWarpsPerBlock - 1) / kWarpsPerBlock, m0.n, mg_coarse_inv.ptr,
-                       cg_r.ptr, z, cg.ptr);
-            } else {
-                ARAP_DISPATCH_LANES(1, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)m0.n * LN), m0.n,
-                                              m0.a_rowptr.ptr, m0.a_colidx.ptr, m0.a_val.ptr, m0.inv_diag.ptr, 0.0, cg_r.ptr, m0.x.ptr, z, cg.ptr));
+                       m0.x.ptr, z, cg.ptr);
+            } else {      // no dense inverse (singular coarse operator): plain Jacobi, z = omega D^-1 r
+                LAUNCH(ARAP_K_MISC, mg_jacobi_kernel, grid_for((size_t)m0.n), m0.n, m0.inv_diag.ptr, (float)m0.omega, m0.x.ptr, z);
             }
-            LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_kernel, reduce_grid(cg_dot_rho_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+            LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             return reduce_stage(CG_STAGE_RHO, 3);
         }
         // down
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel<S>, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
-                       rest4.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
+                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
+                       free_mask.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.b.ptr, f.x.ptr, f.r.ptr, cg.ptr));
             }
             ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
-                                                  f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, c.omega, c.b.ptr,
+                                                  f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
                                                   c.x.ptr, cg.ptr));
         }
         // coarsest: exact dense solve, or one more damped-Jacobi step when the level is too large for a dense inverse
@@ -736,7 +752,7 @@ public:
                    cl.b.ptr, cl.x2.ptr, cg.ptr);
         } else {
             ARAP_DISPATCH_LANES(cl.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)cl.n * LN), cl.n,
-                                                   cl.a_rowptr.ptr, cl.a_colidx.ptr, cl.a_val.ptr, cl.inv_diag.ptr, cl.omega, cl.b.ptr,
+                                                   cl.a_rowptr.ptr, cl.a_colidx.ptr, cl.a_val.ptr, cl.inv_diag.ptr, (float)cl.omega, cl.b.ptr,
                                                    cl.x.ptr, cl.x2.ptr, cg.ptr));
         }
         // up
@@ -746,11 +762,11 @@ public:
             LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel<S>, reduce_grid(mg_fine_postsmooth_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
-                       hot_weight.ptr, rest4.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
+                       hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
-                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, f.omega, f.b.ptr,
+                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
@@ -764,10 +780,10 @@ public:
             const size_t smem = tma_spmv_smem_bytes<S>();
             begin_launch(ARAP_K_CG_SPMV);
             cg_spmv_tma_kernel<S><<<reduce_grid(cg_spmv_tma_kernel<S>, (size_t)R, smem), kBlock, smem, stream>>>(
-                R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
+                R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
             end_launch();
         } else {
-            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr,
+            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr,
                    cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
         }
     }
@@ -789,12 +805,12 @@ public:
         const int n3 = 3 * R, G3 = grid_for(((size_t)n3 + 1) / 2);
         MgLevelDev &m0 = *mg[0];
         { int rc = vcycle(); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const double *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
+        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const float *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
         { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
         launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
-               (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (double *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+               (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (float *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
         return reduce_stage(CG_STAGE_UPDATE_MG, 1);
     }
 
@@ -833,7 +849,7 @@ public:
             { int rc = reduce_stage(CG_STAGE_START_MG, 5); if (rc) return rc; }
         } else {
             LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (Vec3d *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+                   quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
             { int rc = reduce_stage(CG_STAGE_START_JACOBI, 5); if (rc) return rc; }
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
@@ -864,7 +880,7 @@ public:
             if (issued >= max_it || batch == 0) done = true;
             slot ^= 1;
         }
-        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, R, rest4.ptr, cg_x.ptr, cur4.ptr);
+        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, R, free_mask.ptr, cg_x.ptr, cur4.ptr);
         { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));

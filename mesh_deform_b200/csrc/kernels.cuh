@@ -200,7 +200,8 @@ template <typename S>
 __global__ void __launch_bounds__(kBlock) perm_csr_fill_kernel(int n, const int *__restrict__ perm, const int *__restrict__ iperm,
                                                                const int *__restrict__ rowptr_user, const int *__restrict__ colidx_user,
                                                                const S *__restrict__ weight_user, const int *__restrict__ rowptr_hot,
-                                                               int *__restrict__ colidx_hot, S *__restrict__ weight_hot) {
+                                                               int *__restrict__ colidx_hot, S *__restrict__ weight_hot,
+                                                               float *__restrict__ weight_hot_f32) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int u = perm[i];
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(kBlock) perm_csr_fill_kernel(int n, const int 
     for (int k = 0; k < len; ++k) {                 // the user row's column order is kept, so every sum runs in the reference's order
         colidx_hot[dst + k] = iperm[colidx_user[src + k]];
         weight_hot[dst + k] = weight_user[src + k];
+        weight_hot_f32[dst + k] = (float)weight_user[src + k];      // the fp32 multigrid preconditioner's copy
     }
 }
 
@@ -219,11 +221,12 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
                                                             const S *__restrict__ target_xyz, const int *__restrict__ rowptr,
                                                             const S *__restrict__ weight, Vec4T<S> *__restrict__ rest4,
                                                             Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
-                                                            double *__restrict__ inv_diag) {
+                                                            double *__restrict__ inv_diag, unsigned char *__restrict__ free_mask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t u = (size_t)perm[i];
     const bool con = is_constrained[u] != 0;
+    free_mask[i] = con ? 0 : 1;      // one byte per row for the solver kernels (reading rest4[i].w would pull a 32-byte sector)
     const S x = rest_xyz[3 * u], y = rest_xyz[3 * u + 1], z = rest_xyz[3 * u + 2];
     store4<S>(&rest4[i], x, y, z, con ? S(0) : S(1));
     if (con) store4<S>(&cur4[i], target_xyz[3 * u], target_xyz[3 * u + 1], target_xyz[3 * u + 2], S(0));
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                                                               const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
                                                               const double *__restrict__ inv_diag, double omega0,
                                                               Vec3d *__restrict__ r_out, Vec3d *__restrict__ d_out,
-                                                              Vec3d *__restrict__ x_out, Vec3d *__restrict__ x0_out,
+                                                              Vec3d *__restrict__ x_out, float4 *__restrict__ x0_out,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
     double red[5] = {0, 0, 0, 0, 0};   // rho x,y,z ; rr ; ref2
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
         x_out[i] = Vec3d{0, 0, 0};
         if (MG) {
             d_out[i] = Vec3d{0, 0, 0};
-            x0_out[i] = Vec3d{omega0 * z.x, omega0 * z.y, omega0 * z.z};
+            x0_out[i] = make_float4((float)(omega0 * z.x), (float)(omega0 * z.y), (float)(omega0 * z.z), 0.f);
         } else {
             d_out[i] = z;
         }
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
 // =================================================================================================
 template <typename S>
 __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                                                         const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                         const S *__restrict__ weight, const unsigned char *__restrict__ free_mask,
                                                          const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
                                                          double *__restrict__ partials, unsigned *__restrict__ counter,
                                                          CgScalars *__restrict__ cg) {
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__res
     double red[3] = {0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Vec3d out = {0, 0, 0};
-        if (rest4[i].w != S(0)) {
+        if (free_mask[i]) {
             constexpr int CH = kSpmvChunk;
             const int k0 = rowptr[i], k1 = rowptr[i + 1];
             const Vec3d di = d[i];
@@ -582,7 +585,7 @@ constexpr size_t tma_spmv_smem_bytes() { return 2 * (size_t)kTmaStageEntries * (
 
 template <typename S>
 __global__ void __launch_bounds__(kBlock) cg_spmv_tma_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                                                             const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
+                                                             const S *__restrict__ weight, const unsigned char *__restrict__ free_mask,
                                                              const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
                                                              double *__restrict__ partials, unsigned *__restrict__ counter,
                                                              CgScalars *__restrict__ cg) {
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_tma_kernel(int n, const int *_
         const int i = tile * kBlock + threadIdx.x;
         if (i < n) {
             Vec3d out = {0, 0, 0};
-            if (rest4[i].w != S(0)) {
+            if (free_mask[i]) {
                 const int ka = rowptr[i], kb = rowptr[i + 1];
                 const Vec3d di = d[i];
                 const int *cc = staged ? (s_c0 + stage * kTmaStageEntries - k0a) : colidx;      // both indexed by the global entry number
@@ -703,11 +706,11 @@ __global__ void __launch_bounds__(kBlock) cg_direction_kernel(int n, const doubl
 
 // p' += x on the free vertices (the scatter of arap.h:423-428); constrained vertices keep their targets.
 template <typename S>
-__global__ void __launch_bounds__(kBlock) apply_update_kernel(int n, const Vec4T<S> *__restrict__ rest4, const Vec3d *__restrict__ x,
+__global__ void __launch_bounds__(kBlock) apply_update_kernel(int n, const unsigned char *__restrict__ free_mask, const Vec3d *__restrict__ x,
                                                               Vec4T<S> *__restrict__ cur4) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (rest4[i].w == S(0)) return;
+    if (!free_mask[i]) return;
     const Vec4T<S> c = cur4[i];
     const Vec3d xi = x[i];
     store4<S>(&cur4[i], (S)((double)c.x + xi.x), (S)((double)c.y + xi.y), (S)((double)c.z + xi.z), c.w);

@@ -13,6 +13,14 @@ int mgshim_build(int V, const int *rowptr, const int *colidx, const double *w, c
     arap::mg_build_hierarchy<double>(V, rowptr, colidx, w, con, o, g_h);
     return (int)g_h.levels.size();
 }
+int mgshim_build_ordered(int V, const int *rowptr, const int *colidx, const double *w, const unsigned char *con, double theta, int coarse,
+                         const int *visit_order) {
+    arap::MgSetupOptions o;
+    if (theta > 0) o.theta = theta;
+    if (coarse > 0) o.coarse_size = coarse;
+    arap::mg_build_hierarchy<double>(V, rowptr, colidx, w, con, o, g_h, visit_order);
+    return (int)g_h.levels.size();
+}
 double mgshim_complexity() { return g_h.operator_complexity; }
 int mgshim_ncoarse() { return g_h.n_coarse; }
 int mgshim_has_inverse() { return g_h.coarse_inv.empty() ? 0 : 1; }
