@@ -546,6 +546,20 @@ public:
                 keyed[(size_t)v] = {key, v};
             }
             std::sort(keyed.begin(), keyed.end());
+            // Patches, not a space-filling curve: consecutive chunks of the Morton sequence are compact blobs of vertices
+            // (what one CTA should work on, so that most of its one-ring gathers hit lines it fetched itself), but INSIDE a
+            // chunk the user's own order is kept: meshes are usually locally row-coherent, and a warp whose 32 lanes walk a
+            // row gathers 32 contiguous neighbours -- a Z-curve inside the patch would scatter them.
+            {
+                const char *penv = getenv("ARAP_PATCH");
+                const int patch = penv ? atoi(penv) : kBlock;
+                if (patch > 1)
+                    for (int b = 0; b < owned; b += patch) {
+                        const int e = std::min(owned, b + patch);
+                        std::sort(keyed.begin() + b, keyed.begin() + e,
+                                  [](const std::pair<uint64_t, int> &x, const std::pair<uint64_t, int> &y) { return x.second < y.second; });
+                    }
+            }
             // Renumber the memory layout only if it buys locality: count the mesh edges whose end points are within a
             // few CTAs of each other, in the user's order and in Morton order. Generated / scanned-in-strips meshes are
             // often already well ordered (the headline icosphere is: renumbering it made the gather kernels 15 % slower).

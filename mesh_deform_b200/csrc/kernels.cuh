@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
 // Neighbours are gathered in chunks of kGather<S> so that all index loads, then all position gathers
 // of a chunk are in flight together (memory-level parallelism) before the arithmetic starts.
 #ifndef ARAP_LOCAL_CHUNK_F64
-#define ARAP_LOCAL_CHUNK_F64 3
+#define ARAP_LOCAL_CHUNK_F64 2
 #endif
 #ifndef ARAP_RHS_CHUNK_F64
 #define ARAP_RHS_CHUNK_F64 3
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
 #define ARAP_RHS_GATE 0
 #endif
 #ifndef ARAP_LOCAL_MIN_BLOCKS
-#define ARAP_LOCAL_MIN_BLOCKS 1
+#define ARAP_LOCAL_MIN_BLOCKS 4
 #endif
 template <typename S> struct GatherChunk;
 template <> struct GatherChunk<float> { static constexpr int value = 6; };
