@@ -187,13 +187,12 @@ static cudaError_t upload_as_float(DeviceBuffer<float> &dst, const std::vector<T
 }
 
 static inline int pick_lanes(size_t nnz, size_t rows) {
+    // threads per row of the coarse-level CSR kernels: the smallest power of two >= (average row length / kRowsPerLane)
+    static const double per_lane = getenv("ARAP_NNZ_PER_LANE") ? atof(getenv("ARAP_NNZ_PER_LANE")) : 3.0;
     const double avg = rows ? (double)nnz / (double)rows : 0.0;
-    if (avg < 4) return 1;
-    if (avg < 8) return 2;
-    if (avg < 16) return 4;
-    if (avg < 32) return 8;
-    if (avg < 64) return 16;
-    return 32;
+    int lanes = 1;
+    while (lanes < 32 && (double)lanes * per_lane < avg) lanes *= 2;
+    return lanes;
 }
 
 #define ARAP_DISPATCH_LANES(lanes, CALL)                                   \

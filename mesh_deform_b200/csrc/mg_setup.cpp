@@ -5,10 +5,39 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 
 namespace arap {
 
 namespace {
+
+// Run f(begin, end) over contiguous blocks of [0, n) on a few host threads. The block boundaries depend only on n and the
+// thread count, and every block's work is independent, so results do not depend on scheduling.
+int host_threads(int n) {
+    static const int cap = [] {
+        const char *env = getenv("ARAP_MG_THREADS");
+        if (env && atoi(env) > 0) return atoi(env);
+        unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+    }();
+    return std::max(1, std::min(cap, n / 8192));
+}
+
+template <class F>
+void parallel_blocks(int n, F f) {
+    const int threads = host_threads(n);
+    if (threads <= 1) { f(0, n, 0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        const int b = (int)((long long)n * t / threads), e = (int)((long long)n * (t + 1) / threads);
+        pool.emplace_back([=, &f] { f(b, e, t); });
+    }
+    for (auto &th : pool) th.join();
+}
+int parallel_block_count(int n) { return host_threads(n); }
 
 // Level 0: L = D - W on the free vertices, in full vertex index space (reference arap.h:310-334:
 // diagonal sums ALL neighbours, off-diagonals only free neighbours; constrained rows do not exist).
@@ -55,20 +84,27 @@ double estimate_rho(const HostCsr &A, const std::vector<double> &inv_diag) {
     std::vector<double> x((size_t)n), y((size_t)n);
     for (int i = 0; i < n; ++i) x[i] = inv_diag[i] > 0 ? 1.0 + 0.37 * ((i * 2654435761u) % 97) / 97.0 * ((i & 1) ? 1 : -1) : 0.0;
     double rho = 1.0;
-    for (int it = 0; it < 20; ++it) {
+    const int nb = parallel_block_count(n);
+    std::vector<double> pxax((size_t)nb), pxdx((size_t)nb), pnrm((size_t)nb);
+    for (int it = 0; it < 12; ++it) {
+        parallel_blocks(n, [&](int b, int e, int t) {
+            double xax = 0, xdx = 0, nrm = 0;
+            for (int i = b; i < e; ++i) {
+                double s = 0;
+                for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) s += A.val[k] * x[A.colidx[k]];
+                xax += x[i] * s;
+                if (inv_diag[i] > 0) xdx += x[i] * x[i] / inv_diag[i];
+                y[i] = s * inv_diag[i];
+                nrm += y[i] * y[i];
+            }
+            pxax[(size_t)t] = xax; pxdx[(size_t)t] = xdx; pnrm[(size_t)t] = nrm;
+        });
         double xax = 0, xdx = 0, nrm = 0;
-        for (int i = 0; i < n; ++i) {
-            double s = 0;
-            for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) s += A.val[k] * x[A.colidx[k]];
-            xax += x[i] * s;
-            if (inv_diag[i] > 0) xdx += x[i] * x[i] / inv_diag[i];
-            y[i] = s * inv_diag[i];
-            nrm += y[i] * y[i];
-        }
+        for (int t = 0; t < nb; ++t) { xax += pxax[(size_t)t]; xdx += pxdx[(size_t)t]; nrm += pnrm[(size_t)t]; }
         if (xdx > 0) rho = xax / xdx;
         nrm = std::sqrt(nrm);
         if (!(nrm > 0)) break;
-        for (int i = 0; i < n; ++i) x[i] = y[i] / nrm;
+        parallel_blocks(n, [&](int b, int e, int) { for (int i = b; i < e; ++i) x[i] = y[i] / nrm; });
     }
     double gersh = 0;                                  // Gershgorin bound on D^-1 A
     for (int i = 0; i < n; ++i) {
@@ -137,42 +173,75 @@ int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double thet
 }
 
 void sort_rows(HostCsr &M) {
-    std::vector<std::pair<int, double>> tmp;
-    for (int i = 0; i < M.n_rows; ++i) {
-        const int lo = M.rowptr[i], hi = M.rowptr[i + 1];
-        tmp.resize((size_t)(hi - lo));
-        for (int k = lo; k < hi; ++k) tmp[(size_t)(k - lo)] = {M.colidx[k], M.val[k]};
-        std::sort(tmp.begin(), tmp.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
-        for (int k = lo; k < hi; ++k) { M.colidx[k] = tmp[(size_t)(k - lo)].first; M.val[k] = tmp[(size_t)(k - lo)].second; }
-    }
+    parallel_blocks(M.n_rows, [&](int b, int e, int) {
+        std::vector<std::pair<int, double>> tmp;
+        for (int i = b; i < e; ++i) {
+            const int lo = M.rowptr[i], hi = M.rowptr[i + 1];
+            if (hi - lo <= 24) {                               // short rows: in-place insertion sort
+                for (int a = lo + 1; a < hi; ++a) {
+                    const int cj = M.colidx[a];
+                    const double cv = M.val[a];
+                    int q = a - 1;
+                    while (q >= lo && M.colidx[q] > cj) { M.colidx[q + 1] = M.colidx[q]; M.val[q + 1] = M.val[q]; --q; }
+                    M.colidx[q + 1] = cj;
+                    M.val[q + 1] = cv;
+                }
+                continue;
+            }
+            tmp.resize((size_t)(hi - lo));
+            for (int k = lo; k < hi; ++k) tmp[(size_t)(k - lo)] = {M.colidx[k], M.val[k]};
+            std::sort(tmp.begin(), tmp.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b2) { return a.first < b2.first; });
+            for (int k = lo; k < hi; ++k) { M.colidx[k] = tmp[(size_t)(k - lo)].first; M.val[k] = tmp[(size_t)(k - lo)].second; }
+        }
+    });
+}
+
+// Row-blocked assembly of a CSR matrix: every host thread produces the rows of its block into private vectors
+// (emit(i, cols, vals) appends row i), then the blocks are concatenated in order.
+template <class RowFn>
+void assemble_rows(int n_rows, int n_cols, HostCsr &C, RowFn row_fn) {
+    C.n_rows = n_rows;
+    C.n_cols = n_cols;
+    C.rowptr.assign((size_t)n_rows + 1, 0);
+    // (Measured: running this assembly on 8 host threads is SLOWER than on one -- the threads fight over page faults of
+    // their freshly grown output vectors -- so it stays sequential; only the read-only sweeps above use the thread pool.)
+    const int nb = 1;
+    std::vector<std::vector<int>> bc((size_t)nb);
+    std::vector<std::vector<double>> bv((size_t)nb);
+    auto one_block = [&](int b, int e, int t) {
+        std::vector<int> slot((size_t)n_cols, -1);
+        std::vector<int> &cols = bc[(size_t)t];
+        std::vector<double> &vals = bv[(size_t)t];
+        cols.reserve((size_t)(e - b) * 8);
+        vals.reserve((size_t)(e - b) * 8);
+        for (int i = b; i < e; ++i) {
+            const int start = (int)cols.size();
+            row_fn(i, start, cols, vals, slot);
+            for (int q = start; q < (int)cols.size(); ++q) slot[cols[q]] = -1;
+            C.rowptr[(size_t)i + 1] = (int)cols.size() - start;          // row length for now
+        }
+    };
+    one_block(0, n_rows, 0);
+    for (int i = 0; i < n_rows; ++i) C.rowptr[(size_t)i + 1] += C.rowptr[(size_t)i];
+    C.colidx.swap(bc[0]);
+    C.val.swap(bv[0]);
+    sort_rows(C);
 }
 
 // P = (I - omega D^-1 A) T, T piecewise constant over the aggregates.
 void smoothed_prolongator(const HostCsr &A, const std::vector<double> &inv_diag, const std::vector<int> &agg, int n_agg,
                           double omega, HostCsr &P) {
-    const int n = A.n_rows;
-    P.n_rows = n;
-    P.n_cols = n_agg;
-    P.rowptr.assign((size_t)n + 1, 0);
-    P.colidx.clear();
-    P.val.clear();
-    std::vector<int> slot((size_t)n_agg, -1);
-    for (int i = 0; i < n; ++i) {
-        const int start = (int)P.colidx.size();
-        if (inv_diag[i] > 0) {
-            if (agg[i] >= 0) { slot[agg[i]] = (int)P.colidx.size(); P.colidx.push_back(agg[i]); P.val.push_back(1.0); }
-            for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-                const int J = agg[A.colidx[k]];
-                if (J < 0) continue;
-                const double v = -omega * inv_diag[i] * A.val[k];
-                if (slot[J] >= start) P.val[(size_t)slot[J]] += v;
-                else { slot[J] = (int)P.colidx.size(); P.colidx.push_back(J); P.val.push_back(v); }
-            }
-            for (int q = start; q < (int)P.colidx.size(); ++q) slot[P.colidx[q]] = -1;
+    assemble_rows(A.n_rows, n_agg, P, [&](int i, int start, std::vector<int> &cols, std::vector<double> &vals, std::vector<int> &slot) {
+        if (!(inv_diag[i] > 0)) return;
+        if (agg[i] >= 0) { slot[agg[i]] = (int)cols.size(); cols.push_back(agg[i]); vals.push_back(1.0); }
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+            const int J = agg[A.colidx[k]];
+            if (J < 0) continue;
+            const double v = -omega * inv_diag[i] * A.val[k];
+            if (slot[J] >= start) vals[(size_t)slot[J]] += v;
+            else { slot[J] = (int)cols.size(); cols.push_back(J); vals.push_back(v); }
         }
-        P.rowptr[i + 1] = (int)P.colidx.size();
-    }
-    sort_rows(P);
+    });
 }
 
 void transpose(const HostCsr &M, HostCsr &T) {
@@ -194,27 +263,17 @@ void transpose(const HostCsr &M, HostCsr &T) {
 
 // C = A * B (Gustavson, sparse accumulator), rows sorted on exit.
 void spgemm(const HostCsr &A, const HostCsr &B, HostCsr &C) {
-    C.n_rows = A.n_rows;
-    C.n_cols = B.n_cols;
-    C.rowptr.assign((size_t)A.n_rows + 1, 0);
-    C.colidx.clear();
-    C.val.clear();
-    std::vector<int> slot((size_t)B.n_cols, -1);
-    for (int i = 0; i < A.n_rows; ++i) {
-        const int start = (int)C.colidx.size();
+    assemble_rows(A.n_rows, B.n_cols, C, [&](int i, int start, std::vector<int> &cols, std::vector<double> &vals, std::vector<int> &slot) {
         for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
             const int j = A.colidx[k];
             const double a = A.val[k];
             for (int q = B.rowptr[j]; q < B.rowptr[j + 1]; ++q) {
-                const int c = B.colidx[q];
-                if (slot[c] >= start) C.val[(size_t)slot[c]] += a * B.val[q];
-                else { slot[c] = (int)C.colidx.size(); C.colidx.push_back(c); C.val.push_back(a * B.val[q]); }
+                const int cc = B.colidx[q];
+                if (slot[cc] >= start) vals[(size_t)slot[cc]] += a * B.val[q];
+                else { slot[cc] = (int)cols.size(); cols.push_back(cc); vals.push_back(a * B.val[q]); }
             }
         }
-        for (int q = start; q < (int)C.colidx.size(); ++q) slot[C.colidx[q]] = -1;
-        C.rowptr[i + 1] = (int)C.colidx.size();
-    }
-    sort_rows(C);
+    });
 }
 
 // Dense inverse of the (SPD up to a null space) coarsest operator by Gauss-Jordan with partial pivoting.
@@ -257,13 +316,26 @@ bool dense_inverse(const HostCsr &A, std::vector<double> &inv) {
 
 }  // namespace
 
+struct PhaseTimer {
+    bool on = getenv("ARAP_MG_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *what, int level) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mg setup] level %d %-12s %7.1f ms\n", level, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 template <typename S>
 void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *weight, const unsigned char *con,
                         const MgSetupOptions &opt, MgHierarchyHost &out, const int *visit_order) {
+    PhaseTimer timer;
     out.levels.clear();
     out.coarse_inv.clear();
     HostCsr A;
     build_level0<S>(V, rowptr, colidx, weight, con, A);
+    timer.lap("level0", 0);
     const double fine_nnz = std::max(1, A.nnz());
     double total_nnz = 0;
     while (true) {
@@ -275,15 +347,22 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
         for (double d : lvl.inv_diag) if (d > 0) ++active;
         const bool last = active <= opt.coarse_size || (int)out.levels.size() + 1 >= opt.max_levels;
         if (!last) {
+            const int lv = (int)out.levels.size();
             lvl.omega = 4.0 / (3.0 * estimate_rho(lvl.A, lvl.inv_diag));
+            timer.lap("rho", lv);
             std::vector<int> agg;
             const int n_agg = aggregate(lvl.A, lvl.inv_diag, opt.theta, agg, out.levels.empty() ? visit_order : nullptr);
+            timer.lap("aggregate", lv);
             if (n_agg > 0 && n_agg < 0.8 * active) {
                 smoothed_prolongator(lvl.A, lvl.inv_diag, agg, n_agg, lvl.omega, lvl.P);
+                timer.lap("prolongator", lv);
                 transpose(lvl.P, lvl.R);
+                timer.lap("transpose", lv);
                 HostCsr AP;
                 spgemm(lvl.A, lvl.P, AP);
+                timer.lap("A*P", lv);
                 spgemm(lvl.R, AP, A);
+                timer.lap("R*(AP)", lv);
                 out.levels.push_back(std::move(lvl));
                 continue;
             }
@@ -294,6 +373,7 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
         if (lvl.A.n_rows <= opt.max_dense) {
             if (!dense_inverse(lvl.A, out.coarse_inv)) out.coarse_inv.clear();
         }
+        timer.lap("dense inverse", (int)out.levels.size());
         out.levels.push_back(std::move(lvl));
         break;
     }
