@@ -207,7 +207,11 @@ __global__ void __launch_bounds__(kBlock) perm_csr_fill_kernel(int n, const int 
     const int u = perm[i];
     const int src = rowptr_user[u], len = rowptr_user[u + 1] - src, dst = rowptr_hot[i];
     for (int k = 0; k < len; ++k) {                 // the user row's column order is kept, so every sum runs in the reference's order
+#if defined(ARAP_DIAG_SELFGATHER)
+        colidx_hot[dst + k] = (ARAP_DIAG_SELFGATHER == 1) ? i : min(n - 1, i + 1 + k);   /* diagnostic: gathers without inter-CTA reuse */
+#else
         colidx_hot[dst + k] = iperm[colidx_user[src + k]];
+#endif
         weight_hot[dst + k] = weight_user[src + k];
         weight_hot_f32[dst + k] = (float)weight_user[src + k];      // the fp32 multigrid preconditioner's copy
     }
@@ -249,7 +253,10 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
 #define ARAP_RHS_CHUNK_F64 3
 #endif
 #ifndef ARAP_SPMV_CHUNK
-#define ARAP_SPMV_CHUNK 2
+#define ARAP_SPMV_CHUNK 3
+#endif
+#ifndef ARAP_SPMV_MIN_BLOCKS
+#define ARAP_SPMV_MIN_BLOCKS 4
 #endif
 #ifndef ARAP_LOCAL_GATE
 #define ARAP_LOCAL_GATE 0
@@ -534,7 +541,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
 // Replaces SimplicialLDLT::solve (reference arap.h:418-421).
 // =================================================================================================
 template <typename S>
-__global__ void __launch_bounds__(kBlock) cg_spmv_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+__global__ void __launch_bounds__(kBlock, ARAP_SPMV_MIN_BLOCKS) cg_spmv_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                          const S *__restrict__ weight, const unsigned char *__restrict__ free_mask,
                                                          const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
                                                          double *__restrict__ partials, unsigned *__restrict__ counter,
