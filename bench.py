@@ -210,32 +210,28 @@ def batch_arm(args):
     torch.cuda.set_device(local_rank)
     from mesh_deform_b200 import capi, meshgen as G
     from mesh_deform_b200.sharding import shard_range
-    from oracle import oracle as O            # only for the host-side trajectory poses of the workload definition
     z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
     P, F = z["sphere_V"], z["sphere_F"]
     K = args.batch
     begin, end = shard_range(K, rank, world)
     handles = np.sort(np.unique(F[(F == G.SPHERE_HANDLE).any(1)]))
-    idx = np.concatenate([[G.SPHERE_ANCHOR], handles]).astype(np.int32)
 
     def T(t=(0, 0, 0), R=np.eye(3)):
         M = np.eye(4)
         M[:3, :3] = R
         M[:3, 3] = t
         return M
-    traj = O.TrajectorySE3Oracle()
+    traj = capi.TrajectorySE3()                # C ABI arap_trajectory_*: the product's own host-side trajectory
     prev = np.eye(4)
     for step in (T(), T((0.25, 0, 0)), T((0.5, 0, 0)), T(R=G.rot_x(np.pi / 2))):
         prev = prev @ step
         traj.addKeyPose(prev)
-    origin = traj(0.0)
-    targets = np.zeros((end - begin, idx.size, 3))
-    for m, k in enumerate(range(begin, end)):
-        pose = traj(k / max(1, K - 1))
-        targets[m, 0] = P[G.SPHERE_ANCHOR]
-        targets[m, 1:] = O.handle_targets(origin, pose, P[handles])
+    util = capi.DeformationUtil(P, handles, origin=traj(0.0))
+    poses = traj.sample(np.arange(begin, end) / max(1, K - 1))
     bdef = capi.BatchDeformation(P, F, end - begin, np.float64, device=local_rank)
-    bdef.setConstraints(idx, targets)
+    anchor = np.array([G.SPHERE_ANCHOR], np.int32)
+    bdef.setConstraints(anchor, np.repeat(P[anchor][None], end - begin, 0))
+    util.updateConstraints(poses, bdef)        # one call: every member's handle targets are computed on the device
     t0 = time.perf_counter()
     bdef.prepare()
     prepare_ms = 1e3 * (time.perf_counter() - t0)

@@ -29,6 +29,26 @@
 
 namespace deform {
 
+namespace detail {
+// Optional extension of the mesh concept (reference inc/deform/openmesh_adapter.h:49-118 has five members, called once
+// per vertex / face): a mesh whose vertex positions (and faces) are contiguous x,y,z (v0,v1,v2) arrays may also offer
+//     const Scalar *vertexData() const;   Scalar *vertexData();   const int *faceData() const;
+// and the solver then hands those pointers straight to the engine instead of making V (or F) accessor calls per
+// deform(). Detected at compile time; meshes with only the five required members work unchanged.
+template <class M> struct has_vertex_data {
+    template <class T> static char test(decltype(static_cast<const typename T::Scalar *>(static_cast<const T *>(nullptr)->vertexData())) *,
+                                        decltype(static_cast<typename T::Scalar *>(static_cast<T *>(nullptr)->vertexData())) *);
+    template <class T> static long test(...);
+    static const bool value = sizeof(test<M>(nullptr, nullptr)) == sizeof(char);
+};
+template <class M> struct has_face_data {
+    template <class T> static char test(decltype(static_cast<const int *>(static_cast<const T *>(nullptr)->faceData())) *);
+    template <class T> static long test(...);
+    static const bool value = sizeof(test<M>(nullptr)) == sizeof(char);
+};
+template <bool B> struct bool_tag {};
+}  // namespace detail
+
 /** Forward declaration of a class that may look into AsRigidAsPossibleDeformation (used by tests). */
 template <class T> class PrivateAccessor;
 
@@ -45,15 +65,7 @@ public:
     /** Construct from mesh; reads the topology once (reference arap.h:66-70,149-155). */
     explicit AsRigidAsPossibleDeformation(Mesh &mesh) : _mesh(mesh), _handle(nullptr), _dirty(true), _edgeWeights(this) {
         static_assert(sizeof(Scalar) == 4 || sizeof(Scalar) == 8, "PrecisionType must be float or double");
-        const Index nF = _mesh.numberOfFaces();
-        std::vector<int32_t> faces(3 * (size_t)nF);
-        for (Index f = 0; f < nF; ++f) {
-            const auto vids = _mesh.face(f);
-            faces[3 * (size_t)f + 0] = vids(0);
-            faces[3 * (size_t)f + 1] = vids(1);
-            faces[3 * (size_t)f + 2] = vids(2);
-        }
-        arap_create(faces.data(), nF, _mesh.numberOfVertices(), (int32_t)sizeof(Scalar), nullptr, &_handle);
+        createHandle(detail::bool_tag<detail::has_face_data<Mesh>::value && sizeof(int) == sizeof(int32_t)>());
     }
 
     ~AsRigidAsPossibleDeformation() { arap_destroy(_handle); }
@@ -77,9 +89,8 @@ public:
     bool deform(Index numberOfIterations) {
         if (!_handle) return false;
         typedef typename Mesh::Scalar MeshScalar;
-        const Index nV = _mesh.numberOfVertices();
-        _buffer.resize(3 * (size_t)nV * sizeof(MeshScalar));
-        MeshScalar *xyz = reinterpret_cast<MeshScalar *>(_buffer.data());
+        const detail::bool_tag<detail::has_vertex_data<Mesh>::value> bulk;
+        MeshScalar *xyz = vertexBuffer(bulk);               // the mesh's own storage when it offers vertexData()
 
         if (_dirty) {
             if (!_pendingIdx.empty()) {
@@ -88,12 +99,7 @@ public:
                 _pendingIdx.clear();
                 _pendingLoc.clear();
             }
-            for (Index v = 0; v < nV; ++v) {                 // initializeMeshGeometry (arap.h:162-168)
-                const auto p = _mesh.vertexLocation(v);
-                xyz[3 * (size_t)v + 0] = p(0);
-                xyz[3 * (size_t)v + 1] = p(1);
-                xyz[3 * (size_t)v + 2] = p(2);
-            }
+            readVertices(xyz, bulk);                         // initializeMeshGeometry (arap.h:162-168)
             const int rc = arap_prepare(_handle, xyz, (int32_t)sizeof(MeshScalar));
             if (rc == ARAP_UNCONSTRAINED) return true;       // arap.h:113-114 (stays dirty, no write-back)
             if (rc != ARAP_OK) return false;                 // arap.h:116-117
@@ -103,8 +109,7 @@ public:
         if (arap_iterate(_handle, numberOfIterations) != ARAP_OK) return false;
 
         if (arap_get_positions(_handle, xyz, (int32_t)sizeof(MeshScalar)) != ARAP_OK) return false;
-        for (Index i = 0; i < nV; ++i)                       // write-back (arap.h:133-135)
-            _mesh.vertexLocation(i, Eigen::Matrix<MeshScalar, 3, 1>(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]));
+        writeVertices(xyz, bulk);                            // write-back (arap.h:133-135)
         return true;
     }
 
@@ -122,6 +127,45 @@ public:
 
 private:
     template <class> friend class PrivateAccessor;
+
+    // ---- mesh ingest / write-back: bulk pointers when the mesh offers them, the five-member concept otherwise ----
+    void createHandle(detail::bool_tag<true>) {
+        arap_create(reinterpret_cast<const int32_t *>(_mesh.faceData()), _mesh.numberOfFaces(), _mesh.numberOfVertices(),
+                    (int32_t)sizeof(Scalar), nullptr, &_handle);
+    }
+    void createHandle(detail::bool_tag<false>) {             // initializeMeshTopology (arap.h:149-155)
+        const Index nF = _mesh.numberOfFaces();
+        std::vector<int32_t> faces(3 * (size_t)nF);
+        for (Index f = 0; f < nF; ++f) {
+            const auto vids = _mesh.face(f);
+            faces[3 * (size_t)f + 0] = vids(0);
+            faces[3 * (size_t)f + 1] = vids(1);
+            faces[3 * (size_t)f + 2] = vids(2);
+        }
+        arap_create(faces.data(), nF, _mesh.numberOfVertices(), (int32_t)sizeof(Scalar), nullptr, &_handle);
+    }
+    typename Mesh::Scalar *vertexBuffer(detail::bool_tag<true>) { return _mesh.vertexData(); }
+    typename Mesh::Scalar *vertexBuffer(detail::bool_tag<false>) {
+        _buffer.resize(3 * (size_t)_mesh.numberOfVertices() * sizeof(typename Mesh::Scalar));
+        return reinterpret_cast<typename Mesh::Scalar *>(_buffer.data());
+    }
+    void readVertices(typename Mesh::Scalar *, detail::bool_tag<true>) {}
+    void readVertices(typename Mesh::Scalar *xyz, detail::bool_tag<false>) {
+        const Index nV = _mesh.numberOfVertices();
+        for (Index v = 0; v < nV; ++v) {
+            const auto p = _mesh.vertexLocation(v);
+            xyz[3 * (size_t)v + 0] = p(0);
+            xyz[3 * (size_t)v + 1] = p(1);
+            xyz[3 * (size_t)v + 2] = p(2);
+        }
+    }
+    void writeVertices(const typename Mesh::Scalar *, detail::bool_tag<true>) {}
+    void writeVertices(const typename Mesh::Scalar *xyz, detail::bool_tag<false>) {
+        typedef typename Mesh::Scalar MeshScalar;
+        const Index nV = _mesh.numberOfVertices();
+        for (Index i = 0; i < nV; ++i)
+            _mesh.vertexLocation(i, Eigen::Matrix<MeshScalar, 3, 1>(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]));
+    }
 
 #ifdef DEFORM_HAVE_EIGEN
     typedef Eigen::SparseMatrix<Scalar, Eigen::RowMajor> SparseMatrix;

@@ -55,6 +55,17 @@ public:
     int numberOfFaces() const { return (int)_mesh.n_faces(); }
     int numberOfVertices() const { return (int)_mesh.n_vertices(); }
 
+    /** Optional bulk access (see deform/arap.h): OpenMesh keeps its points in one contiguous property array of
+     *  VectorT<Scalar,3> in vertex-index order, so the solver can read and write all positions with one copy each
+     *  instead of n_vertices() accessor calls. Faces are not stored contiguously; `face()` stays the only way. */
+    const Scalar *vertexData() const {
+        static_assert(sizeof(typename Mesh::Point) == 3 * sizeof(Scalar), "OpenMesh points are expected to be packed x,y,z");
+        return _mesh.n_vertices() ? &_mesh.point(_mesh.vertex_handle(0u))[0] : nullptr;
+    }
+    Scalar *vertexData() {
+        return _mesh.n_vertices() ? &_mesh.point(_mesh.vertex_handle(0u))[0] : nullptr;
+    }
+
 private:
     Mesh &_mesh;
 };

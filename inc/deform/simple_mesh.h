@@ -76,6 +76,11 @@ public:
     int numberOfFaces() const { return (int)_mesh.triangles.size() / 3; }      // required
     int numberOfVertices() const { return (int)_mesh.positions.size() / 3; }   // required
 
+    // optional bulk accessors (see deform/arap.h): contiguous x,y,z per vertex and v0,v1,v2 per face
+    const Scalar *vertexData() const { return _mesh.positions.data(); }
+    Scalar *vertexData() { return _mesh.positions.data(); }
+    const int *faceData() const { return _mesh.triangles.data(); }
+
 private:
     Mesh &_mesh;
 };

@@ -164,6 +164,30 @@ int arap_batch_get_positions(arap_batch *b, void *out_xyz /* batch_size x V x 3 
 /* The underlying handle (statistics, profiling, timers, total energy over all members). */
 arap_handle *arap_batch_handle(arap_batch *b);
 
+/* ---- handle poses: DeformationUtil / TrajectorySE3 front end ---------------------------------------------------
+ * The reference drives its handles with rigid transforms: DeformationUtil::updateConstraints
+ * (reference inc/deform/deformation_util.h:48-57) calls setConstraint(h_i, origin * t * origin^-1 * p0_i) once per
+ * handle, with t taken from TrajectorySE3::operator() (reference inc/deform/trajectory.h:61-73). These entry points
+ * do the same per CALL instead of per vertex: the handle indices, their rest positions and one 4x4 transform per
+ * batch member go to the device, and a kernel writes every member's targets into the constraint table.
+ * All transforms are 4x4 ROW-MAJOR arrays of 16 doubles. */
+typedef struct arap_trajectory arap_trajectory;
+int arap_trajectory_create(arap_trajectory **out);
+void arap_trajectory_destroy(arap_trajectory *t);
+/* TrajectorySE3::addKeyPose (trajectory.h:55-59). */
+int arap_trajectory_add_key_pose(arap_trajectory *t, const double *pose16);
+/* TrajectorySE3::operator() at n times in [0,1] (trajectory.h:61-73); needs >= 4 key poses (cubic spline), else
+ * ARAP_ERR_INVALID. poses16_out: n x 16. */
+int arap_trajectory_evaluate(arap_trajectory *t, int32_t n, const double *times, double *poses16_out);
+/* out = origin * pose * origin^-1, origin^-1 as an isometry inverse (deformation_util.h:38,51). */
+int arap_rigid_conjugate(const double *origin16, const double *pose16, double *out16);
+/* setConstraint(vertex_idx[k], transform * rest_xyz[k]) for k < n (deformation_util.h:51-55); marks the handle dirty. */
+int arap_set_rigid_constraints(arap_handle *h, int32_t n, const int32_t *vertex_idx, const void *rest_xyz, int32_t rest_scalar_bytes,
+                               const double *transform16);
+/* The same for every member of a batch: member m gets transforms16[m] (batch_size x 16) applied to the shared rest_xyz. */
+int arap_batch_set_rigid_constraints(arap_batch *b, int32_t n, const int32_t *vertex_idx, const void *rest_xyz,
+                                     int32_t rest_scalar_bytes, const double *transforms16);
+
 /* ---- one mesh partitioned over several GPUs (BASELINE.json configs[4]) ------------------------------------------
  * Every rank creates an ordinary handle for ITS local mesh: the vertices it owns first (local indices
  * [0, n_owned)), then its halo (one-ring neighbours owned by other ranks, grouped by owner), and every face that

@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
     "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
     "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle", "arap_comm_unique_id", "arap_attach_partition",
+    "arap_trajectory_create", "arap_trajectory_destroy", "arap_trajectory_add_key_pose", "arap_trajectory_evaluate",
+    "arap_rigid_conjugate", "arap_set_rigid_constraints", "arap_batch_set_rigid_constraints",
 )
 
 
@@ -112,6 +114,14 @@ def lib():
     L.arap_batch_get_positions.argtypes = [vp, vp, i32]
     L.arap_batch_handle.argtypes = [vp]
     L.arap_batch_handle.restype = vp
+    L.arap_trajectory_create.argtypes = [C.POINTER(vp)]
+    L.arap_trajectory_destroy.argtypes = [vp]
+    L.arap_trajectory_destroy.restype = None
+    L.arap_trajectory_add_key_pose.argtypes = [vp, vp]
+    L.arap_trajectory_evaluate.argtypes = [vp, i32, vp, vp]
+    L.arap_rigid_conjugate.argtypes = [vp, vp, vp]
+    L.arap_set_rigid_constraints.argtypes = [vp, i32, vp, vp, i32, vp]
+    L.arap_batch_set_rigid_constraints.argtypes = [vp, i32, vp, vp, i32, vp]
     L.arap_comm_unique_id.argtypes = [vp, i32]
     L.arap_attach_partition.argtypes = [vp, C.POINTER(PartitionPlan), i32, i32, i32, vp, i32]
     L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -211,6 +221,15 @@ class AsRigidAsPossibleDeformation:
             loc = loc.astype(np.float64)
         self._check(lib().arap_set_constraints(self._h, idx.size, _ptr(idx), _ptr(loc), loc.dtype.itemsize))
 
+
+    def setRigidConstraints(self, indices, rest_points, transform):
+        """setConstraint(indices[k], transform @ rest_points[k]) in one call (DeformationUtil::updateConstraints,
+        reference deformation_util.h:48-57); transform: 4x4."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        pts = np.ascontiguousarray(rest_points, dtype=np.float64).reshape(-1, 3)
+        T = np.ascontiguousarray(transform, dtype=np.float64).reshape(4, 4)
+        assert pts.shape[0] == idx.size
+        self._check(lib().arap_set_rigid_constraints(self._h, idx.size, _ptr(idx), _ptr(pts), 8, _ptr(T)))
     def deform(self, numberOfIterations):
         """-> bool, like the reference (False only when the linear system is unusable)."""
         rc = lib().arap_deform(self._h, _ptr(self.mesh), self.mesh.dtype.itemsize, int(numberOfIterations))
@@ -296,6 +315,73 @@ class AsRigidAsPossibleDeformation:
         self._check(lib().arap_synchronize(self._h))
 
 
+class TrajectorySE3:
+    """deform::TrajectorySE3 (reference inc/deform/trajectory.h:33-83) over the C ABI's arap_trajectory_*: key poses in,
+    smooth pose curve out (cubic B-spline through the se(3) logs). Poses are 4x4 numpy arrays."""
+
+    def __init__(self):
+        self._t = C.c_void_p()
+        rc = lib().arap_trajectory_create(C.byref(self._t))
+        if rc != ARAP_OK:
+            self._t = None
+            raise ArapError(rc, "arap_trajectory_create failed")
+
+    def close(self):
+        if getattr(self, "_t", None):
+            lib().arap_trajectory_destroy(self._t)
+            self._t = None
+
+    __del__ = close
+
+    def addKeyPose(self, transform):
+        T = np.ascontiguousarray(transform, dtype=np.float64).reshape(4, 4)
+        rc = lib().arap_trajectory_add_key_pose(self._t, _ptr(T))
+        if rc != ARAP_OK:
+            raise ArapError(rc, "arap_trajectory_add_key_pose failed")
+        return T.copy()
+
+    def sample(self, times):
+        """(n, 4, 4) poses at `times` (each in [0,1])."""
+        u = np.ascontiguousarray(np.atleast_1d(times), dtype=np.float64)
+        out = np.zeros((u.size, 4, 4))
+        rc = lib().arap_trajectory_evaluate(self._t, u.size, _ptr(u), _ptr(out))
+        if rc != ARAP_OK:
+            raise ArapError(rc, lib().arap_create_error().decode())
+        return out
+
+    def __call__(self, time):
+        return self.sample([time])[0]
+
+
+def rigid_conjugate(origin, pose):
+    """origin @ pose @ origin^-1 (isometry inverse), reference deformation_util.h:38,51."""
+    a = np.ascontiguousarray(origin, dtype=np.float64).reshape(4, 4)
+    b = np.ascontiguousarray(pose, dtype=np.float64).reshape(4, 4)
+    out = np.zeros((4, 4))
+    rc = lib().arap_rigid_conjugate(_ptr(a), _ptr(b), _ptr(out))
+    if rc != ARAP_OK:
+        raise ArapError(rc, "arap_rigid_conjugate failed")
+    return out
+
+
+class DeformationUtil:
+    """deform::DeformationUtil (reference inc/deform/deformation_util.h:19-64): remembers where the handles are at
+    construction; updateConstraints(t, arap) pins every handle at origin @ t @ origin^-1 @ p0 in ONE call. `arap` may
+    be an AsRigidAsPossibleDeformation (t: 4x4) or a BatchDeformation (t: (K,4,4), one transform per member)."""
+
+    def __init__(self, mesh_positions, handles, origin=None):
+        self.handles = np.ascontiguousarray(handles, dtype=np.int32)
+        self.points = np.array(np.asarray(mesh_positions, dtype=np.float64)[self.handles])
+        self.origin = np.eye(4) if origin is None else np.array(origin, dtype=np.float64).reshape(4, 4)
+
+    def updateConstraints(self, t, arap):
+        t = np.asarray(t, dtype=np.float64)
+        if t.ndim == 2:
+            arap.setRigidConstraints(self.handles, self.points, rigid_conjugate(self.origin, t))
+        else:
+            arap.setRigidConstraints(self.handles, self.points, np.stack([rigid_conjugate(self.origin, x) for x in t]))
+
+
 class BatchDeformation:
     """K independent deformations of one mesh advanced together (C ABI arap_batch_*): same topology, rest pose and
     constrained vertex set, per-member targets -- BASELINE.json configs[3] (one member per trajectory key frame)."""
@@ -334,6 +420,15 @@ class BatchDeformation:
         tgt = np.ascontiguousarray(targets, dtype=np.float64)
         assert tgt.shape == (self.K, idx.size, 3)
         self._check(lib().arap_batch_set_constraints(self._b, idx.size, _ptr(idx), _ptr(tgt), 8))
+
+    def setRigidConstraints(self, indices, rest_points, transforms):
+        """Member m: setConstraint(indices[k], transforms[m] @ rest_points[k]); transforms: (K, 4, 4). The targets are
+        computed on the device (arap_batch_set_rigid_constraints)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        pts = np.ascontiguousarray(rest_points, dtype=np.float64).reshape(-1, 3)
+        T = np.ascontiguousarray(transforms, dtype=np.float64)
+        assert pts.shape[0] == idx.size and T.shape == (self.K, 4, 4)
+        self._check(lib().arap_batch_set_rigid_constraints(self._b, idx.size, _ptr(idx), _ptr(pts), 8, _ptr(T)))
 
     def prepare(self):
         return self._check(lib().arap_batch_prepare(self._b, _ptr(self.rest), 8))

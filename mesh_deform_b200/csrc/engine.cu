@@ -10,6 +10,7 @@
 #include "mg_kernels.cuh"
 #include "mg_setup.h"
 #include "partition.cuh"
+#include "../../inc/deform/detail/se3_spline.h"
 
 #include <cuda_runtime.h>
 
@@ -79,6 +80,8 @@ class EngineBase {
 public:
     virtual ~EngineBase() {}
     virtual int set_constraints(int n, const int *idx, const void *xyz, int scalar_bytes) = 0;
+    virtual int set_rigid_constraints(int n, int batch, int member_stride, const int *idx, const void *rest, int scalar_bytes,
+                                      const double *transforms16) = 0;
     virtual int prepare(const void *rest_xyz, int scalar_bytes) = 0;
     virtual int iterate(int n) = 0;
     virtual int get_positions(void *out, int scalar_bytes) = 0;
@@ -388,6 +391,39 @@ public:
         end_launch();
         ARAP_CUDA(cudaGetLastError());
         ARAP_CUDA(cudaStreamSynchronize(stream));   // host buffers are caller-owned: finish the copies before returning
+        return ARAP_OK;
+    }
+
+    int set_rigid_constraints(int n, int batch, int member_stride, const int *idx, const void *rest, int scalar_bytes,
+                              const double *transforms16) override {
+        if (n < 0 || batch <= 0 || (n > 0 && (!idx || !rest || !transforms16)) || (scalar_bytes != 4 && scalar_bytes != 8))
+            return fail(ARAP_ERR_INVALID, "set_rigid_constraints: bad arguments");
+        for (int k = 0; k < n; ++k)
+            if (idx[k] < 0 || idx[k] >= member_stride || (long long)idx[k] + (long long)(batch - 1) * member_stride >= n_vertices)
+                return fail(ARAP_ERR_INVALID, "set_rigid_constraints: vertex index out of range");
+        dirty = true;                                                    // arap.h:84
+        if (n == 0) return ARAP_OK;
+        std::vector<double> rows(12 * (size_t)batch);                    // top three rows of each 4x4
+        for (int m = 0; m < batch; ++m) std::memcpy(&rows[12 * (size_t)m], transforms16 + 16 * (size_t)m, 12 * sizeof(double));
+        const size_t idx_bytes = sizeof(int) * (size_t)n, xyz_bytes = (size_t)scalar_bytes * 3 * (size_t)n, tr_bytes = rows.size() * sizeof(double);
+        const size_t xyz_off = (idx_bytes + 15) & ~(size_t)15, tr_off = (xyz_off + xyz_bytes + 15) & ~(size_t)15;
+        ARAP_CUDA(staging.ensure(tr_off + tr_bytes));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr, idx, idx_bytes, cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr + xyz_off, rest, xyz_bytes, cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaMemcpyAsync(staging.ptr + tr_off, rows.data(), tr_bytes, cudaMemcpyHostToDevice, stream));
+        begin_launch(ARAP_K_MISC);
+        const unsigned grid = grid_for((size_t)n * (size_t)batch);
+        if (scalar_bytes == 4)
+            set_rigid_constraints_kernel<S, float><<<grid, kBlock, 0, stream>>>(
+                n, batch, member_stride, (const int *)staging.ptr, (const float *)(staging.ptr + xyz_off),
+                (const double *)(staging.ptr + tr_off), n_vertices, is_constrained.ptr, target_xyz.ptr);
+        else
+            set_rigid_constraints_kernel<S, double><<<grid, kBlock, 0, stream>>>(
+                n, batch, member_stride, (const int *)staging.ptr, (const double *)(staging.ptr + xyz_off),
+                (const double *)(staging.ptr + tr_off), n_vertices, is_constrained.ptr, target_xyz.ptr);
+        end_launch();
+        ARAP_CUDA(cudaGetLastError());
+        ARAP_CUDA(cudaStreamSynchronize(stream));   // host buffers (and `rows`) must outlive the copies
         return ARAP_OK;
     }
 
@@ -1240,6 +1276,54 @@ int arap_batch_iterate(arap_batch *b, int32_t n_iterations) { return b ? arap_it
 
 int arap_batch_get_positions(arap_batch *b, void *out_xyz, int32_t out_scalar_bytes) {
     return b ? arap_get_positions(b->handle, out_xyz, out_scalar_bytes) : ARAP_ERR_INVALID;
+}
+
+// ---- handle poses: trajectory + rigid constraint front end (host arithmetic shared with inc/deform/trajectory.h) --------
+struct arap_trajectory {
+    deform::detail::SplineSE3<double> spline;
+};
+
+int arap_trajectory_create(arap_trajectory **out) {
+    if (!out) return ARAP_ERR_INVALID;
+    *out = new (std::nothrow) arap_trajectory;
+    return *out ? ARAP_OK : ARAP_ERR_ALLOC;
+}
+void arap_trajectory_destroy(arap_trajectory *t) { delete t; }
+
+int arap_trajectory_add_key_pose(arap_trajectory *t, const double *pose16) {
+    if (!t || !pose16) return ARAP_ERR_INVALID;
+    t->spline.addKeyPose(pose16);
+    return ARAP_OK;
+}
+
+int arap_trajectory_evaluate(arap_trajectory *t, int32_t n, const double *times, double *poses16_out) {
+    if (!t || n < 0 || (n > 0 && (!times || !poses16_out))) return ARAP_ERR_INVALID;
+    if (t->spline.numberOfKeyPoses() < 4) {
+        arap::g_create_error = "arap_trajectory_evaluate: a cubic trajectory needs at least 4 key poses";
+        return ARAP_ERR_INVALID;
+    }
+    for (int k = 0; k < n; ++k) t->spline.pose(times[k], poses16_out + 16 * (size_t)k);
+    return ARAP_OK;
+}
+
+int arap_rigid_conjugate(const double *origin16, const double *pose16, double *out16) {
+    if (!origin16 || !pose16 || !out16) return ARAP_ERR_INVALID;
+    deform::detail::conjugate_rigid<double>(origin16, pose16, out16);
+    return ARAP_OK;
+}
+
+int arap_set_rigid_constraints(arap_handle *h, int32_t n, const int32_t *vertex_idx, const void *rest_xyz, int32_t rest_scalar_bytes,
+                               const double *transform16) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->set_rigid_constraints(n, 1, h->engine->n_vertices, vertex_idx, rest_xyz, rest_scalar_bytes, transform16);
+}
+
+int arap_batch_set_rigid_constraints(arap_batch *b, int32_t n, const int32_t *vertex_idx, const void *rest_xyz,
+                                     int32_t rest_scalar_bytes, const double *transforms16) {
+    if (!b) return ARAP_ERR_INVALID;
+    arap_handle *h = b->handle;
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->set_rigid_constraints(n, b->batch, b->n_vertices, vertex_idx, rest_xyz, rest_scalar_bytes, transforms16);
 }
 
 int arap_comm_unique_id(void *out_bytes, int32_t capacity) {

@@ -164,6 +164,25 @@ __global__ void __launch_bounds__(kBlock) set_constraints_kernel(int n, const in
     for (int d = 0; d < 3; ++d) target_xyz[3 * (size_t)v + d] = (S)xyz[3 * (size_t)k + d];
 }
 
+// DeformationUtil::updateConstraints (deformation_util.h:48-57) for a whole batch: member m's handle k goes to
+// transform_m * rest_k. transforms: 12 doubles per member (the top three rows of the 4x4, row-major).
+template <typename S, typename T>
+__global__ void __launch_bounds__(kBlock) set_rigid_constraints_kernel(int n, int batch, int member_stride, const int *__restrict__ idx,
+                                                                       const T *__restrict__ rest, const double *__restrict__ transforms,
+                                                                       int n_vertices, unsigned char *__restrict__ is_constrained,
+                                                                       S *__restrict__ target_xyz) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * batch) return;
+    const int m = (int)(t / n), k = (int)(t - (size_t)m * n);
+    const long long v = (long long)idx[k] + (long long)m * member_stride;
+    if (idx[k] < 0 || v >= n_vertices) return;
+    const double *M = transforms + 12 * (size_t)m;
+    const double x = (double)rest[3 * (size_t)k], y = (double)rest[3 * (size_t)k + 1], z = (double)rest[3 * (size_t)k + 2];
+    is_constrained[v] = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) target_xyz[3 * (size_t)v + d] = (S)(M[4 * d] * x + M[4 * d + 1] * y + M[4 * d + 2] * z + M[4 * d + 3]);
+}
+
 template <typename S, typename T>
 __global__ void __launch_bounds__(kBlock) cast_xyz_kernel(size_t n, const T *__restrict__ in, S *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

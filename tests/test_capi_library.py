@@ -10,6 +10,7 @@ import pytest
 
 from conftest import ROOT
 from oracle import oracle as O
+from mesh_deform_b200 import capi
 
 
 def header_symbols():
@@ -140,3 +141,47 @@ def test_device_cotan_math_is_bit_exact(host_math, meshes, dt, sfx):
         for t in vals[1:]:
             s = dt(s + t)
         assert lookup[(x, y)] == s and lookup[(y, x)] == s
+
+
+def test_trajectory_abi_matches_reference_pins_and_oracle(trajectory_golden):
+    """arap_trajectory_* (host arithmetic, no device needed): the endpoint pins of reference tests/test_trajectory.cpp:
+    17-39, the committed oracle samples in between, and a 7-key-pose curve (interior knots) against the oracle."""
+    poses = trajectory_golden["key_poses"]
+    path = capi.TrajectorySE3()
+    for p_ in poses:
+        back = path.addKeyPose(p_)
+        assert np.array_equal(back, p_)                                   # addKeyPose returns its argument (trajectory.h:58)
+    for u, want in ((0.0, poses[0]), (1.0, poses[3])):
+        got = path(u)
+        assert np.linalg.norm(got - want) <= 1e-3 * min(np.linalg.norm(got), np.linalg.norm(want))
+    got = path.sample(trajectory_golden["u"])
+    assert np.abs(got - trajectory_golden["samples"]).max() < 1e-12
+    rng = np.random.default_rng(5)
+    a, b = capi.TrajectorySE3(), O.TrajectorySE3Oracle()
+    for _ in range(7):
+        xi = rng.standard_normal(6) * np.array([1, 1, 1, 0.6, 0.6, 0.6])
+        T = O.se3_exp(xi)
+        a.addKeyPose(T)
+        b.addKeyPose(T)
+    us = np.linspace(0, 1, 41)
+    want = np.stack([b(float(u)) for u in us])
+    assert np.abs(a.sample(us) - want).max() < 1e-11
+
+
+def test_trajectory_abi_rejects_too_few_key_poses():
+    path = capi.TrajectorySE3()
+    for _ in range(3):
+        path.addKeyPose(np.eye(4))
+    with pytest.raises(capi.ArapError):
+        path(0.5)
+
+
+def test_rigid_conjugate_matches_oracle():
+    """arap_rigid_conjugate = origin * t * origin^-1 of reference deformation_util.h:51."""
+    rng = np.random.default_rng(11)
+    origin = O.se3_exp(rng.standard_normal(6))
+    t = O.se3_exp(rng.standard_normal(6) * 0.5)
+    pts = rng.standard_normal((9, 3))
+    M = capi.rigid_conjugate(origin, t)
+    got = pts @ M[:3, :3].T + M[:3, 3]
+    assert np.abs(got - O.handle_targets(origin, t, pts)).max() < 1e-13

@@ -57,8 +57,10 @@ def test_cotan_cpp_reference_test(cpp_build):
 
 
 @pytest.mark.gpu
-def test_demo_bar_cpp_matches_oracle(cpp_build, meshes, golden, tmp_path):
-    """reference examples/deform_bar.cpp's workload through the C++ facade (float mesh, double precision)."""
+@pytest.mark.parametrize("mesh_access", ["bulk", "minimal"])
+def test_demo_bar_cpp_matches_oracle(cpp_build, meshes, golden, tmp_path, mesh_access):
+    """reference examples/deform_bar.cpp's workload through the C++ facade (float mesh, double precision), with the
+    mesh read/written through the bulk pointers and through the reference's five-member mesh concept."""
     P, F = meshes["bar"]
     obj = tmp_path / "bar.obj"
     with open(obj, "w") as fh:
@@ -70,7 +72,7 @@ def test_demo_bar_cpp_matches_oracle(cpp_build, meshes, golden, tmp_path):
     with open(con, "w") as fh:
         for i, t in zip(golden["bar_idx"], golden["bar_tgt"]):
             fh.write("%d %.17g %.17g %.17g\n" % (i, t[0], t[1], t[2]))
-    out = subprocess.run([os.path.join(cpp_build, "demo_bar"), str(obj), str(con), "10"], capture_output=True, text=True)
+    out = subprocess.run([os.path.join(cpp_build, "demo_bar"), str(obj), str(con), "10"] + (["minimal"] if mesh_access == "minimal" else []), capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     pos = np.array([list(map(float, l.split()[1:])) for l in out.stdout.splitlines() if l.startswith("V ")])
     energy = float([l for l in out.stdout.splitlines() if l.startswith("ENERGY")][0].split()[1])

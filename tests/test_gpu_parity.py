@@ -299,6 +299,52 @@ def test_batch_of_sphere_deformations_matches_oracle(meshes):
         assert np.abs(pos[k] - mesh).max() <= POS_TOL * diag, k
 
 
+def test_rigid_constraint_front_end_matches_per_vertex_constraints(meshes):
+    """DeformationUtil::updateConstraints in one call (arap_set_rigid_constraints / arap_batch_set_rigid_constraints,
+    targets computed on the device) against setConstraint with the oracle's targets (deformation_util.h:48-57)."""
+    P, F = meshes["sphere"]
+    K = 5
+    handles = np.sort(np.unique(F[(F == G.SPHERE_HANDLE).any(1)]))
+    otraj = sphere_trajectory()
+    ptraj = capi.TrajectorySE3()
+    for pose in otraj._poses:                              # same key poses into the product's trajectory
+        ptraj.addKeyPose(pose)
+    origin = ptraj(0.0)
+    assert np.abs(origin - otraj(0.0)).max() < 1e-12
+    us = np.arange(K) / (K - 1)
+    poses = ptraj.sample(us)
+    util = capi.DeformationUtil(P, handles, origin)
+    anchor = np.array([G.SPHERE_ANCHOR], np.int32)
+    # single mesh
+    for k in (1, K - 1):
+        a = capi.AsRigidAsPossibleDeformation(P.copy(), F, np.float64)
+        a.setConstraints(anchor, P[anchor])
+        util.updateConstraints(poses[k], a)
+        assert a.deform(6)
+        mesh = P.copy()
+        o = O.ArapOracle(mesh, F, np.float64)
+        o.setConstraint(int(anchor[0]), P[anchor[0]])
+        constrain(o, handles, O.handle_targets(otraj(0.0), otraj(float(us[k])), P[handles]))
+        assert o.deform(6)
+        assert np.abs(a.mesh - mesh).max() <= POS_TOL * bbox_diag(P)
+    # batch: one pose per member
+    b = capi.BatchDeformation(P, F, K, np.float64)
+    b.setConstraints(anchor, np.repeat(P[anchor][None], K, 0))
+    util.updateConstraints(poses, b)
+    assert b.prepare() == capi.ARAP_OK
+    b.iterate(6)
+    pos = b.positions()
+    for k in range(K):
+        mesh = P.copy()
+        o = O.ArapOracle(mesh, F, np.float64)
+        o.setConstraint(int(anchor[0]), P[anchor[0]])
+        constrain(o, handles, O.handle_targets(otraj(0.0), otraj(float(us[k])), P[handles]))
+        assert o.deform(6)
+        assert np.abs(pos[k] - mesh).max() <= POS_TOL * bbox_diag(P), k
+    with pytest.raises(capi.ArapError):
+        b.setRigidConstraints(np.array([P.shape[0]], np.int32), P[:1], poses)
+
+
 @pytest.mark.parametrize("solver", ["mg", "jacobi"])
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_partitioned_mesh_in_process_matches_oracle(world, solver):
