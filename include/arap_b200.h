@@ -209,6 +209,24 @@ int arap_comm_unique_id(void *out_bytes, int32_t capacity /* >= 128 */);
 int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32_t rank, int32_t world_size, int32_t transport,
                           const void *id, int32_t id_bytes);
 
+/* Optional, after arap_attach_partition and before arap_prepare: the GLOBAL mesh, so that every rank can build the same
+ * multigrid hierarchy for the whole mesh (aggregates never straddle two ranks) and keep its share of every level. The
+ * V-cycle then exchanges halos level by level and converges like the single-GPU solver; without this call each rank
+ * preconditions only its own block (block-Jacobi across ranks), which costs many more CG iterations. Every rank must
+ * pass the same mesh, owner array and constrained set; call it again when the rest pose or the constrained set changes.
+ * Host cost per rank: a single-GPU multigrid setup of the WHOLE mesh. All arrays are copied. */
+typedef struct arap_global_mesh {
+    int32_t n_vertices, n_faces;
+    const int32_t *faces;             /* n_faces x 3 global vertex ids */
+    const void *rest_xyz;             /* n_vertices x 3 */
+    int32_t rest_scalar_bytes;        /* 4 | 8 */
+    const int32_t *owner;             /* n_vertices: owning rank of every vertex */
+    const int32_t *local_to_global;   /* this rank's local vertex -> global id (one per local vertex, halo included) */
+    int32_t n_constrained;
+    const int32_t *constrained;       /* global ids of ALL constrained vertices, whoever owns them */
+} arap_global_mesh;
+int arap_partition_set_global_mesh(arap_handle *h, const arap_global_mesh *g);
+
 /* Page-locked host memory for mesh buffers handed to arap_deform / arap_prepare / arap_get_positions
  * (optional: pageable memory works too, pinned memory makes the copies run at full PCIe rate). */
 int arap_host_alloc(size_t bytes, void **out);

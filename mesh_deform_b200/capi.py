@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle", "arap_comm_unique_id", "arap_attach_partition",
     "arap_trajectory_create", "arap_trajectory_destroy", "arap_trajectory_add_key_pose", "arap_trajectory_evaluate",
     "arap_rigid_conjugate", "arap_set_rigid_constraints", "arap_batch_set_rigid_constraints",
+    "arap_partition_set_global_mesh",
 )
 
 
@@ -48,6 +49,12 @@ class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
                 ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
                 ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double)]
+
+
+class GlobalMesh(C.Structure):
+    _fields_ = [("n_vertices", C.c_int32), ("n_faces", C.c_int32), ("faces", C.c_void_p), ("rest_xyz", C.c_void_p),
+                ("rest_scalar_bytes", C.c_int32), ("owner", C.c_void_p), ("local_to_global", C.c_void_p),
+                ("n_constrained", C.c_int32), ("constrained", C.c_void_p)]
 
 
 class PartitionPlan(C.Structure):
@@ -124,6 +131,7 @@ def lib():
     L.arap_batch_set_rigid_constraints.argtypes = [vp, i32, vp, vp, i32, vp]
     L.arap_comm_unique_id.argtypes = [vp, i32]
     L.arap_attach_partition.argtypes = [vp, C.POINTER(PartitionPlan), i32, i32, i32, vp, i32]
+    L.arap_partition_set_global_mesh.argtypes = [vp, C.POINTER(GlobalMesh)]
     L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.arap_host_free.argtypes = [vp]
     L.arap_last_error.argtypes = [vp]
@@ -478,10 +486,15 @@ class PartitionedDeformation:
     comm_id = an int group key) -- the latter is how the single-GPU test tier runs the very same solver code path.
     """
 
-    def __init__(self, positions, faces, owner, rank, world, transport, comm_id, precision=np.float64, **options):
+    def __init__(self, positions, faces, owner, rank, world, transport, comm_id, precision=np.float64, global_multigrid=True,
+                 **options):
         from . import partition as part_mod
         self.part = part_mod.build_local_part(faces, owner, rank, world)
-        self.global_rest = np.asarray(positions, dtype=np.float64)
+        self.global_rest = np.ascontiguousarray(positions, dtype=np.float64)
+        self.global_faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+        self.owner = np.ascontiguousarray(owner, dtype=np.int32)
+        self.global_multigrid = bool(global_multigrid)
+        self._constrained = np.zeros(0, np.int32)
         self.local_mesh = np.ascontiguousarray(self.global_rest[self.part.local_to_global], dtype=np.dtype(precision))
         self.arap = AsRigidAsPossibleDeformation(self.local_mesh, self.part.faces, precision, **options)
         pl = self.part
@@ -494,12 +507,21 @@ class PartitionedDeformation:
         self.arap._check(lib().arap_attach_partition(self.arap._h, C.byref(plan), rank, world, transport, _ptr(ident), ident.nbytes))
 
     def setConstraints(self, global_indices, targets):
+        """Every rank passes the SAME global constraint set; each keeps the part it holds (owned and halo)."""
         from . import partition as part_mod
+        self._constrained = np.union1d(self._constrained, np.asarray(global_indices, dtype=np.int32)).astype(np.int32)
         idx, tgt = part_mod.local_constraints(self.part, global_indices, targets)
         if idx.size:
             self.arap.setConstraints(idx, tgt)
 
     def prepare(self):
+        if self.global_multigrid:
+            # the global mesh lets every rank build the same whole-mesh multigrid hierarchy (arap_partition_set_global_mesh)
+            l2g = np.ascontiguousarray(self.part.local_to_global, dtype=np.int32)
+            con = np.ascontiguousarray(self._constrained, dtype=np.int32)
+            g = GlobalMesh(self.global_rest.shape[0], self.global_faces.shape[0], self.global_faces.ctypes.data,
+                           self.global_rest.ctypes.data, 8, self.owner.ctypes.data, l2g.ctypes.data, con.size, con.ctypes.data)
+            self.arap._check(lib().arap_partition_set_global_mesh(self.arap._h, C.byref(g)))
         return self.arap.prepare()
 
     def iterate(self, n):

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_setup.h"
+#include "mg_partition.h"
 #include "partition.cuh"
 #include "../../inc/deform/detail/se3_spline.h"
 
@@ -48,7 +49,7 @@ struct Status {
         }                                                                                            \
     } while (0)
 
-static inline int grid_for(size_t n) { return (int)((n + kBlock - 1) / kBlock); }
+static inline int grid_for(size_t n) { return n ? (int)((n + kBlock - 1) / kBlock) : 1; }   // kernels bound-check; never a 0-CTA launch
 // Kernels that end in a grid-wide reduction run as persistent grid-stride kernels: exactly as many CTAs
 // as fit on the GPU at once (occupancy API, per kernel), so the number of per-block partials -- and the tail
 // in which the last CTA sums them -- stays small. Measured (profiles/r01_d_variants.txt): 10 % per CG iteration.
@@ -91,6 +92,7 @@ public:
     virtual int get_rotations(void *rot9) = 0;
     virtual int energy(double *e) = 0;
     virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
+    virtual int set_global_mesh(const arap_global_mesh *g) = 0;
 
     int fail(int code, const std::string &msg) {
         last_error = msg;
@@ -177,6 +179,10 @@ struct MgLevelDev {
     DeviceBuffer<float> a_val, p_val, r_val, inv_diag;     // the V-cycle runs in fp32 (mg_kernels.cuh)
     DeviceBuffer<MgVec> b, x, x2, r;          // x: iterate before post-smoothing, x2: the level's result
     int a_lanes = 1, r_lanes = 1;             // threads per row for A and R kernels
+    // partitioned mode with a global hierarchy: n = rows this rank owns, n_ext = owned + halo (vector length)
+    int n_ext = 0;
+    HaloPlan plan;
+    DeviceBuffer<int> send_index;
 };
 
 template <typename T>
@@ -264,6 +270,18 @@ public:
     DeviceBuffer<int> send_index_dev;
     DeviceBuffer<unsigned char> halo_sendbuf;
     std::unique_ptr<Transport> transport;
+    int my_rank = 0, world_size = 1;
+    // the GLOBAL mesh (arap_partition_set_global_mesh): lets every rank build the same global multigrid hierarchy
+    struct GlobalMesh {
+        int n_vertices = 0, n_faces = 0;
+        std::vector<int> faces, owner, local_to_global;
+        std::vector<double> rest;
+        std::vector<unsigned char> constrained;
+    } global_mesh;
+    bool have_global = false;
+    bool mg_global = false;                        // the current hierarchy is this rank's share of the global one
+    std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
+    DeviceBuffer<unsigned char> mg_sendbuf;
     cudaGraph_t cg_graph = nullptr;                // one CG iteration (preconditioner included), replayed per iteration
     cudaGraphExec_t cg_graph_exec = nullptr;
     bool have_warm_rotations = false;              // quat[] holds the previous iteration's R_i
@@ -510,15 +528,24 @@ public:
             std::vector<unsigned char> mask((size_t)V);      // user order is fine here: it is only compared with the previous one
             if (V > 0) ARAP_CUDA(cudaMemcpyAsync(mask.data(), is_constrained.ptr, (size_t)V, cudaMemcpyDeviceToHost, stream));
             ARAP_CUDA(cudaStreamSynchronize(stream));
-            const bool reusable = !mg.empty() && !mg_stale && mask == mg_mask && nnz == mg_nnz && getenv("ARAP_MG_ALWAYS_REBUILD") == nullptr;
+            // Partitioned mode with a global hierarchy: every rank must take the same decision, so only facts all ranks
+            // share may enter it (the global constrained set, and mg_stale, which derives from all-reduced CG counts).
+            const bool want_global = transport && have_global && getenv("ARAP_MG_BLOCK_JACOBI") == nullptr;
+            const bool same_problem = want_global ? (mg_global && global_mesh.constrained == mg_global_mask) : (!mg_global && mask == mg_mask && nnz == mg_nnz);
+            const bool reusable = !mg.empty() && !mg_stale && same_problem && getenv("ARAP_MG_ALWAYS_REBUILD") == nullptr;
             if (reusable) {
                 stats.mg_levels = (int)mg.size();
                 stats.mg_operator_complexity = mg_complexity;
                 stats.setup_host_ms = 0.0;
                 mg_fresh = false;
             } else {
-                int rc = setup_multigrid();
-                if (rc) return rc;
+                mg_global = false;
+                if (want_global) {
+                    int rc = setup_multigrid_global();
+                    if (rc) return rc;
+                    mg_global_mask = global_mesh.constrained;
+                }
+                if (!mg_global) { int rc = setup_multigrid(); if (rc) return rc; }
                 mg_mask.swap(mask);
                 mg_nnz = nnz;
                 mg_complexity = stats.mg_operator_complexity;
@@ -640,6 +667,8 @@ public:
     int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) override {
         if (!p || p->n_owned < 0 || p->n_owned > n_vertices || p->n_neighbors < 0 || world <= 0 || rank < 0 || rank >= world)
             return fail(ARAP_ERR_INVALID, "attach_partition: bad arguments");
+        my_rank = rank;
+        world_size = world;
         plan = HaloPlan();
         plan.n_owned = p->n_owned;
         plan.neighbor_rank.assign(p->neighbor_rank, p->neighbor_rank + p->n_neighbors);
@@ -681,6 +710,46 @@ public:
             end_launch();
         }
         if (transport->exchange(stream, plan, (const char *)halo_sendbuf.ptr, (char *)array, elem_bytes)) return fail(ARAP_ERR_CUDA, transport->error);
+        return ARAP_OK;
+    }
+
+    int set_global_mesh(const arap_global_mesh *g) override {
+        if (!transport) return fail(ARAP_ERR_INVALID, "set_global_mesh: call arap_attach_partition first");
+        if (!g || g->n_vertices <= 0 || g->n_faces < 0 || !g->faces || !g->rest_xyz || !g->owner || !g->local_to_global ||
+            (g->rest_scalar_bytes != 4 && g->rest_scalar_bytes != 8) || g->n_constrained < 0 || (g->n_constrained > 0 && !g->constrained))
+            return fail(ARAP_ERR_INVALID, "set_global_mesh: bad arguments");
+        GlobalMesh &m = global_mesh;
+        m.n_vertices = g->n_vertices;
+        m.n_faces = g->n_faces;
+        m.faces.assign(g->faces, g->faces + 3 * (size_t)g->n_faces);
+        for (int v : m.faces) if (v < 0 || v >= m.n_vertices) return fail(ARAP_ERR_INVALID, "set_global_mesh: face references a vertex out of range");
+        m.owner.assign(g->owner, g->owner + g->n_vertices);
+        for (int o : m.owner) if (o < 0 || o >= world_size) return fail(ARAP_ERR_INVALID, "set_global_mesh: owner rank out of range");
+        m.local_to_global.assign(g->local_to_global, g->local_to_global + n_vertices);
+        for (int v : m.local_to_global) if (v < 0 || v >= m.n_vertices) return fail(ARAP_ERR_INVALID, "set_global_mesh: local_to_global out of range");
+        m.rest.resize(3 * (size_t)m.n_vertices);
+        for (size_t k = 0; k < m.rest.size(); ++k)
+            m.rest[k] = g->rest_scalar_bytes == 4 ? (double)((const float *)g->rest_xyz)[k] : ((const double *)g->rest_xyz)[k];
+        m.constrained.assign((size_t)m.n_vertices, 0);
+        for (int k = 0; k < g->n_constrained; ++k) {
+            if (g->constrained[k] < 0 || g->constrained[k] >= m.n_vertices) return fail(ARAP_ERR_INVALID, "set_global_mesh: constrained index out of range");
+            m.constrained[(size_t)g->constrained[k]] = 1;
+        }
+        have_global = true;
+        dirty = true;
+        return ARAP_OK;
+    }
+
+    // refresh the halo slots of one multigrid level's vector (global hierarchy, partitioned mode)
+    int exchange_level(MgLevelDev &lv, MgVec *array) {
+        const int n = lv.plan.n_send();
+        if (n > 0) {
+            begin_launch(ARAP_K_HALO_PACK);
+            halo_pack_kernel<<<(n * 2 + 255) / 256, 256, 0, stream>>>(n, 2, lv.send_index.ptr, (const unsigned long long *)array,
+                                                                      (unsigned long long *)mg_sendbuf.ptr);
+            end_launch();
+        }
+        if (transport->exchange(stream, lv.plan, (const char *)mg_sendbuf.ptr, (char *)array, sizeof(MgVec))) return fail(ARAP_ERR_CUDA, transport->error);
         return ARAP_OK;
     }
 
@@ -760,10 +829,140 @@ public:
         return ARAP_OK;
     }
 
+    // ---- partitioned mode: this rank's share of the GLOBAL hierarchy (mg_partition.h) -----------------------------
+    // Returns ARAP_OK with mg_global == false when the global hierarchy is unusable for a reason every rank sees alike
+    // (single level / no dense coarsest level); the caller then falls back to the per-rank hierarchy.
+    int setup_multigrid_global() {
+        auto t0 = std::chrono::steady_clock::now();
+        mg_global = false;
+        const GlobalMesh &gm = global_mesh;
+        MgHierarchyHost H;
+        {
+            std::vector<int> g_rowptr, g_colidx, visit;
+            std::vector<double> g_w;
+            build_global_csr(gm.n_vertices, gm.n_faces, gm.faces.data(), gm.rest.data(), g_rowptr, g_colidx, g_w);
+            morton_sequence(gm.n_vertices, gm.rest.data(), visit);
+            MgSetupOptions mo;
+            mg_build_hierarchy<double>(gm.n_vertices, g_rowptr.data(), g_colidx.data(), g_w.data(), gm.constrained.data(), mo, H,
+                                       visit.data(), gm.owner.data());
+        }
+        if (H.levels.size() < 2 || H.coarse_inv.empty()) return ARAP_OK;
+        const int V = n_vertices;
+        std::vector<int> h_perm((size_t)V), global_of_local((size_t)V);
+        if (V > 0) ARAP_CUDA(cudaMemcpyAsync(h_perm.data(), perm.ptr, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < V; ++i) global_of_local[(size_t)i] = gm.local_to_global[(size_t)h_perm[(size_t)i]];
+        MgLocalHierarchy LH;
+        std::string err;
+        if (!mg_slice_hierarchy(H, my_rank, n_rows, V, global_of_local.data(), LH, err)) return fail(ARAP_ERR_SOLVER, err);
+        { MgHierarchyHost().levels.swap(H.levels); }          // the global matrices are no longer needed
+        mg.clear();
+        std::vector<float> fscratch;
+        size_t max_send = 1;
+        const size_t L = LH.levels.size();
+        for (size_t l = 0; l < L; ++l) {
+            const MgLocalLevel &hl = LH.levels[l];
+            std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+            d->n = (l == 0) ? V : hl.n_own;                  // level 0 vectors are indexed like every other per-vertex array
+            d->n_ext = (l == 0) ? V : hl.n_own + hl.n_halo;
+            d->omega = hl.omega;
+            const size_t len = (size_t)(d->n_ext > 0 ? d->n_ext : 1);
+            if (l > 0 && l + 1 < L) {
+                ARAP_CUDA(upload_vector(d->a_rowptr, hl.A.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->a_colidx, hl.A.colidx, stream));
+                ARAP_CUDA(upload_as_float(d->a_val, hl.A.val, stream, fscratch));
+                d->plan = hl.plan;
+                ARAP_CUDA(upload_vector(d->send_index, hl.plan.send_index, stream));
+                max_send = std::max(max_send, (size_t)hl.plan.n_send());
+                d->a_lanes = pick_lanes(hl.A.colidx.size(), (size_t)hl.A.n_rows);
+            }
+            if (l > 0) {
+                ARAP_CUDA(d->b.ensure(len));
+                ARAP_CUDA(cudaMemsetAsync(d->b.ptr, 0, sizeof(MgVec) * len, stream));
+                ARAP_CUDA(upload_as_float(d->inv_diag, hl.inv_diag, stream, fscratch));
+            }
+            if (l + 1 < L) {
+                ARAP_CUDA(upload_vector(d->p_rowptr, hl.P.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->p_colidx, hl.P.colidx, stream));
+                ARAP_CUDA(upload_as_float(d->p_val, hl.P.val, stream, fscratch));
+                ARAP_CUDA(upload_vector(d->r_rowptr, hl.R.rowptr, stream));
+                ARAP_CUDA(upload_vector(d->r_colidx, hl.R.colidx, stream));
+                ARAP_CUDA(upload_as_float(d->r_val, hl.R.val, stream, fscratch));
+                ARAP_CUDA(d->r.ensure(len));
+                ARAP_CUDA(cudaMemsetAsync(d->r.ptr, 0, sizeof(MgVec) * len, stream));
+                d->r_lanes = pick_lanes(hl.R.colidx.size(), (size_t)hl.R.n_rows);
+            }
+            ARAP_CUDA(d->x.ensure(len));
+            ARAP_CUDA(d->x2.ensure(len));
+            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * len, stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * len, stream));
+            mg.push_back(std::move(d));
+        }
+        ARAP_CUDA(mg_sendbuf.ensure(max_send * sizeof(MgVec)));
+        mg_dense = true;
+        ARAP_CUDA(upload_as_float(mg_coarse_inv, LH.coarse_inv, stream, fscratch));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        stats.mg_levels = (int)mg.size();
+        stats.mg_operator_complexity = LH.operator_complexity;
+        stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        mg_global = true;
+        return ARAP_OK;
+    }
+
+    // The V(1,1) cycle of vcycle() on a hierarchy whose rows are spread over the ranks: same kernels on the owned rows,
+    // with the halo of every gathered vector refreshed right before the kernel that gathers it.
+    int vcycle_partitioned() {
+        const int R = n_rows;
+        const int L = (int)mg.size();
+        MgLevelDev &m0 = *mg[0];
+        MgVec *z = m0.x2.ptr;
+        // down
+        { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec)); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
+        LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
+               free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
+        { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec)); if (rc) return rc; }
+        for (int l = 0; l + 1 < L; ++l) {
+            MgLevelDev &f = *mg[l], &c = *mg[l + 1];
+            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+                                                  f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
+                                                  c.x.ptr, cg.ptr));
+            if (l + 1 == L - 1) break;
+            { int rc = exchange_level(c, c.x.ptr); if (rc) return rc; }
+            ARAP_DISPATCH_LANES(c.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+                                                  c.a_rowptr.ptr, c.a_colidx.ptr, c.a_val.ptr, c.b.ptr, c.x.ptr, c.r.ptr, cg.ptr));
+            { int rc = exchange_level(c, c.r.ptr); if (rc) return rc; }
+        }
+        // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
+        MgLevelDev &cl = *mg[L - 1];
+        if (transport->allreduce_sum_f32(stream, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
+        LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
+               cl.b.ptr, cl.x2.ptr, cg.ptr);
+        // up
+        for (int l = L - 2; l >= 0; --l) {
+            MgLevelDev &f = *mg[l], &c = *mg[l + 1];
+            const int rows = (l == 0) ? R : f.n;
+            if (l + 1 < L - 1) { int rc = exchange_level(c, c.x2.ptr); if (rc) return rc; }
+            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+                   c.x2.ptr, f.x.ptr, cg.ptr);
+            if (l == 0) {
+                { int rc = exchange_halo(f.x.ptr, sizeof(MgVec)); if (rc) return rc; }
+                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
+                       hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+            } else {
+                { int rc = exchange_level(f, f.x.ptr); if (rc) return rc; }
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
+                                                      f.x.ptr, f.x2.ptr, cg.ptr));
+            }
+        }
+        return reduce_stage(CG_STAGE_RHO, 3);
+    }
+
     // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
     // Buffer roles are fixed (no pointer swapping) so that the launch sequence can be captured in a CUDA graph:
     // on every level x = iterate before post-smoothing, x2 = the level's result; level 0's result is z = mg[0]->x2.
     int vcycle() {
+        if (mg_global) return vcycle_partitioned();
         const int R = n_rows;                 // owned rows (== n_vertices on a single GPU)
         const int L = (int)mg.size();
         MgLevelDev &m0 = *mg[0];
@@ -1341,6 +1540,11 @@ int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32
                           const void *id, int32_t id_bytes) {
     ARAP_ENGINE_OR_FAIL(h);
     return h->engine->attach_partition(plan, rank, world_size, transport, id, id_bytes);
+}
+
+int arap_partition_set_global_mesh(arap_handle *h, const arap_global_mesh *g) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->set_global_mesh(g);
 }
 
 int arap_host_alloc(size_t bytes, void **out) {

@@ -119,7 +119,8 @@ double estimate_rho(const HostCsr &A, const std::vector<double> &inv_diag) {
 
 // Greedy aggregation on the strength graph. agg[i] = aggregate id, or -1 if the row takes no part
 // in the coarse level (empty row, or no strong neighbour: Jacobi alone solves such rows).
-int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double theta, std::vector<int> &agg, const int *order) {
+int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double theta, std::vector<int> &agg, const int *order,
+              const int *block) {
     const int n = A.n_rows;
     std::vector<unsigned char> strong((size_t)A.nnz(), 0);
     std::vector<unsigned char> has_strong((size_t)n, 0);
@@ -128,6 +129,7 @@ int aggregate(const HostCsr &A, const std::vector<double> &inv_diag, double thet
         for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
             const int j = A.colidx[k];
             if (j == i || !(inv_diag[j] > 0)) continue;
+            if (block && block[i] != block[j]) continue;       // aggregates stay inside one partition block
             // |a_ij| >= theta sqrt(a_ii a_jj)  <=>  a_ij^2 * inv_ii * inv_jj >= theta^2
             if (A.val[k] * A.val[k] * inv_diag[i] * inv_diag[j] >= theta * theta) { strong[k] = 1; has_strong[i] = 1; }
         }
@@ -329,8 +331,10 @@ struct PhaseTimer {
 
 template <typename S>
 void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *weight, const unsigned char *con,
-                        const MgSetupOptions &opt, MgHierarchyHost &out, const int *visit_order) {
+                        const MgSetupOptions &opt, MgHierarchyHost &out, const int *visit_order, const int *block) {
     PhaseTimer timer;
+    std::vector<int> cur_block;
+    if (block) cur_block.assign(block, block + V);
     out.levels.clear();
     out.coarse_inv.clear();
     HostCsr A;
@@ -341,6 +345,7 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
     while (true) {
         MgLevelHost lvl;
         lvl.A = std::move(A);
+        lvl.block = cur_block;
         extract_inv_diag(lvl.A, lvl.inv_diag);
         total_nnz += lvl.A.nnz();
         int active = 0;
@@ -351,7 +356,8 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
             lvl.omega = 4.0 / (3.0 * estimate_rho(lvl.A, lvl.inv_diag));
             timer.lap("rho", lv);
             std::vector<int> agg;
-            const int n_agg = aggregate(lvl.A, lvl.inv_diag, opt.theta, agg, out.levels.empty() ? visit_order : nullptr);
+            const int n_agg = aggregate(lvl.A, lvl.inv_diag, opt.theta, agg, out.levels.empty() ? visit_order : nullptr,
+                                        block ? lvl.block.data() : nullptr);
             timer.lap("aggregate", lv);
             if (n_agg > 0 && n_agg < 0.8 * active) {
                 smoothed_prolongator(lvl.A, lvl.inv_diag, agg, n_agg, lvl.omega, lvl.P);
@@ -363,6 +369,10 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
                 timer.lap("A*P", lv);
                 spgemm(lvl.R, AP, A);
                 timer.lap("R*(AP)", lv);
+                if (block) {
+                    cur_block.assign((size_t)n_agg, 0);
+                    for (int i = 0; i < lvl.A.n_rows; ++i) if (agg[(size_t)i] >= 0) cur_block[(size_t)agg[(size_t)i]] = lvl.block[(size_t)i];
+                }
                 out.levels.push_back(std::move(lvl));
                 continue;
             }
@@ -381,8 +391,8 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
 }
 
 template void mg_build_hierarchy<float>(int, const int *, const int *, const float *, const unsigned char *,
-                                        const MgSetupOptions &, MgHierarchyHost &, const int *);
+                                        const MgSetupOptions &, MgHierarchyHost &, const int *, const int *);
 template void mg_build_hierarchy<double>(int, const int *, const int *, const double *, const unsigned char *,
-                                         const MgSetupOptions &, MgHierarchyHost &, const int *);
+                                         const MgSetupOptions &, MgHierarchyHost &, const int *, const int *);
 
 }  // namespace arap

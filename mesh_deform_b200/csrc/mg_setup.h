@@ -29,6 +29,7 @@ struct MgLevelHost {
     double omega = 2.0 / 3.0;        // damped-Jacobi weight
     HostCsr P;                       // n_l x n_{l+1}
     HostCsr R;                       // P^T
+    std::vector<int> block;          // per row: the partition block (owner rank) it belongs to; empty without blocks
 };
 
 struct MgHierarchyHost {
@@ -49,9 +50,12 @@ struct MgSetupOptions {
 // visit_order (optional, n_vertices entries): the order in which the greedy aggregation of the FINE level walks the
 // vertices. A spatially coherent order (Morton) gives compact, regular aggregates -- fewer CG iterations -- whatever
 // the memory order of the vertices is; coarse levels inherit it through the aggregate numbering.
+// block (optional, n_vertices entries): a partition of the vertices (owner rank per vertex, partitioned mode). Aggregates
+// never contain vertices of two blocks, on any level, so every coarse row has a well-defined owner (levels[l].block)
+// and the restriction of an owned coarse row only reads fine rows within one ring of the owner's rows.
 template <typename S>
 void mg_build_hierarchy(int n_vertices, const int *rowptr, const int *colidx, const S *weight,
                         const unsigned char *is_constrained, const MgSetupOptions &opt, MgHierarchyHost &out,
-                        const int *visit_order = nullptr);
+                        const int *visit_order = nullptr, const int *block = nullptr);
 
 }  // namespace arap

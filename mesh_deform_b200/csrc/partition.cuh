@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include "halo_plan.h"
+
 #include <condition_variable>
 #include <cstdint>
 #include <map>
@@ -24,16 +26,6 @@
 #include <vector>
 
 namespace arap {
-
-struct HaloPlan {
-    int n_owned = 0;
-    std::vector<int> neighbor_rank;   // ranks this rank exchanges with
-    std::vector<int> send_offset;     // [n_neighbors + 1] into send_index
-    std::vector<int> send_index;      // owned local indices, grouped by neighbour, in the neighbour's halo order
-    std::vector<int> recv_offset;     // [n_neighbors + 1]: halo from neighbour k sits at local n_owned + recv_offset[k] ...
-    int n_send() const { return send_offset.empty() ? 0 : send_offset.back(); }
-    int n_halo() const { return recv_offset.empty() ? 0 : recv_offset.back(); }
-};
 
 // sendbuf[k] = array[send_index[k]] in 8-byte words (element sizes are 16, 24 or 32 bytes)
 __global__ void __launch_bounds__(256) halo_pack_kernel(int n_send, int words_per_elem, const int *__restrict__ send_index,
@@ -50,6 +42,7 @@ public:
     // sendbuf: packed device buffer (plan.send_offset layout, elem_bytes per entry); array: device base of the local array
     virtual int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) = 0;
     virtual int allreduce_sum(cudaStream_t stream, double *dev, int n) = 0;
+    virtual int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) = 0;
     std::string error;
 };
 
@@ -136,6 +129,9 @@ public:
     int allreduce_sum(cudaStream_t stream, double *dev, int n) override {
         return check(api->AllReduce(dev, dev, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
     }
+    int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) override {
+        return check(api->AllReduce(dev, dev, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
+    }
 };
 
 // ---- in-process transport: P partitions on one GPU, one host thread each ------------------------------------------------
@@ -203,20 +199,26 @@ public:
         group->barrier();      // nobody repacks its send buffer before every reader is done
         return 0;
     }
-    int allreduce_sum(cudaStream_t stream, double *dev, int n) override {
+    template <typename T>
+    int allreduce_host(cudaStream_t stream, T *dev, int n) {
         std::vector<double> mine((size_t)n);
-        if (cudaMemcpyAsync(mine.data(), dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        std::vector<T> raw((size_t)n);
+        if (cudaMemcpyAsync(raw.data(), dev, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
             cudaStreamSynchronize(stream) != cudaSuccess) { error = "in-process allreduce: D2H failed"; return -1; }
+        for (int c = 0; c < n; ++c) mine[(size_t)c] = (double)raw[(size_t)c];
         group->values[(size_t)rank] = mine;
         group->barrier();
         std::vector<double> sum((size_t)n, 0.0);
         for (int r = 0; r < group->world; ++r)                 // fixed rank order: every partition gets identical bits
             for (int c = 0; c < n; ++c) sum[(size_t)c] += group->values[(size_t)r][(size_t)c];
-        if (cudaMemcpyAsync(dev, sum.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        for (int c = 0; c < n; ++c) raw[(size_t)c] = (T)sum[(size_t)c];
+        if (cudaMemcpyAsync(dev, raw.data(), sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
             cudaStreamSynchronize(stream) != cudaSuccess) { error = "in-process allreduce: H2D failed"; return -1; }
         group->barrier();
         return 0;
     }
+    int allreduce_sum(cudaStream_t stream, double *dev, int n) override { return allreduce_host<double>(stream, dev, n); }
+    int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) override { return allreduce_host<float>(stream, dev, n); }
 };
 
 }  // namespace arap

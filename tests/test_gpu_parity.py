@@ -384,6 +384,46 @@ def test_partitioned_mesh_in_process_matches_oracle(world, solver):
     assert len(its) == 1                      # every rank took exactly the same control path
 
 
+def _run_partitioned(P, F, idx, tgt, world, key, iters, **kw):
+    from mesh_deform_b200 import partition as PT
+    owner = PT.strip_owner(P, world)
+    parts = [capi.PartitionedDeformation(P, F, owner, r, world, capi.TRANSPORT_IN_PROCESS, key, np.float64, **kw) for r in range(world)]
+
+    def work(p):
+        def run():
+            p.setConstraints(idx, tgt)
+            assert p.prepare() == capi.ARAP_OK
+            p.iterate(iters)
+        return run
+    capi.run_partitions_in_process([work(p) for p in parts])
+    pos = np.zeros_like(P)
+    for p in parts:
+        gid, xyz = p.owned_positions()
+        pos[gid] = xyz
+    return pos, parts[0].solver_stats()
+
+
+def test_partitioned_global_multigrid_keeps_the_iteration_count():
+    """The point of the global hierarchy (arap_partition_set_global_mesh): partitioning must not cost CG iterations.
+    Block-Jacobi across ranks (each rank preconditioning only its own block) is the baseline it replaces."""
+    nx, nz, iters = 192, 160, 3
+    P, F = G.grid_plane(nx, nz)
+    idx, tgt = G.grid_constraints(nx, nz, P)
+    single = capi.AsRigidAsPossibleDeformation(P.copy(), F, np.float64)
+    single.setConstraints(idx, tgt)
+    assert single.deform(iters)
+    its_single = single.solver_stats()["cg_iterations_total"]
+    pos_g, st_g = _run_partitioned(P, F, idx, tgt, 4, 2001, iters)
+    pos_b, st_b = _run_partitioned(P, F, idx, tgt, 4, 2002, iters, global_multigrid=False)
+    print("cg iterations: single", its_single, "partitioned global", st_g["cg_iterations_total"], "block-Jacobi", st_b["cg_iterations_total"],
+          "levels", st_g["mg_levels"])
+    diag = bbox_diag(P)
+    assert np.abs(pos_g - single.mesh).max() <= POS_TOL * diag
+    assert np.abs(pos_b - single.mesh).max() <= POS_TOL * diag
+    assert st_g["cg_iterations_total"] <= its_single + 2 * iters          # at most a couple more per global step
+    assert st_b["cg_iterations_total"] > st_g["cg_iterations_total"]
+
+
 def test_hierarchy_reuse_across_dirty_cycles_keeps_parity():
     """The reference's demos change a constraint every frame (full dirty rebuild, arap.h:84,102-120). The engine keeps the
     multigrid hierarchy while the constrained SET is unchanged; the result must still match the oracle frame by frame."""
