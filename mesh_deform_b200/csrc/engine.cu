@@ -564,8 +564,18 @@ public:
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
-        if (transport) destroy_cg_graph();                                // collectives are issued from the host between kernels
-        else { int rc = build_cg_graph(); if (rc) return rc; }
+        if (!transport) { int rc = build_cg_graph(); if (rc) return rc; }
+        else if (transport->capturable()) {
+            // NCCL calls are stream operations and can sit inside the graph, which removes ~70 host-side enqueues per CG
+            // iteration. Connections are opened on first use, which must not happen during capture: touch every exchange
+            // plan and both all-reduce flavours once, eagerly, with the (still zero) solver vectors.
+            int rc = warm_up_transport();
+            if (rc) return rc;
+            if (build_cg_graph() != ARAP_OK) {                            // every rank fails alike: plain enqueueing instead
+                destroy_cg_graph();
+                cudaGetLastError();
+            }
+        } else destroy_cg_graph();                                        // in-process transport synchronises on the host
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
@@ -750,6 +760,21 @@ public:
             end_launch();
         }
         if (transport->exchange(stream, lv.plan, (const char *)mg_sendbuf.ptr, (char *)array, sizeof(MgVec))) return fail(ARAP_ERR_CUDA, transport->error);
+        return ARAP_OK;
+    }
+
+    int warm_up_transport() {
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
+        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
+        double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
+        if (transport->allreduce_sum(stream, red, 5)) return fail(ARAP_ERR_CUDA, transport->error);
+        if (use_mg && mg_global) {
+            { int rc = exchange_halo(mg[0]->x.ptr, sizeof(MgVec)); if (rc) return rc; }
+            for (size_t l = 1; l + 1 < mg.size(); ++l) { int rc = exchange_level(*mg[l], mg[l]->x.ptr); if (rc) return rc; }
+            MgLevelDev &cl = *mg.back();
+            if (transport->allreduce_sum_f32(stream, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
         return ARAP_OK;
     }
 

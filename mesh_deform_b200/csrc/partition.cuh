@@ -43,6 +43,9 @@ public:
     virtual int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) = 0;
     virtual int allreduce_sum(cudaStream_t stream, double *dev, int n) = 0;
     virtual int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) = 0;
+    // true if every call only enqueues work on the stream (no host synchronisation), i.e. a CG iteration with its
+    // exchanges and reductions can be captured into a CUDA graph
+    virtual bool capturable() const { return false; }
     std::string error;
 };
 
@@ -110,6 +113,7 @@ public:
         return 0;
     }
     ~NcclTransport() override { if (api && comm) api->CommDestroy(comm); }
+    bool capturable() const override { return getenv("ARAP_NCCL_NO_GRAPH") == nullptr; }
     int check(int rc, const char *what) {
         if (rc == 0) return 0;
         error = std::string(what) + ": " + api->GetErrorString(rc);
