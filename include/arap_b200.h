@@ -196,7 +196,11 @@ int arap_batch_set_rigid_constraints(arap_batch *b, int32_t n, const int32_t *ve
  * the CG direction and all-reducing the CG's dot products through the chosen transport. The reference has no
  * counterpart (single-threaded CPU code); the partition itself is made by the caller (mesh_deform_b200/partition.py). */
 enum { ARAP_TRANSPORT_NCCL = 0,        /* one process per GPU; id = the 128 bytes from arap_comm_unique_id, broadcast by the caller */
-       ARAP_TRANSPORT_IN_PROCESS = 1   /* several partitions on one GPU, one host thread per partition; id = an int32 group key */ };
+       ARAP_TRANSPORT_IN_PROCESS = 1,  /* several partitions on one GPU, one host thread per partition; id = an int32 group key */
+       /* Halo exchange and reductions by direct stores into the peers' memory over NVLink / NVSwitch (one put kernel and
+        * one wait kernel per exchange, no library call in the iteration; see csrc/peer_transport.cuh). */
+       ARAP_TRANSPORT_PEER = 2,             /* one process per GPU of ONE node; bootstraps over NCCL (id as for NCCL) + CUDA IPC */
+       ARAP_TRANSPORT_PEER_IN_PROCESS = 3   /* several partitions on one GPU in one process (id = an int32 group key) */ };
 typedef struct arap_partition_plan {
     int32_t n_owned;                /* owned vertices come first in the local numbering */
     int32_t n_neighbors;

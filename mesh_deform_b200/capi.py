@@ -62,7 +62,7 @@ class PartitionPlan(C.Structure):
                 ("send_index", C.c_void_p), ("recv_offset", C.c_void_p)]
 
 
-TRANSPORT_NCCL, TRANSPORT_IN_PROCESS = 0, 1
+TRANSPORT_NCCL, TRANSPORT_IN_PROCESS, TRANSPORT_PEER, TRANSPORT_PEER_IN_PROCESS = 0, 1, 2, 3
 
 
 class Profile(C.Structure):
@@ -500,7 +500,7 @@ class PartitionedDeformation:
         pl = self.part
         self._keep = [np.ascontiguousarray(a, dtype=np.int32) for a in (pl.neighbor_rank, pl.send_offset, pl.send_index, pl.recv_offset)]
         plan = PartitionPlan(pl.n_owned, int(pl.neighbor_rank.size), *[a.ctypes.data for a in self._keep])
-        if transport == TRANSPORT_NCCL:
+        if transport in (TRANSPORT_NCCL, TRANSPORT_PEER):
             ident = np.ascontiguousarray(comm_id, dtype=np.uint8)
         else:
             ident = np.array([int(comm_id)], np.int32)

@@ -11,6 +11,7 @@
 #include "mg_setup.h"
 #include "mg_partition.h"
 #include "partition.cuh"
+#include "peer_transport.cuh"
 #include "../../inc/deform/detail/se3_spline.h"
 
 #include <cuda_runtime.h>
@@ -170,6 +171,14 @@ public:
         kernel<<<(grid), kBlock, 0, stream>>>(__VA_ARGS__);                          \
         end_launch();                                                                \
     } while (0)
+
+// Communication call sites of the partitioned solver (partition.cuh, SiteSpec): the same numbers on every rank.
+enum {
+    SITE_CUR4 = 0, SITE_QUAT, SITE_CG_D, SITE_MG0_X_PRE, SITE_MG0_R, SITE_MG0_X_POST, SITE_COARSE_B,
+    SITE_RED_BASE = 8,          // + CgStage
+    SITE_LEVEL_BASE = 16,       // + 4 * level + {0: x after pre-smoothing, 1: residual, 2: level result, 3: x after prolongation}
+    SITE_COUNT = 64
+};
 
 // One multigrid level on the device. Level 0 keeps no explicit A (matrix-free on the one-ring CSR).
 struct MgLevelDev {
@@ -564,18 +573,21 @@ public:
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        if (transport) { int rc = configure_transport(); if (rc) return rc; }
         if (!transport) { int rc = build_cg_graph(); if (rc) return rc; }
         else if (transport->capturable()) {
-            // NCCL calls are stream operations and can sit inside the graph, which removes ~70 host-side enqueues per CG
-            // iteration. Connections are opened on first use, which must not happen during capture: touch every exchange
-            // plan and both all-reduce flavours once, eagerly, with the (still zero) solver vectors.
-            int rc = warm_up_transport();
-            if (rc) return rc;
+            // NCCL calls and the peer transport's kernels are stream operations and can sit inside the graph, which removes
+            // ~70 host-side enqueues per CG iteration. NCCL opens connections on first use, which must not happen during
+            // capture: touch every exchange plan and both all-reduce flavours once, eagerly, with the (still zero) vectors.
+            if (transport->needs_warm_up()) { int rc = warm_up_transport(); if (rc) return rc; }
             if (build_cg_graph() != ARAP_OK) {                            // every rank fails alike: plain enqueueing instead
                 destroy_cg_graph();
                 cudaGetLastError();
             }
         } else destroy_cg_graph();                                        // in-process transport synchronises on the host
+        // Partitions that share one GPU and wait on each other inside kernels (in-process peer transport) must not start
+        // iterating while another one is still allocating: cudaFree waits for ALL device work, spinning kernels included.
+        if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
@@ -699,6 +711,23 @@ public:
             std::unique_ptr<LocalTransport> t(new LocalTransport());
             if (t->init(rank, world, *(const int32_t *)id)) return fail(ARAP_ERR_INVALID, t->error);
             transport = std::move(t);
+        } else if (kind == ARAP_TRANSPORT_PEER || kind == ARAP_TRANSPORT_PEER_IN_PROCESS) {
+            // direct stores into the peers' memory; the other transport of the pair only bootstraps (setup-time all-gathers)
+            std::unique_ptr<Transport> boot;
+            if (kind == ARAP_TRANSPORT_PEER) {
+                if (!id || id_bytes < 128) return fail(ARAP_ERR_INVALID, "attach_partition: the peer transport bootstraps over NCCL and needs the 128-byte unique id");
+                std::unique_ptr<NcclTransport> t(new NcclTransport());
+                if (t->init(rank, world, id)) return fail(ARAP_ERR_CUDA, t->error);
+                boot = std::move(t);
+            } else {
+                if (!id || id_bytes < 4) return fail(ARAP_ERR_INVALID, "attach_partition: in-process transport needs an int32 group key");
+                std::unique_ptr<LocalTransport> t(new LocalTransport());
+                if (t->init(rank, world, *(const int32_t *)id)) return fail(ARAP_ERR_INVALID, t->error);
+                boot = std::move(t);
+            }
+            std::unique_ptr<PeerTransport> t(new PeerTransport());
+            if (t->init(std::move(boot), kind == ARAP_TRANSPORT_PEER_IN_PROCESS, rank, world)) return fail(ARAP_ERR_CUDA, t->error);
+            transport = std::move(t);
         } else {
             return fail(ARAP_ERR_INVALID, "attach_partition: unknown transport");
         }
@@ -710,16 +739,12 @@ public:
     }
 
     // refresh the halo slots of a per-vertex array from their owners (no-op on a single GPU)
-    int exchange_halo(void *array, size_t elem_bytes) {
+    int exchange_halo(void *array, size_t elem_bytes, int site) {
         if (!transport) return ARAP_OK;
-        const int words = (int)(elem_bytes / 8), n = plan.n_send();
-        if (n > 0) {
-            begin_launch(ARAP_K_HALO_PACK);
-            halo_pack_kernel<<<(n * words + 255) / 256, 256, 0, stream>>>(n, words, send_index_dev.ptr, (const unsigned long long *)array,
-                                                                          (unsigned long long *)halo_sendbuf.ptr);
-            end_launch();
-        }
-        if (transport->exchange(stream, plan, (const char *)halo_sendbuf.ptr, (char *)array, elem_bytes)) return fail(ARAP_ERR_CUDA, transport->error);
+        begin_launch(ARAP_K_HALO_PACK);
+        const int rc = transport->exchange(stream, site, plan, send_index_dev.ptr, (char *)halo_sendbuf.ptr, (char *)array, elem_bytes);
+        end_launch();
+        if (rc) return fail(ARAP_ERR_CUDA, transport->error);
         return ARAP_OK;
     }
 
@@ -750,29 +775,51 @@ public:
         return ARAP_OK;
     }
 
-    // refresh the halo slots of one multigrid level's vector (global hierarchy, partitioned mode)
-    int exchange_level(MgLevelDev &lv, MgVec *array) {
-        const int n = lv.plan.n_send();
-        if (n > 0) {
-            begin_launch(ARAP_K_HALO_PACK);
-            halo_pack_kernel<<<(n * 2 + 255) / 256, 256, 0, stream>>>(n, 2, lv.send_index.ptr, (const unsigned long long *)array,
-                                                                      (unsigned long long *)mg_sendbuf.ptr);
-            end_launch();
+    // refresh the halo slots of one multigrid level's vector (global hierarchy, partitioned mode); which: see SITE_LEVEL_BASE
+    int exchange_level(int level, int which, MgVec *array) {
+        MgLevelDev &lv = *mg[(size_t)level];
+        begin_launch(ARAP_K_HALO_PACK);
+        const int rc = transport->exchange(stream, SITE_LEVEL_BASE + 4 * level + which, lv.plan, lv.send_index.ptr, (char *)mg_sendbuf.ptr,
+                                           (char *)array, sizeof(MgVec));
+        end_launch();
+        if (rc) return fail(ARAP_ERR_CUDA, transport->error);
+        return ARAP_OK;
+    }
+
+    // tell the transport about every call site (peer transport: mailboxes and flags per site); collective
+    int configure_transport() {
+        std::vector<SiteSpec> sites((size_t)SITE_COUNT);
+        auto ex = [&](int site, const HaloPlan *pl, int bytes) { sites[(size_t)site].kind = SiteSpec::EXCHANGE; sites[(size_t)site].plan = pl; sites[(size_t)site].elem_bytes = bytes; };
+        ex(SITE_CUR4, &plan, (int)sizeof(Vec4T<S>));
+        ex(SITE_QUAT, &plan, (int)sizeof(Vec4T<S>));
+        ex(SITE_CG_D, &plan, (int)sizeof(Vec3d));
+        for (int st = 0; st <= CG_STAGE_RHO; ++st) { sites[(size_t)(SITE_RED_BASE + st)].kind = SiteSpec::REDUCE_F64; sites[(size_t)(SITE_RED_BASE + st)].n = 8; }
+        if (use_mg && mg_global) {
+            ex(SITE_MG0_X_PRE, &plan, (int)sizeof(MgVec));
+            ex(SITE_MG0_R, &plan, (int)sizeof(MgVec));
+            ex(SITE_MG0_X_POST, &plan, (int)sizeof(MgVec));
+            for (size_t l = 1; l + 1 < mg.size(); ++l)
+                for (int w = 0; w < 4; ++w) {
+                    if (SITE_LEVEL_BASE + 4 * (int)l + w >= SITE_COUNT) return fail(ARAP_ERR_SOLVER, "too many multigrid levels for the transport's site table");
+                    ex(SITE_LEVEL_BASE + 4 * (int)l + w, &mg[l]->plan, (int)sizeof(MgVec));
+                }
+            sites[SITE_COARSE_B].kind = SiteSpec::REDUCE_F32;
+            sites[SITE_COARSE_B].n = 4 * mg.back()->n;
         }
-        if (transport->exchange(stream, lv.plan, (const char *)mg_sendbuf.ptr, (char *)array, sizeof(MgVec))) return fail(ARAP_ERR_CUDA, transport->error);
+        if (transport->configure(stream, sites)) return fail(ARAP_ERR_CUDA, transport->error);
         return ARAP_OK;
     }
 
     int warm_up_transport() {
-        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
-        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
+        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>), SITE_CUR4); if (rc) return rc; }
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
-        if (transport->allreduce_sum(stream, red, 5)) return fail(ARAP_ERR_CUDA, transport->error);
+        if (transport->allreduce_sum(stream, SITE_RED_BASE, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
         if (use_mg && mg_global) {
-            { int rc = exchange_halo(mg[0]->x.ptr, sizeof(MgVec)); if (rc) return rc; }
-            for (size_t l = 1; l + 1 < mg.size(); ++l) { int rc = exchange_level(*mg[l], mg[l]->x.ptr); if (rc) return rc; }
+            { int rc = exchange_halo(mg[0]->x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }
+            for (size_t l = 1; l + 1 < mg.size(); ++l) { int rc = exchange_level((int)l, 0, mg[l]->x.ptr); if (rc) return rc; }
             MgLevelDev &cl = *mg.back();
-            if (transport->allreduce_sum_f32(stream, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
+            if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
         }
         ARAP_CUDA(cudaStreamSynchronize(stream));
         return ARAP_OK;
@@ -782,7 +829,8 @@ public:
     int reduce_stage(int stage, int n_values) {
         if (!transport) return ARAP_OK;
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
-        if (transport->allreduce_sum(stream, red, n_values)) return fail(ARAP_ERR_CUDA, transport->error);
+        (void)n_values;             // always the whole red[8] block: one site layout for every stage
+        if (transport->allreduce_sum(stream, SITE_RED_BASE + stage, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
         begin_launch(ARAP_K_CG_FINALIZE);
         cg_finalize_kernel<<<1, 1, 0, stream>>>(cg.ptr, stage);
         end_launch();
@@ -942,39 +990,39 @@ public:
         MgLevelDev &m0 = *mg[0];
         MgVec *z = m0.x2.ptr;
         // down
-        { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec)); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
+        { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
         LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
                free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
-        { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec)); if (rc) return rc; }
+        { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec), SITE_MG0_R); if (rc) return rc; }
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
                                                   c.x.ptr, cg.ptr));
             if (l + 1 == L - 1) break;
-            { int rc = exchange_level(c, c.x.ptr); if (rc) return rc; }
+            { int rc = exchange_level(l + 1, 0, c.x.ptr); if (rc) return rc; }
             ARAP_DISPATCH_LANES(c.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   c.a_rowptr.ptr, c.a_colidx.ptr, c.a_val.ptr, c.b.ptr, c.x.ptr, c.r.ptr, cg.ptr));
-            { int rc = exchange_level(c, c.r.ptr); if (rc) return rc; }
+            { int rc = exchange_level(l + 1, 1, c.r.ptr); if (rc) return rc; }
         }
         // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
         MgLevelDev &cl = *mg[L - 1];
-        if (transport->allreduce_sum_f32(stream, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
+        if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
         LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
                cl.b.ptr, cl.x2.ptr, cg.ptr);
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             const int rows = (l == 0) ? R : f.n;
-            if (l + 1 < L - 1) { int rc = exchange_level(c, c.x2.ptr); if (rc) return rc; }
+            if (l + 1 < L - 1) { int rc = exchange_level(l + 1, 2, c.x2.ptr); if (rc) return rc; }
             LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                { int rc = exchange_halo(f.x.ptr, sizeof(MgVec)); if (rc) return rc; }
+                { int rc = exchange_halo(f.x.ptr, sizeof(MgVec), SITE_MG0_X_POST); if (rc) return rc; }
                 LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
                        hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                { int rc = exchange_level(f, f.x.ptr); if (rc) return rc; }
+                { int rc = exchange_level(l, 3, f.x.ptr); if (rc) return rc; }
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
@@ -1063,7 +1111,7 @@ public:
 
     int cg_iteration_jacobi() {
         const int R = n_rows;
-        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
         launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)R), R, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
@@ -1079,7 +1127,7 @@ public:
         MgLevelDev &m0 = *mg[0];
         { int rc = vcycle(); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const float *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
-        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d)); if (rc) return rc; }
+        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
         launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
         LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
@@ -1154,9 +1202,10 @@ public:
             slot ^= 1;
         }
         LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, R, free_mask.ptr, cg_x.ptr, cur4.ptr);
-        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
+        { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>), SITE_CUR4); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        if (transport && transport->poll_error()) return fail(ARAP_ERR_CUDA, transport->error);
         ARAP_CUDA(cudaGetLastError());
         stats.global_steps += 1;
         stats.cg_iterations_total += cg_host[0].iterations;
@@ -1181,7 +1230,7 @@ public:
                    redo_list.ptr, redo_count.ptr);
             LAUNCH(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
                    quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
-            { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>)); if (rc) return rc; }
+            { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>), SITE_QUAT); if (rc) return rc; }
             int rc = global_step();
             if (rc) return rc;
         }

@@ -36,17 +36,42 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(int n_send, int words_pe
     sendbuf[t] = array[(size_t)send_index[k] * words_per_elem + w];
 }
 
+// One communication call site of the solver (a halo exchange of one array, or a small all-reduce). Sites are numbered
+// the same on every rank; transports that keep per-site state (peer_transport.cuh) are told about them in configure().
+struct SiteSpec {
+    enum Kind { UNUSED = 0, EXCHANGE, REDUCE_F64, REDUCE_F32 } kind = UNUSED;
+    const HaloPlan *plan = nullptr;   // EXCHANGE
+    int elem_bytes = 0;               // EXCHANGE: 16, 24 or 32
+    int n = 0;                        // REDUCE_*: number of values
+};
+
 class Transport {
 public:
     virtual ~Transport() {}
-    // sendbuf: packed device buffer (plan.send_offset layout, elem_bytes per entry); array: device base of the local array
-    virtual int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) = 0;
-    virtual int allreduce_sum(cudaStream_t stream, double *dev, int n) = 0;
-    virtual int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) = 0;
+    // array[n_owned + recv slots] <- the owners' values. send_index_dev: plan.send_index on the device; scratch: room for
+    // plan.n_send() packed elements.
+    virtual int exchange(cudaStream_t stream, int site, const HaloPlan &plan, const int *send_index_dev, char *scratch, char *array,
+                         size_t elem_bytes) = 0;
+    virtual int allreduce_sum(cudaStream_t stream, int site, double *dev, int n) = 0;
+    virtual int allreduce_sum_f32(cudaStream_t stream, int site, float *dev, int n) = 0;
+    // out = the `bytes` of every rank, in rank order (host buffers; setup-time only)
+    virtual int allgather_host(cudaStream_t stream, const void *in, size_t bytes, void *out) = 0;
+    virtual int configure(cudaStream_t, const std::vector<SiteSpec> &) { return 0; }
     // true if every call only enqueues work on the stream (no host synchronisation), i.e. a CG iteration with its
     // exchanges and reductions can be captured into a CUDA graph
     virtual bool capturable() const { return false; }
+    virtual bool needs_warm_up() const { return false; }
+    virtual int poll_error() { return 0; }
+    // every rank has reached this point (host-level); only transports whose kernels wait on each other need one
+    virtual int barrier(cudaStream_t) { return 0; }
     std::string error;
+protected:
+    static void pack(cudaStream_t stream, const HaloPlan &plan, const int *send_index_dev, const char *array, char *scratch, size_t elem_bytes) {
+        const int n = plan.n_send(), words = (int)(elem_bytes / 8);
+        if (n > 0)
+            halo_pack_kernel<<<(n * words + 255) / 256, 256, 0, stream>>>(n, words, send_index_dev, (const unsigned long long *)array,
+                                                                          (unsigned long long *)scratch);
+    }
 };
 
 // ---- NCCL (dlopen'ed) --------------------------------------------------------------------------------------------------
@@ -61,6 +86,7 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, Comm, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     void *lib = nullptr;
 
@@ -90,6 +116,7 @@ struct NcclApi {
                 ARAP_NCCL_SYM(Send, "ncclSend")
                 ARAP_NCCL_SYM(Recv, "ncclRecv")
                 ARAP_NCCL_SYM(AllReduce, "ncclAllReduce")
+                ARAP_NCCL_SYM(AllGather, "ncclAllGather")
                 ARAP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef ARAP_NCCL_SYM
             }
@@ -108,33 +135,48 @@ public:
         if (!api) return -1;
         NcclApi::UniqueId id;
         memcpy(&id, unique_id, sizeof(id));
+        this->world = world;
         const int rc = api->CommInitRank(&comm, world, id, rank);
         if (rc != 0) { error = std::string("ncclCommInitRank: ") + api->GetErrorString(rc); return -1; }
         return 0;
     }
     ~NcclTransport() override { if (api && comm) api->CommDestroy(comm); }
-    bool capturable() const override { return getenv("ARAP_NCCL_NO_GRAPH") == nullptr; }
     int check(int rc, const char *what) {
         if (rc == 0) return 0;
         error = std::string(what) + ": " + api->GetErrorString(rc);
         return -1;
     }
-    int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) override {
+    int world = 1;
+    bool capturable() const override { return getenv("ARAP_NCCL_NO_GRAPH") == nullptr; }
+    bool needs_warm_up() const override { return true; }      // connections are opened on first use: not inside a capture
+    int exchange(cudaStream_t stream, int, const HaloPlan &plan, const int *send_index_dev, char *scratch, char *array, size_t elem_bytes) override {
         if (plan.neighbor_rank.empty()) return 0;
+        pack(stream, plan, send_index_dev, array, scratch, elem_bytes);
         if (check(api->GroupStart(), "ncclGroupStart")) return -1;
         for (size_t k = 0; k < plan.neighbor_rank.size(); ++k) {
             const size_t ns = (size_t)(plan.send_offset[k + 1] - plan.send_offset[k]) * elem_bytes;
             const size_t nr = (size_t)(plan.recv_offset[k + 1] - plan.recv_offset[k]) * elem_bytes;
-            if (ns && check(api->Send(sendbuf + (size_t)plan.send_offset[k] * elem_bytes, ns, /*ncclChar*/ 0, plan.neighbor_rank[k], comm, stream), "ncclSend")) return -1;
+            if (ns && check(api->Send(scratch + (size_t)plan.send_offset[k] * elem_bytes, ns, /*ncclChar*/ 0, plan.neighbor_rank[k], comm, stream), "ncclSend")) return -1;
             if (nr && check(api->Recv(array + ((size_t)plan.n_owned + plan.recv_offset[k]) * elem_bytes, nr, 0, plan.neighbor_rank[k], comm, stream), "ncclRecv")) return -1;
         }
         return check(api->GroupEnd(), "ncclGroupEnd");
     }
-    int allreduce_sum(cudaStream_t stream, double *dev, int n) override {
+    int allreduce_sum(cudaStream_t stream, int, double *dev, int n) override {
         return check(api->AllReduce(dev, dev, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
     }
-    int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) override {
+    int allreduce_sum_f32(cudaStream_t stream, int, float *dev, int n) override {
         return check(api->AllReduce(dev, dev, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
+    }
+    int allgather_host(cudaStream_t stream, const void *in, size_t bytes, void *out) override {
+        char *dev = nullptr;
+        if (cudaMalloc(&dev, bytes * ((size_t)world + 1)) != cudaSuccess) { error = "allgather: cudaMalloc failed"; return -1; }
+        int rc = 0;
+        if (cudaMemcpyAsync(dev, in, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = -1;
+        if (!rc) rc = check(api->AllGather(dev, dev + bytes, bytes, /*ncclChar*/ 0, comm, stream), "ncclAllGather");
+        if (!rc && (cudaMemcpyAsync(out, dev + bytes, bytes * (size_t)world, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                    cudaStreamSynchronize(stream) != cudaSuccess)) { error = "allgather: copy failed"; rc = -1; }
+        cudaFree(dev);
+        return rc;
     }
 };
 
@@ -148,6 +190,7 @@ struct LocalGroup {
     std::vector<const char *> sendbuf;
     std::vector<const HaloPlan *> plan;
     std::vector<std::vector<double>> values;
+    std::vector<std::vector<unsigned char>> blobs;
 
     void barrier() {
         std::unique_lock<std::mutex> lock(mu);
@@ -166,6 +209,7 @@ struct LocalGroup {
             g->sendbuf.assign((size_t)world, nullptr);
             g->plan.assign((size_t)world, nullptr);
             g->values.assign((size_t)world, std::vector<double>());
+            g->blobs.assign((size_t)world, std::vector<unsigned char>());
             registry[key] = g;
         }
         return g;
@@ -182,7 +226,9 @@ public:
         if (group->world != world) { error = "in-process group: world size mismatch"; return -1; }
         return 0;
     }
-    int exchange(cudaStream_t stream, const HaloPlan &plan, const char *sendbuf, char *array, size_t elem_bytes) override {
+    int exchange(cudaStream_t stream, int, const HaloPlan &plan, const int *send_index_dev, char *scratch, char *array, size_t elem_bytes) override {
+        pack(stream, plan, send_index_dev, array, scratch, elem_bytes);
+        const char *sendbuf = scratch;
         if (cudaStreamSynchronize(stream) != cudaSuccess) { error = "sync before exchange"; return -1; }
         group->sendbuf[(size_t)rank] = sendbuf;
         group->plan[(size_t)rank] = &plan;
@@ -221,8 +267,18 @@ public:
         group->barrier();
         return 0;
     }
-    int allreduce_sum(cudaStream_t stream, double *dev, int n) override { return allreduce_host<double>(stream, dev, n); }
-    int allreduce_sum_f32(cudaStream_t stream, float *dev, int n) override { return allreduce_host<float>(stream, dev, n); }
+    int allreduce_sum(cudaStream_t stream, int, double *dev, int n) override { return allreduce_host<double>(stream, dev, n); }
+    int allreduce_sum_f32(cudaStream_t stream, int, float *dev, int n) override { return allreduce_host<float>(stream, dev, n); }
+    int allgather_host(cudaStream_t, const void *in, size_t bytes, void *out) override {
+        group->blobs[(size_t)rank].assign((const unsigned char *)in, (const unsigned char *)in + bytes);
+        group->barrier();
+        for (int r = 0; r < group->world; ++r) {
+            if (group->blobs[(size_t)r].size() != bytes) { error = "in-process allgather: size mismatch"; return -1; }
+            memcpy((char *)out + bytes * (size_t)r, group->blobs[(size_t)r].data(), bytes);
+        }
+        group->barrier();
+        return 0;
+    }
 };
 
 }  // namespace arap

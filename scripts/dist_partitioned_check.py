@@ -31,7 +31,8 @@ def main():
         uid.copy_(torch.from_numpy(capi.comm_unique_id()))
     dist.broadcast(uid, 0)
     block_jacobi = os.environ.get("ARAP_DIST_BLOCK_JACOBI", "0") == "1"      # the per-rank preconditioner, for comparison
-    p = capi.PartitionedDeformation(P, F, owner, rank, world, capi.TRANSPORT_NCCL, uid.cpu().numpy(), np.float64,
+    kind = capi.TRANSPORT_PEER if os.environ.get("ARAP_DIST_TRANSPORT", "nccl") == "peer" else capi.TRANSPORT_NCCL
+    p = capi.PartitionedDeformation(P, F, owner, rank, world, kind, uid.cpu().numpy(), np.float64,
                                     global_multigrid=not block_jacobi, device=local)
     p.setConstraints(idx, tgt)
     t0 = time.perf_counter()
@@ -53,6 +54,7 @@ def main():
         for g, x, _, _ in pieces:
             pos[g] = x
         out = {"world": world, "vertices": int(P.shape[0]), "iterations": iters, "ms_per_iteration": float(t.item()) / iters,
+               "transport": "peer memory (direct stores + flags)" if kind == capi.TRANSPORT_PEER else "nccl",
                "preconditioner": "block-Jacobi multigrid per rank" if block_jacobi else "global multigrid, rows partitioned",
                "prepare_s": prep, "mg_levels": pieces[0][3]["mg_levels"], "setup_host_ms": pieces[0][3]["setup_host_ms"], "cg_iterations_per_step": pieces[0][3]["cg_iterations_total"] / max(1, pieces[0][3]["global_steps"]),
                "halo_vertices_rank0": int(p.part.n_local - p.part.n_owned)}

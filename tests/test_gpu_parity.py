@@ -345,9 +345,10 @@ def test_rigid_constraint_front_end_matches_per_vertex_constraints(meshes):
         b.setRigidConstraints(np.array([P.shape[0]], np.int32), P[:1], poses)
 
 
+@pytest.mark.parametrize("transport", ["host", "peer"])
 @pytest.mark.parametrize("solver", ["mg", "jacobi"])
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_partitioned_mesh_in_process_matches_oracle(world, solver):
+def test_partitioned_mesh_in_process_matches_oracle(world, solver, transport):
     """BASELINE.json configs[4] in small: the plane.obj-topology grid with 2+2 constraint columns, partitioned into
     `world` strips that run concurrently on ONE GPU (in-process transport: same solver code path as NCCL, copies
     instead of NVLink). Result must match the unpartitioned CPU oracle."""
@@ -356,8 +357,9 @@ def test_partitioned_mesh_in_process_matches_oracle(world, solver):
     P, F = G.grid_plane(nx, nz)
     idx, tgt = G.grid_constraints(nx, nz, P)
     owner = PT.strip_owner(P, world)
-    key = 1000 + 10 * world + (0 if solver == "mg" else 1)
-    parts = [capi.PartitionedDeformation(P, F, owner, r, world, capi.TRANSPORT_IN_PROCESS, key, np.float64, solver=SOLVERS[solver])
+    key = 1000 + 10 * world + (0 if solver == "mg" else 1) + (100 if transport == "peer" else 0)
+    kind = capi.TRANSPORT_PEER_IN_PROCESS if transport == "peer" else capi.TRANSPORT_IN_PROCESS     # peer: direct stores + flags
+    parts = [capi.PartitionedDeformation(P, F, owner, r, world, kind, key, np.float64, solver=SOLVERS[solver])
              for r in range(world)]
 
     def work(p):
@@ -378,16 +380,17 @@ def test_partitioned_mesh_in_process_matches_oracle(world, solver):
     assert o.deform(iters)
     err = np.abs(pos - omesh).max() / bbox_diag(P)
     de = abs(energy - o.energy()) / o.energy()
-    print("partitioned", world, solver, "err/diag", err, "rel dE", de, [p.solver_stats()["last_cg_iterations"] for p in parts])
+    print("partitioned", world, solver, transport, "err/diag", err, "rel dE", de, [p.solver_stats()["last_cg_iterations"] for p in parts])
     assert err <= POS_TOL and de <= E_TOL
     its = {p.solver_stats()["cg_iterations_total"] for p in parts}
     assert len(its) == 1                      # every rank took exactly the same control path
 
 
-def _run_partitioned(P, F, idx, tgt, world, key, iters, **kw):
+def _run_partitioned(P, F, idx, tgt, world, key, iters, transport=None, **kw):
     from mesh_deform_b200 import partition as PT
     owner = PT.strip_owner(P, world)
-    parts = [capi.PartitionedDeformation(P, F, owner, r, world, capi.TRANSPORT_IN_PROCESS, key, np.float64, **kw) for r in range(world)]
+    kind = capi.TRANSPORT_IN_PROCESS if transport is None else transport
+    parts = [capi.PartitionedDeformation(P, F, owner, r, world, kind, key, np.float64, **kw) for r in range(world)]
 
     def work(p):
         def run():
@@ -414,6 +417,8 @@ def test_partitioned_global_multigrid_keeps_the_iteration_count():
     assert single.deform(iters)
     its_single = single.solver_stats()["cg_iterations_total"]
     pos_g, st_g = _run_partitioned(P, F, idx, tgt, 4, 2001, iters)
+    pos_p, st_p = _run_partitioned(P, F, idx, tgt, 4, 2003, iters, transport=capi.TRANSPORT_PEER_IN_PROCESS)
+    assert np.array_equal(pos_p, pos_g) and st_p["cg_iterations_total"] == st_g["cg_iterations_total"]     # same arithmetic, other wires
     pos_b, st_b = _run_partitioned(P, F, idx, tgt, 4, 2002, iters, global_multigrid=False)
     print("cg iterations: single", its_single, "partitioned global", st_g["cg_iterations_total"], "block-Jacobi", st_b["cg_iterations_total"],
           "levels", st_g["mg_levels"])
