@@ -120,6 +120,8 @@ typedef struct arap_solver_stats {
     int32_t mg_levels;             /* 0 when the Jacobi preconditioner is in use */
     double mg_operator_complexity;
     double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare */
+    int32_t cg_graph;              /* 1: a CG iteration (with its exchanges, if partitioned) is replayed from a CUDA graph */
+    int32_t mg_global;             /* 1: partitioned mode with the global hierarchy (arap_partition_set_global_mesh) */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 
@@ -130,7 +132,7 @@ enum {
     ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC,
     ARAP_K_MG_FINE_RESIDUAL, ARAP_K_MG_FINE_POSTSMOOTH, ARAP_K_MG_CSR_RESIDUAL, ARAP_K_MG_RESTRICT, ARAP_K_MG_PROLONG,
     ARAP_K_MG_CSR_POSTSMOOTH, ARAP_K_MG_DENSE_SOLVE, ARAP_K_CG_UPDATE_MG, ARAP_K_CG_DIRECTION_MG, ARAP_K_CG_DOT,
-    ARAP_K_HALO_PACK, ARAP_K_CG_FINALIZE, ARAP_K_LOCAL_STEP_REDO, ARAP_K_COUNT_MAX = 32
+    ARAP_K_HALO_PACK, ARAP_K_CG_FINALIZE, ARAP_K_LOCAL_STEP_REDO, ARAP_K_MG_TAIL, ARAP_K_COUNT_MAX = 32
 };
 typedef struct arap_profile {
     int64_t launches[ARAP_K_COUNT_MAX];

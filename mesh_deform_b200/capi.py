@@ -48,7 +48,7 @@ class Options(C.Structure):
 class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
                 ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
-                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double)]
+                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32)]
 
 
 class GlobalMesh(C.Structure):

@@ -33,7 +33,7 @@ static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
     "cg_update", "cg_direction", "apply_update", "energy", "misc",
     "mg_fine_residual", "mg_fine_postsmooth", "mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add",
-    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize", "local_step_redo"};
+    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize", "local_step_redo", "mg_tail"};
 
 static thread_local std::string g_create_error;
 
@@ -291,6 +291,10 @@ public:
     bool mg_global = false;                        // the current hierarchy is this rank's share of the global one
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
+    // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
+    MgTailArgs tail_args;
+    int tail_first = 0;                            // 0 = no tail kernel
+    int tail_cluster = 8;
     cudaGraph_t cg_graph = nullptr;                // one CG iteration (preconditioner included), replayed per iteration
     cudaGraphExec_t cg_graph_exec = nullptr;
     bool have_warm_rotations = false;              // quat[] holds the previous iteration's R_i
@@ -588,6 +592,8 @@ public:
         // Partitions that share one GPU and wait on each other inside kernels (in-process peer transport) must not start
         // iterating while another one is still allocating: cudaFree waits for ALL device work, spinning kernels included.
         if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
+        stats.cg_graph = cg_graph_exec ? 1 : 0;
+        stats.mg_global = (use_mg && mg_global) ? 1 : 0;
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
@@ -896,6 +902,7 @@ public:
         mg_dense = !H.coarse_inv.empty();
         if (mg_dense) ARAP_CUDA(upload_as_float(mg_coarse_inv, H.coarse_inv, stream, fscratch));
         ARAP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
+        { int rc = plan_tail(); if (rc) return rc; }
         stats.mg_levels = (int)mg.size();
         stats.mg_operator_complexity = H.operator_complexity;
         stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1031,6 +1038,60 @@ public:
         return reduce_stage(CG_STAGE_RHO, 3);
     }
 
+    // Which levels the one-kernel tail covers: from the first level with at most ARAP_TAIL_ROWS rows down to the coarsest,
+    // provided its parent is small enough for the two transfer phases to run inside one cluster.
+    // OFF by default (ARAP_TAIL_ROWS unset = 0). Measured at 1M vertices (profiles/r01_d_variants.txt, "one-kernel tail"): the
+    // 7 launches it replaces cost ~25 us per CG iteration when replayed from the CUDA graph (3.6 us each), the cluster kernel
+    // 34-42 us: with only 8-16 CTAs every phase is a chain of dependent L2 round trips that the full-GPU launches overlap.
+    int plan_tail() {
+        tail_first = 0;
+        const int L = (int)mg.size();
+        const char *env_rows = getenv("ARAP_TAIL_ROWS"), *env_parent = getenv("ARAP_TAIL_PARENT_ROWS"), *env_cluster = getenv("ARAP_TAIL_CLUSTER");
+        const int max_rows = env_rows ? atoi(env_rows) : 0, max_parent = env_parent ? atoi(env_parent) : 65536;
+        tail_cluster = env_cluster ? atoi(env_cluster) : 8;
+        if (L < 2 || max_rows <= 0 || mg_global) return ARAP_OK;
+        int t = 0;
+        for (int l = 1; l < L; ++l) if (mg[(size_t)l]->n <= max_rows) { t = l; break; }
+        if (t == 0 || mg[(size_t)t - 1]->n > max_parent || L - t + 1 > kTailMaxLevels) return ARAP_OK;
+        if (t - 1 == 0 && transport) return ARAP_OK;           // partitioned: level 0 rows are the owned rows only; keep the plain path
+        std::memset(&tail_args, 0, sizeof(tail_args));
+        tail_args.n_levels = L - t + 1;
+        tail_args.dense = mg_dense ? 1 : 0;
+        tail_args.coarse_inv = mg_coarse_inv.ptr;
+        for (int l = t - 1; l < L; ++l) {
+            MgLevelDev &d = *mg[(size_t)l];
+            MgTailLevel &a = tail_args.lv[l - (t - 1)];
+            a.n = d.n; a.a_lanes = d.a_lanes; a.r_lanes = d.r_lanes; a.omega = (float)d.omega;
+            a.a_rowptr = d.a_rowptr.ptr; a.a_colidx = d.a_colidx.ptr; a.a_val = d.a_val.ptr; a.inv_diag = d.inv_diag.ptr;
+            a.p_rowptr = d.p_rowptr.ptr; a.p_colidx = d.p_colidx.ptr; a.p_val = d.p_val.ptr;
+            a.r_rowptr = d.r_rowptr.ptr; a.r_colidx = d.r_colidx.ptr; a.r_val = d.r_val.ptr;
+            a.b = d.b.ptr; a.x = d.x.ptr; a.x2 = d.x2.ptr; a.r = d.r.ptr;
+        }
+        if (tail_cluster > 8) ARAP_CUDA(cudaFuncSetAttribute(mg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        tail_first = t;
+        return ARAP_OK;
+    }
+
+    int launch_tail() {
+        cudaLaunchConfig_t cfg;
+        cfg = cudaLaunchConfig_t();
+        cfg.gridDim = dim3((unsigned)tail_cluster, 1, 1);
+        cfg.blockDim = dim3(kTailThreads, 1, 1);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)tail_cluster;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        begin_launch(ARAP_K_MG_TAIL);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mg_tail_kernel, tail_args, (const CgScalars *)cg.ptr);
+        end_launch();
+        if (e != cudaSuccess) return fail(ARAP_ERR_CUDA, std::string("mg_tail_kernel launch: ") + cudaGetErrorString(e));
+        return ARAP_OK;
+    }
+
     // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
     // Buffer roles are fixed (no pointer swapping) so that the launch sequence can be captured in a CUDA graph:
     // on every level x = iterate before post-smoothing, x2 = the level's result; level 0's result is z = mg[0]->x2.
@@ -1053,7 +1114,9 @@ public:
             return reduce_stage(CG_STAGE_RHO, 3);
         }
         // down
-        for (int l = 0; l + 1 < L; ++l) {
+        // levels [tail_first, L) run inside mg_tail_kernel, which also restricts into and prolongates out of them
+        const int top = tail_first > 0 ? tail_first - 1 : L - 1;      // the coarsest level handled launch by launch
+        for (int l = 0; l <= top && l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
                 LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
@@ -1062,13 +1125,17 @@ public:
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.b.ptr, f.x.ptr, f.r.ptr, cg.ptr));
             }
+            if (l == top) break;                                       // the tail kernel restricts out of this level itself
             ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
                                                   c.x.ptr, cg.ptr));
         }
         // coarsest: exact dense solve, or one more damped-Jacobi step when the level is too large for a dense inverse
         MgLevelDev &cl = *mg[L - 1];
-        if (mg_dense) {
+        if (tail_first > 0) {
+            int rc = launch_tail();
+            if (rc) return rc;
+        } else if (mg_dense) {
             LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
                    cl.b.ptr, cl.x2.ptr, cg.ptr);
         } else {
@@ -1077,11 +1144,12 @@ public:
                                                    cl.x.ptr, cl.x2.ptr, cg.ptr));
         }
         // up
-        for (int l = L - 2; l >= 0; --l) {
+        for (int l = (tail_first > 0 ? top : L - 2); l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             const int rows = (l == 0) ? R : f.n;
-            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
-                   c.x2.ptr, f.x.ptr, cg.ptr);
+            if (!(tail_first > 0 && l == top))                         // the tail kernel already prolongated into its parent
+                LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+                       c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
                 LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
                        hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);

@@ -12,6 +12,8 @@
 
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
+
 namespace arap {
 
 typedef float4 MgVec;      // (x, y, z, unused)
@@ -203,6 +205,157 @@ __global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, const flo
         s2 += __shfl_down_sync(0xffffffffu, s2, o);
     }
     if (lane == 0) x[row] = MgVec{s0, s1, s2, 0.f};
+}
+
+// ---- the tail of the V-cycle in ONE kernel -----------------------------------------------------------------------
+// On the coarse levels (a few thousand rows and fewer) every kernel above is pure launch latency: ~11 dependent launches of
+// ~3-5 us each per CG iteration, a quarter of the iteration at 1M vertices. This kernel runs the whole tail -- restriction
+// into the first small level, residual / restriction down to the coarsest level, the dense solve, prolongation and
+// post-smoothing back up, and the prolongation out of the tail -- as phases of one thread-block CLUSTER separated by the
+// hardware cluster barrier (~0.5 us instead of a kernel boundary). All vectors of the tail live in global memory / L2 and
+// are read with ld.global.cg (never through L1: another CTA of the cluster wrote them in the previous phase).
+constexpr int kTailMaxLevels = 12;
+constexpr int kTailThreads = 1024;
+
+struct MgTailLevel {
+    int n, a_lanes, r_lanes;
+    float omega;
+    const int *a_rowptr, *a_colidx;
+    const float *a_val, *inv_diag;
+    const int *p_rowptr, *p_colidx;          // P: rows of this level -> columns of the next (coarser) level
+    const float *p_val;
+    const int *r_rowptr, *r_colidx;          // R: rows of the next level <- columns of this level
+    const float *r_val;
+    MgVec *b, *x, *x2, *r;
+};
+struct MgTailArgs {
+    int n_levels;                            // lv[0] = the parent of the tail (only its r, x, P, R are used), lv[n_levels-1] = coarsest
+    int dense;                               // coarsest level: dense inverse (else one more damped-Jacobi step)
+    const float *coarse_inv;
+    MgTailLevel lv[kTailMaxLevels];
+};
+
+__device__ __forceinline__ MgVec tail_load(const MgVec *p) { return __ldcg(p); }
+
+// (M v)_row with `lanes` threads per row; complete in the row's lane 0. All threads of a warp must call it together.
+__device__ __forceinline__ float3 tail_apply_row(int row, bool valid, int lanes, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                 const float *__restrict__ val, const MgVec *v) {
+    float3 out = {0.f, 0.f, 0.f};
+    if (valid) {
+        const int k1 = __ldg(&rowptr[row + 1]);
+        for (int k = __ldg(&rowptr[row]) + (int)(threadIdx.x & (lanes - 1)); k < k1; k += lanes) {
+            const float a = __ldg(&val[k]);
+            const MgVec xj = tail_load(&v[__ldg(&colidx[k])]);
+            out.x += a * xj.x; out.y += a * xj.y; out.z += a * xj.z;
+        }
+    }
+    for (int o = lanes >> 1; o > 0; o >>= 1) {
+        out.x += __shfl_down_sync(0xffffffffu, out.x, o, lanes);
+        out.y += __shfl_down_sync(0xffffffffu, out.y, o, lanes);
+        out.z += __shfl_down_sync(0xffffffffu, out.z, o, lanes);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const MgTailArgs args, const CgScalars *__restrict__ cg) {
+    namespace cgrp = cooperative_groups;
+    cgrp::cluster_group cluster = cgrp::this_cluster();
+    if (cg->converged) return;                                  // uniform over the cluster: nobody reaches a barrier
+    const int nt = (int)cluster.num_blocks() * kTailThreads;
+    const int tid = (int)cluster.block_rank() * kTailThreads + (int)threadIdx.x;
+    const int L = args.n_levels;
+
+    auto restrict_presmooth = [&](const MgTailLevel &f, const MgTailLevel &c) {      // b_c = R r_f ; x_c = omega_c D_c^-1 b_c
+        const int lanes = f.r_lanes, per = nt / lanes;
+        for (int base = 0; base < c.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 bc = tail_apply_row(row, row < c.n, lanes, f.r_rowptr, f.r_colidx, f.r_val, f.r);
+            if (row < c.n && (threadIdx.x & (lanes - 1)) == 0) {
+                c.b[row] = MgVec{bc.x, bc.y, bc.z, 0.f};
+                const float s = c.omega * __ldg(&c.inv_diag[row]);
+                c.x[row] = MgVec{s * bc.x, s * bc.y, s * bc.z, 0.f};
+            }
+        }
+    };
+    auto residual = [&](const MgTailLevel &f) {                                       // r = b - A x
+        const int lanes = f.a_lanes, per = nt / lanes;
+        for (int base = 0; base < f.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 ax = tail_apply_row(row, row < f.n, lanes, f.a_rowptr, f.a_colidx, f.a_val, f.x);
+            if (row < f.n && (threadIdx.x & (lanes - 1)) == 0) {
+                const MgVec bi = tail_load(&f.b[row]);
+                f.r[row] = MgVec{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z, 0.f};
+            }
+        }
+    };
+    auto postsmooth = [&](const MgTailLevel &f) {                                     // x2 = x + omega D^-1 (b - A x)
+        const int lanes = f.a_lanes, per = nt / lanes;
+        for (int base = 0; base < f.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 ax = tail_apply_row(row, row < f.n, lanes, f.a_rowptr, f.a_colidx, f.a_val, f.x);
+            if (row < f.n && (threadIdx.x & (lanes - 1)) == 0) {
+                const MgVec bi = tail_load(&f.b[row]), xi = tail_load(&f.x[row]);
+                const float s = f.omega * __ldg(&f.inv_diag[row]);
+                f.x2[row] = MgVec{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z), 0.f};
+            }
+        }
+    };
+    auto prolong_add = [&](const MgTailLevel &f, const MgTailLevel &c) {              // x_f += P x2_c (P rows are short: one thread each)
+        for (int row = tid; row < f.n; row += nt) {
+            const int k0 = __ldg(&f.p_rowptr[row]), k1 = __ldg(&f.p_rowptr[row + 1]);
+            if (k0 == k1) continue;
+            MgVec xi = tail_load(&f.x[row]);
+            for (int k = k0; k < k1; ++k) {
+                const float a = __ldg(&f.p_val[k]);
+                const MgVec xc = tail_load(&c.x2[__ldg(&f.p_colidx[k])]);
+                xi.x += a * xc.x; xi.y += a * xc.y; xi.z += a * xc.z;
+            }
+            f.x[row] = xi;
+        }
+    };
+
+    // down
+    restrict_presmooth(args.lv[0], args.lv[1]);
+    cluster.sync();
+    for (int l = 1; l + 1 < L; ++l) {
+        residual(args.lv[l]);
+        cluster.sync();
+        restrict_presmooth(args.lv[l], args.lv[l + 1]);
+        cluster.sync();
+    }
+    // coarsest
+    {
+        const MgTailLevel &c = args.lv[L - 1];
+        if (args.dense) {                                         // x2 = A^-1 b, one warp per row
+            const int lane = threadIdx.x & 31, n = c.n;
+            for (int row = tid >> 5; row < n; row += nt >> 5) {
+                float s0 = 0, s1 = 0, s2 = 0;
+                for (int k = lane; k < n; k += 32) {
+                    const float a = __ldg(&args.coarse_inv[(size_t)row * n + k]);
+                    const MgVec bk = tail_load(&c.b[k]);
+                    s0 += a * bk.x; s1 += a * bk.y; s2 += a * bk.z;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_down_sync(0xffffffffu, s2, o);
+                }
+                if (lane == 0) c.x2[row] = MgVec{s0, s1, s2, 0.f};
+            }
+        } else {
+            postsmooth(c);
+        }
+    }
+    cluster.sync();
+    // up
+    for (int l = L - 2; l >= 1; --l) {
+        prolong_add(args.lv[l], args.lv[l + 1]);
+        cluster.sync();
+        postsmooth(args.lv[l]);
+        cluster.sync();
+    }
+    prolong_add(args.lv[0], args.lv[1]);
 }
 
 // single-level hierarchies (tiny meshes): the V-cycle input/output live in fp64 CG vectors

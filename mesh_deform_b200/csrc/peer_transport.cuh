@@ -44,7 +44,7 @@ struct PeerExchangeDev {
     const unsigned long long *local_payload;            // this site's mailbox in my arena (halo order)
     const unsigned long long *local_flag[kPeerMaxRanks];
     int n_recv_words;
-    unsigned long long send_epoch, recv_epoch;
+    unsigned long long send_epoch;
     unsigned int done;
 };
 
@@ -54,7 +54,7 @@ struct PeerReduceDev {
     unsigned long long *remote_flag[kPeerMaxRanks];
     const void *local_slots;                            // `world` slots of n values in my arena
     const unsigned long long *local_flag[kPeerMaxRanks];
-    unsigned long long send_epoch, recv_epoch;
+    unsigned long long send_epoch;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -104,20 +104,29 @@ __global__ void __launch_bounds__(256) peer_put_kernel(PeerExchangeDev *site, co
     }
 }
 
-// receiver (ONE CTA): wait for every neighbour's flag, then mailbox -> halo slots
-__global__ void __launch_bounds__(1024) peer_wait_unpack_kernel(PeerExchangeDev *site, unsigned long long *__restrict__ halo, int *error) {
+// receiver: wait for every neighbour's flag, then mailbox -> halo slots (16 bytes per thread and step; a few CTAs, each
+// waiting for itself). The epoch to wait for is this rank's OWN send count at the site: every exchange is a put
+// followed by a wait on every rank, so after my put kernel (earlier in the stream) send_epoch is exactly the number
+// of the exchange the neighbours are publishing.
+template <bool WIDE>      // WIDE: the halo slots start 16-byte aligned (always, except for 24-byte elements behind an odd owned count)
+__global__ void __launch_bounds__(256) peer_wait_unpack_kernel(const PeerExchangeDev *site, unsigned long long *__restrict__ halo, int *error) {
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
-    const unsigned long long epoch = site->recv_epoch + 1;
+    const unsigned long long epoch = site->send_epoch;
     if ((int)threadIdx.x < site->n_nbr && !peer_spin_until(site->local_flag[threadIdx.x], epoch, error)) ok = 0;
     __syncthreads();
-    if (ok) {
-        const volatile unsigned long long *src = site->local_payload;      // written by a peer: never through L1
-        for (int t = threadIdx.x; t < site->n_recv_words; t += blockDim.x) halo[t] = src[t];
+    if (!ok) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const int nw = site->n_recv_words;
+    if (WIDE) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(site->local_payload);
+        uint4 *dst = reinterpret_cast<uint4 *>(halo);
+        for (int t = tid; t < nw / 2; t += stride) dst[t] = __ldcv(src + t);                    // written by a peer: never through L1
+        if ((nw & 1) && tid == 0) halo[nw - 1] = __ldcv(site->local_payload + nw - 1);
+    } else {
+        for (int t = tid; t < nw; t += stride) halo[t] = __ldcv(site->local_payload + t);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) site->recv_epoch = epoch;
 }
 
 template <typename T>
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(256) peer_reduce_wait_kernel(PeerReduceDev *si
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
-    const unsigned long long epoch = site->recv_epoch + 1;
+    const unsigned long long epoch = site->send_epoch;          // my own put for this reduction came first (see above)
     const int n = site->n, world = site->world;
     if ((int)threadIdx.x < world && !peer_spin_until(site->local_flag[threadIdx.x], epoch, error)) ok = 0;
     __syncthreads();
@@ -154,8 +163,6 @@ __global__ void __launch_bounds__(256) peer_reduce_wait_kernel(PeerReduceDev *si
             values[c] = sum;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) site->recv_epoch = epoch;
 }
 
 class PeerTransport : public Transport {
@@ -321,7 +328,12 @@ public:
         int grid = (total + 255) / 256;
         grid = grid < 1 ? 1 : (grid > 128 ? 128 : grid);
         peer_put_kernel<<<grid, 256, 0, stream>>>(ex_dev + site, send_index_dev, (const unsigned long long *)array);
-        peer_wait_unpack_kernel<<<1, 1024, 0, stream>>>(ex_dev + site, (unsigned long long *)(array + (size_t)plan.n_owned * elem_bytes), error_flag);
+        const size_t recv_bytes = (size_t)plan.n_halo() * elem_bytes;
+        int wgrid = (int)((recv_bytes + 16383) / 16384);
+        wgrid = wgrid < 1 ? 1 : (wgrid > 16 ? 16 : wgrid);
+        unsigned long long *halo = (unsigned long long *)(array + (size_t)plan.n_owned * elem_bytes);
+        if (((uintptr_t)halo & 15) == 0) peer_wait_unpack_kernel<true><<<wgrid, 256, 0, stream>>>(ex_dev + site, halo, error_flag);
+        else peer_wait_unpack_kernel<false><<<wgrid, 256, 0, stream>>>(ex_dev + site, halo, error_flag);
         return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
     }
     int allreduce_sum(cudaStream_t stream, int site, double *dev, int n) override { return reduce<double>(stream, site, dev, n, SiteSpec::REDUCE_F64); }

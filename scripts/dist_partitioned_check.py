@@ -56,7 +56,7 @@ def main():
         out = {"world": world, "vertices": int(P.shape[0]), "iterations": iters, "ms_per_iteration": float(t.item()) / iters,
                "transport": "peer memory (direct stores + flags)" if kind == capi.TRANSPORT_PEER else "nccl",
                "preconditioner": "block-Jacobi multigrid per rank" if block_jacobi else "global multigrid, rows partitioned",
-               "prepare_s": prep, "mg_levels": pieces[0][3]["mg_levels"], "setup_host_ms": pieces[0][3]["setup_host_ms"], "cg_iterations_per_step": pieces[0][3]["cg_iterations_total"] / max(1, pieces[0][3]["global_steps"]),
+               "prepare_s": prep, "cg_graph": pieces[0][3]["cg_graph"], "mg_levels": pieces[0][3]["mg_levels"], "setup_host_ms": pieces[0][3]["setup_host_ms"], "cg_iterations_per_step": pieces[0][3]["cg_iterations_total"] / max(1, pieces[0][3]["global_steps"]),
                "halo_vertices_rank0": int(p.part.n_local - p.part.n_owned)}
         if check:
             from oracle import oracle as O
