@@ -265,8 +265,9 @@ def main():
     ap.add_argument("--nu", type=int, default=316, help="icosphere frequency (316 -> 998,562 vertices)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-iters", type=int, default=2, help="oracle iterations in the cpu_baseline sample")
+    ap.add_argument("--cpu-iters", type=int, default=4, help="oracle iterations in the cpu_baseline sample")
     ap.add_argument("--cg-tol", type=float, default=0.0)
+    ap.add_argument("--pos-tol", type=float, default=0.0, help="position_tolerance of the multigrid solver (0 = engine default)")
     ap.add_argument("--solver", default="auto", choices=["auto", "jacobi", "mg"])
     ap.add_argument("--workload", default="icosphere", choices=["icosphere", "batch_spheres"])
     ap.add_argument("--batch", type=int, default=4096)
@@ -294,6 +295,8 @@ def main():
     opts = {"device": local_rank, "solver": {"auto": 0, "jacobi": 1, "mg": 2}[args.solver]}
     if args.cg_tol > 0:
         opts["cg_tolerance"] = args.cg_tol
+    if args.pos_tol > 0:
+        opts["position_tolerance"] = args.pos_tol
 
     # ---- device-resident arm ------------------------------------------------------------------
     pinned = capi.PinnedArray((V, 3), real)
@@ -433,7 +436,7 @@ def main():
                    "sharding": "one independent deformation per GPU, no collective" if world > 1 else "single GPU",
                    "solver": ("warm-started CG, smoothed-aggregation multigrid V(1,1) preconditioner, %d levels, operator complexity %.2f"
                               % (stats["mg_levels"], stats["mg_operator_complexity"])) if stats["mg_levels"] else
-                   "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "cg_tolerance": float(arap_tolerance(args)),
+                   "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "stopping_rule": stopping_rule(args),
                    "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
                 "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",
@@ -457,8 +460,16 @@ def main():
     return 0
 
 
-def arap_tolerance(args):
-    return args.cg_tol if args.cg_tol > 0 else (1e-9 if args.solver == "jacobi" else 1e-6)
+def stopping_rule(args):
+    """The engine's rule for ending a global solve (include/arap_b200.h: cg_tolerance, position_tolerance)."""
+    if args.solver == "jacobi":
+        return {"relative_residual": args.cg_tol if args.cg_tol > 0 else 1e-9}
+    rule = {}
+    if args.cg_tol > 0:
+        rule["relative_residual"] = args.cg_tol
+    if args.pos_tol > 0 or not args.cg_tol > 0:
+        rule["estimated_position_error_over_bbox_diagonal"] = args.pos_tol if args.pos_tol > 0 else 3e-8
+    return rule
 
 
 if __name__ == "__main__":

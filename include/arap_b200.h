@@ -61,10 +61,14 @@ typedef struct arap_options {
     int32_t solver;             /* ARAP_SOLVER_* */
     int32_t max_cg_iterations;  /* per global step; <= 0 -> default */
     double cg_tolerance;        /* stop when |r|_2 <= tol * |rhs|_2 (all three coordinates together); <= 0 -> per-solver default:
-                                 * 1e-6 with the multigrid preconditioner (measured: positions within ~2e-8 x bbox diagonal of a
-                                 * direct solve after 20 iterations), 1e-9 with plain Jacobi */
+                                 * plain Jacobi: 1e-9; multigrid: no residual test (1e-13 floor), position_tolerance decides */
     int32_t cg_check_interval;  /* CG iterations between convergence polls; <= 0 -> default */
     int32_t profile;            /* != 0: time every kernel launch with CUDA events (see arap_profile_*) */
+    double position_tolerance;  /* multigrid solver only: stop a global solve when the estimated position error of the
+                                 * iterate (the 8-norm over the vertices of z = M^-1 r, M^-1 one V-cycle) is below
+                                 * position_tolerance x bounding-box diagonal of the rest pose. This is the default stopping
+                                 * rule (<= 0 -> 3e-8 when cg_tolerance is not given; ignored when cg_tolerance > 0 unless set
+                                 * explicitly): unlike a residual tolerance it means the same thing on every mesh. */
 } arap_options;
 
 /* Fill `opt` with the defaults (and struct_size). */
@@ -122,6 +126,7 @@ typedef struct arap_solver_stats {
     double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare */
     int32_t cg_graph;              /* 1: a CG iteration (with its exchanges, if partitioned) is replayed from a CUDA graph */
     int32_t mg_global;             /* 1: partitioned mode with the global hierarchy (arap_partition_set_global_mesh) */
+    double last_position_error;    /* multigrid: the estimate the stopping rule used, as a fraction of the bbox diagonal */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 

@@ -42,13 +42,13 @@ EXPORTED_SYMBOLS = (
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("solver", C.c_int32),
                 ("max_cg_iterations", C.c_int32), ("cg_tolerance", C.c_double),
-                ("cg_check_interval", C.c_int32), ("profile", C.c_int32)]
+                ("cg_check_interval", C.c_int32), ("profile", C.c_int32), ("position_tolerance", C.c_double)]
 
 
 class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
                 ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
-                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32)]
+                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32), ("last_position_error", C.c_double)]
 
 
 class GlobalMesh(C.Structure):

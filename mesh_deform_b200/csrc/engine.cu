@@ -16,6 +16,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <algorithm>
 #include <chrono>
@@ -27,6 +28,11 @@
 #include <vector>
 
 namespace arap {
+
+// Default stopping rule of the multigrid solver (include/arap_b200.h, position_tolerance); chosen from the
+// sweep in profiles/r01_h_stopping_rule.txt: 20 ARAP iterations stay within 5e-7 x bbox diagonal and 2e-7 relative energy of
+// the direct solve on regular AND badly conditioned meshes, 20x / 5x inside the parity bar.
+static const double kDefaultPositionTolerance = 3e-8;
 
 static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "weights_count", "weights_fill", "row_sort_merge", "csr_compact", "scan",
@@ -571,8 +577,18 @@ public:
         std::memset(&init, 0, sizeof(init));
         // default tolerance: with the multigrid preconditioner the residual tracks the error closely (1e-6 keeps
         // positions within ~2e-8 x bbox diagonal of a direct solve, measured); plain Jacobi needs a much smaller one.
-        const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : (use_mg ? 1e-6 : 1e-9);
+        // Stopping rule. Jacobi-PCG: relative residual (default 1e-9). Multigrid: the estimated position error of the
+        // iterate (kernels.cuh, CG_STAGE_RHO) against position_tolerance x bbox diagonal -- the parity bar is a position
+        // bar, and the same relative residual means very different position errors on different meshes. An explicit
+        // cg_tolerance keeps the residual rule (and switches the position rule off unless that is given explicitly too).
+        const double tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : (use_mg ? 1e-13 : 1e-9);
         init.tol2 = tol * tol;
+        if (use_mg && (opt.position_tolerance > 0 || !(opt.cg_tolerance > 0))) {
+            const double ptol = opt.position_tolerance > 0 ? opt.position_tolerance : kDefaultPositionTolerance;
+            init.z8_tol = std::pow(ptol, 8.0);
+            const double len = rest_bbox_diagonal(rest_host, scalar_bytes);
+            init.inv_len2 = len > 0 ? 1.0 / (len * len) : 1.0;
+        }
         init.distributed = transport ? 1 : 0;
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
@@ -598,6 +614,23 @@ public:
         dirty = false;                                                   // arap.h:119
         prepared = true;
         return ARAP_OK;
+    }
+
+    // bounding-box diagonal of the rest pose: the length scale of the position-error stopping rule. Partitioned mode with
+    // the global mesh known: the GLOBAL box (every rank must scale alike); otherwise this rank's box (smaller: conservative).
+    double rest_bbox_diagonal(const void *rest_host, int scalar_bytes) const {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        auto add = [&](double x, int d) { if (x < lo[d]) lo[d] = x; if (x > hi[d]) hi[d] = x; };
+        if (transport && have_global) {
+            for (size_t k = 0; k < global_mesh.rest.size(); ++k) add(global_mesh.rest[k], (int)(k % 3));
+        } else {
+            const size_t n3 = 3 * (size_t)n_vertices;
+            if (scalar_bytes == 4) for (size_t k = 0; k < n3; ++k) add((double)((const float *)rest_host)[k], (int)(k % 3));
+            else for (size_t k = 0; k < n3; ++k) add(((const double *)rest_host)[k], (int)(k % 3));
+        }
+        double s = 0;
+        for (int d = 0; d < 3; ++d) if (hi[d] > lo[d]) s += (hi[d] - lo[d]) * (hi[d] - lo[d]);
+        return std::sqrt(s);
     }
 
     // ---- internal vertex order --------------------------------------------------------------------------------------
@@ -1035,7 +1068,7 @@ public:
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
-        return reduce_stage(CG_STAGE_RHO, 3);
+        return reduce_stage(CG_STAGE_RHO, 4);
     }
 
     // Which levels the one-kernel tail covers: from the first level with at most ARAP_TAIL_ROWS rows down to the coarsest,
@@ -1111,7 +1144,7 @@ public:
                 LAUNCH(ARAP_K_MISC, mg_jacobi_kernel, grid_for((size_t)m0.n), m0.n, m0.inv_diag.ptr, (float)m0.omega, m0.x.ptr, z);
             }
             LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
-            return reduce_stage(CG_STAGE_RHO, 3);
+            return reduce_stage(CG_STAGE_RHO, 4);
         }
         // down
         // levels [tail_first, L) run inside mg_tail_kernel, which also restricts into and prolongates out of them
@@ -1159,7 +1192,7 @@ public:
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
-        return reduce_stage(CG_STAGE_RHO, 3);
+        return reduce_stage(CG_STAGE_RHO, 4);
     }
 
     bool use_tma = getenv("ARAP_TMA") != nullptr && atoi(getenv("ARAP_TMA")) != 0;
@@ -1284,6 +1317,7 @@ public:
             else if (!mg_fresh && mg_fresh_iterations > 0 && cg_host[0].iterations > (3 * mg_fresh_iterations) / 2 + 3) mg_stale = true;
         }
         stats.last_relative_residual = cg_host[0].ref2 > 0 ? sqrt(cg_host[0].rr / cg_host[0].ref2) : 0.0;
+        stats.last_position_error = cg_host[0].z8_tol > 0 ? std::pow(cg_host[0].z8, 0.125) : 0.0;
         if (!(cg_host[0].rr == cg_host[0].rr)) return fail(ARAP_ERR_SOLVER, "global step: CG residual is NaN");
         return ARAP_OK;
     }
@@ -1385,6 +1419,7 @@ void arap_default_options(arap_options *opt) {
     opt->cg_tolerance = 0.0;   /* 0 = per-solver default: 1e-6 (multigrid), 1e-9 (Jacobi) */
     opt->cg_check_interval = 32;
     opt->profile = 0;
+    opt->position_tolerance = 0.0;   /* 0 = default (multigrid, when cg_tolerance is not given) */
 }
 
 const char *arap_create_error(void) { return arap::g_create_error.c_str(); }

@@ -407,7 +407,10 @@ struct CgScalars {
     double beta[3];
     double rr;           // |r|^2 over the three coordinates
     double ref2;         // |rhs|^2 over the three coordinates
-    double tol2;         // tolerance^2
+    double tol2;         // tolerance^2 on |r| / |rhs| (0 = residual criterion off)
+    double z8_tol;       // multigrid only: stop when sum_i (|z_i| / length)^8 <= z8_tol, z = M^-1 r (0 = off); see cg_finalize
+    double inv_len2;     // 1 / length^2, length = bounding-box diagonal of the rest pose
+    double z8;           // last value of that sum (diagnostics)
     double red[8];       // partitioned mode: this rank's partial sums, all-reduced in place before cg_finalize_kernel
     int converged;
     int iterations;
@@ -446,11 +449,21 @@ __device__ __forceinline__ void cg_finalize(CgScalars *cg, int stage, const doub
             cg->iterations += 1;
             if (t[0] <= cg->tol2 * cg->ref2) cg->converged = 1;
             break;
-        case CG_STAGE_RHO:               // t = r.z per coordinate
+        case CG_STAGE_RHO:               // t = r.z per coordinate ; sum_i (|z_i| / length)^8
             for (int c = 0; c < 3; ++c) {
                 cg->beta[c] = (cg->rho[c] > 0.0) ? t[c] / cg->rho[c] : 0.0;
                 cg->rho[c] = t[c];
             }
+            // z = M^-1 r with M^-1 one multigrid V-cycle is, up to the quality of the preconditioner (~ +-40 %), the ERROR
+            // A^-1 r of the current iterate, in position units. Its 8-norm is a smooth stand-in for the largest per-vertex
+            // error (max <= 8-norm <= V^(1/8) max) that can be summed -- and all-reduced -- like every other CG scalar.
+            // A residual tolerance cannot play this role: the same |r|/|rhs| means 8e-10 of the bounding box on a regular
+            // sphere and 4e-5 on a Delaunay patch with sliver triangles (weights from 5e-11 to 3e3).
+            // (An energy rule on r.z ~ |e|_A^2, the energy excess of the iterate, was tried on top of this one and never bit:
+            // the energy deviation that remains after 20 ARAP iterations comes from the drift of the ARAP state, i.e. from the
+            // position error, not from the last solve -- profiles/r01_h_stopping_rule.txt.)
+            cg->z8 = t[3];
+            if (cg->z8_tol > 0.0 && t[3] <= cg->z8_tol) cg->converged = 1;
             break;
     }
 }
@@ -706,13 +719,13 @@ __global__ void __launch_bounds__(kBlock) cg_dot_rho_kernel(int n, const Vec3d *
                                                             double *__restrict__ partials, unsigned *__restrict__ counter,
                                                             CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    double red[3] = {0, 0, 0};
+    double red[4] = {0, 0, 0, 1e300};      // [3]: the position-error sum of CG_STAGE_RHO; this (unpreconditioned) path has none
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec3d ri = r[i], zi = z[i];
         red[0] += ri.x * zi.x; red[1] += ri.y * zi.y; red[2] += ri.z * zi.z;
     }
-    double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_RHO, total);
+    double total[4];
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
 }
 
 // d = z + beta d. Launched after cg_update; skipped (like everything else) once converged.

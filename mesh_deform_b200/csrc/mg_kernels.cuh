@@ -25,6 +25,13 @@ __device__ __forceinline__ float gather_gate(const MgVec (&a)[kSpmvChunk]) {
     return 0.0f * s;
 }
 
+// (|z| / length)^8 of one vertex: the summand of the position-error stopping criterion (cg_finalize, CG_STAGE_RHO)
+__device__ __forceinline__ double z_norm8(const MgVec &z, double inv_len2) {
+    const double q = ((double)z.x * z.x + (double)z.y * z.y + (double)z.z * z.z) * inv_len2;
+    const double q2 = q * q;
+    return q2 * q2;
+}
+
 // ---- fine level (matrix-free): (A x)_i = sum_j w_ij (x_i - x_j) on free rows ---------------------------
 __device__ __forceinline__ float3 fine_apply_row(int i, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                  const float *__restrict__ weight, const MgVec *__restrict__ x) {
@@ -80,7 +87,8 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
                                                                     MgVec *__restrict__ z, double *__restrict__ partials,
                                                                     unsigned *__restrict__ counter, CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    double red[3] = {0, 0, 0};
+    double red[4] = {0, 0, 0, 0};
+    const double inv_len2 = cg->inv_len2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         MgVec out = {0.f, 0.f, 0.f, 0.f};
         if (free_mask[i]) {
@@ -90,11 +98,12 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
             const float s = (float)(omega * inv_diag[i]);
             out.x = xi.x + s * ((float)bi.x - ax.x); out.y = xi.y + s * ((float)bi.y - ax.y); out.z = xi.z + s * ((float)bi.z - ax.z);
             red[0] += bi.x * (double)out.x; red[1] += bi.y * (double)out.y; red[2] += bi.z * (double)out.z;
+            red[3] += z_norm8(out, inv_len2);
         }
         z[i] = out;
     }
-    double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_RHO, total);
+    double total[4];
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
 }
 
 // ---- generic CSR levels -------------------------------------------------------------------------------
@@ -374,14 +383,16 @@ __global__ void __launch_bounds__(kBlock) cg_dot_rho_f_kernel(int n, const Vec3d
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
     if (cg->converged) return;
-    double red[3] = {0, 0, 0};
+    double red[4] = {0, 0, 0, 0};
+    const double inv_len2 = cg->inv_len2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec3d ri = r[i];
         const MgVec zi = z[i];
         red[0] += ri.x * (double)zi.x; red[1] += ri.y * (double)zi.y; red[2] += ri.z * (double)zi.z;
+        red[3] += z_norm8(zi, inv_len2);
     }
-    double total[3];
-    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_RHO, total);
+    double total[4];
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
 }
 
 __device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }

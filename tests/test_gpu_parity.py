@@ -236,6 +236,102 @@ def test_edge_cases():
         a.setConstraint(10 ** 6, [0, 0, 0])
 
 
+def delaunay_patch(n, seed):
+    """An irregular open surface: Delaunay triangulation of random points in the unit square, lifted to a bumpy height field.
+    Valences range from 3 to ~12 and there is a boundary -- unlike the generated spheres and grids."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    uv = rng.random((n, 2))
+    tri = Delaunay(uv).simplices.astype(np.int32)
+    P = np.column_stack([uv[:, 0], 0.15 * np.sin(5 * uv[:, 0]) * np.cos(4 * uv[:, 1]), uv[:, 1]])
+    return np.ascontiguousarray(P), np.ascontiguousarray(tri)
+
+
+@pytest.mark.parametrize("solver", ["mg", "jacobi"])
+def test_irregular_delaunay_mesh_parity(solver):
+    """Badly conditioned on purpose (sliver triangles: cotan weights from 5e-11 to 3e3). The multigrid solver's default
+    stopping rule is a position-error estimate precisely because a residual tolerance tuned on regular meshes left this
+    mesh 4e-5 x bbox diagonal away from the direct solve (profiles/r01_h_stopping_rule.txt)."""
+    P, F = delaunay_patch(6000, 21)
+    val = np.bincount(F.ravel(), minlength=len(P))
+    assert val.min() <= 4 and val.max() >= 10                      # really irregular
+    rng = np.random.default_rng(4)
+    idx = rng.choice(len(P), 60, replace=False).astype(np.int32)
+    tgt = P[idx] + 0.05 * rng.standard_normal((60, 3))
+    mesh, omesh = P.copy(), P.copy()
+    a, o = ARAP(mesh, F, np.float64, solver=SOLVERS[solver]), O.ArapOracle(omesh, F, np.float64)
+    a.setConstraints(idx, tgt)
+    constrain(o, idx, tgt)
+    assert a.deform(4) and o.deform(4)
+    rp, ci, w = a.cotanWeights()
+    orp, oci, ow = o.cotanWeights()
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(w, ow)
+    assert w.max() / w.min() > 1e12
+    err = np.abs(mesh - omesh).max() / bbox_diag(P)
+    de = abs(a.energy() - o.energy()) / o.energy()
+    print("delaunay", solver, "err/diag", err, "rel dE", de)
+    assert err <= POS_TOL and de <= E_TOL
+    # PrecisionType float on the same mesh: the weights are still bit-exact, but a float LDL^T on this system (the float
+    # oracle) is itself ~2e-2 x diag away from the double solution -- the engine, which solves in fp64 whatever the
+    # PrecisionType, must be at least as close to the double solution as the float reference is.
+    fmesh, fomesh = P.astype(np.float32), P.astype(np.float32)
+    fa, fo = ARAP(fmesh, F, np.float32, solver=SOLVERS[solver]), O.ArapOracle(fomesh, F, np.float32)
+    fa.setConstraints(idx, tgt)
+    constrain(fo, idx, tgt)
+    assert fa.deform(4) and fo.deform(4)
+    frp, fci, fw = fa.cotanWeights()
+    forp, foci, fow = fo.cotanWeights()
+    assert np.array_equal(frp, forp) and np.array_equal(fci, foci) and np.array_equal(fw, fow)
+    err_engine = np.abs(fmesh.astype(np.float64) - omesh).max() / bbox_diag(P)
+    err_reference = np.abs(fomesh.astype(np.float64) - omesh).max() / bbox_diag(P)
+    print("delaunay float: engine vs double", err_engine, "float oracle vs double", err_reference)
+    assert np.isfinite(fmesh).all() and err_engine <= max(err_reference, 1e-3) * 1.05
+
+
+def test_nonmanifold_duplicate_faces_and_two_components():
+    """setFromTriplets semantics on awkward input (arap.h:220-238): an edge shared by three faces, a face listed twice and
+    a face with reversed winding all just add their half-cotans; two components, each with its own constraints."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [0.5, 1, 0], [0.5, -1, 0.2], [0.5, 0.3, 1.0], [1.5, 1, 0.1],     # fan around edge 0-1
+                  [5, 0, 0], [6, 0, 0], [5, 1, 0], [6, 1, 0.3]], np.float64)                                  # second component
+    F = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4], [1, 5, 2], [1, 5, 2], [2, 5, 1], [6, 7, 8], [7, 9, 8]], np.int32)
+    idx = np.array([0, 3, 6, 9], np.int32)
+    tgt = P[idx] + np.array([[0, 0, 0], [0, 0, 0.3], [0, 0, 0], [0.2, 0, 0.2]])
+    for prec in (np.float64, np.float32):
+        mesh, omesh = P.astype(prec), P.astype(prec)
+        a, o = ARAP(mesh, F, prec), O.ArapOracle(omesh, F, prec)
+        a.setConstraints(idx, tgt)
+        constrain(o, idx, tgt)
+        assert a.deform(6) and o.deform(6)
+        rp, ci, w = a.cotanWeights()
+        orp, oci, ow = o.cotanWeights()
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(w, ow)
+        tol = POS_TOL if prec == np.float64 else 300 * POS_TOL
+        assert np.abs(mesh.astype(np.float64) - omesh.astype(np.float64)).max() <= tol * bbox_diag(P)
+
+
+def test_full_size_equivariance_and_energy_descent():
+    """Properties that need no oracle, at the headline size (998,562 vertices): (1) the ARAP energy never increases from
+    one iteration to the next; (2) moving the whole problem -- rest pose and targets -- by a rigid motion moves the result by
+    the same rigid motion (cotan weights, covariances and the linear system are all invariant)."""
+    P, F = G.icosphere(316)
+    idx, tgt = G.cap_constraints(P)
+    a = ARAP(P.copy(), F, np.float64, cg_tolerance=1e-9)
+    a.setConstraints(idx, tgt)
+    energies = []
+    for _ in range(6):
+        assert a.deform(1)
+        energies.append(a.energy())
+    assert all(e1 <= e0 * (1 + 1e-9) for e0, e1 in zip(energies, energies[1:])), energies
+    Rm = G.rot_x(0.7) @ G.rot_z(-1.1)
+    t = np.array([0.3, -2.0, 1.5])
+    b = ARAP(np.ascontiguousarray(P @ Rm.T + t), F, np.float64, cg_tolerance=1e-9)
+    b.setConstraints(idx, tgt @ Rm.T + t)
+    assert b.deform(6)
+    err = np.abs(b.mesh - (a.mesh @ Rm.T + t)).max() / bbox_diag(P)
+    print("full-size equivariance err/diag", err, "energies", energies[0], energies[-1], "dE", abs(b.energy() - a.energy()) / a.energy())
+    assert err <= 1e-7 and abs(b.energy() - a.energy()) <= 1e-7 * a.energy()
+
+
 def test_midsize_grid_parity_mg():
     """Config 5's construction (plane.obj topology up-scaled, 2+2 constraint columns) at 200 x 200:
     every quad diagonal carries the 1e-10 clamp weight and iteration-1 covariances are rank 2."""
