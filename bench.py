@@ -256,6 +256,56 @@ def batch_arm(args):
     return 0
 
 
+def partitioned_arm(args):
+    """--workload partitioned_grid: BASELINE.json configs[4] -- ONE nx x nx grid mesh (plane.obj topology, 2+2 constraint
+    columns) partitioned into strips over the ranks: halo exchange of p', R and the CG direction, all-reduced CG scalars, one
+    global multigrid hierarchy with its rows spread over the ranks. Strong scaling: the mesh is fixed,
+    value = ARAP iterations/s of the whole mesh. Informational: the headline line is the icosphere workload."""
+    rank, world, local_rank, dist = dist_setup(args.gpus)
+    import torch
+    torch.cuda.set_device(local_rank)
+    from mesh_deform_b200 import capi, meshgen as G, partition as PT
+    nx = args.nx
+    P, F = G.grid_plane(nx, nx)
+    idx, tgt = G.grid_constraints(nx, nx, P)
+    owner = PT.strip_owner(P, world)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if world > 1:
+        if rank == 0:
+            uid.copy_(torch.from_numpy(capi.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        kind = capi.TRANSPORT_PEER if args.transport == "peer" else capi.TRANSPORT_NCCL
+        ident = uid.cpu().numpy()
+    else:
+        kind, ident = capi.TRANSPORT_IN_PROCESS, 7      # a single partition: same code path, no peer
+    part = capi.PartitionedDeformation(P, F, owner, rank, world, kind, ident, np.float64, device=local_rank)
+    part.setConstraints(idx, tgt)
+    t0 = time.perf_counter()
+    part.prepare()
+    prepare_ms = 1e3 * (time.perf_counter() - t0)
+    part.iterate(args.warmup)
+    barrier_and_sync(dist)
+    part.arap.timer_start()
+    part.iterate(args.steps)
+    ms = part.arap.timer_stop()
+    barrier_and_sync(dist)
+    ms = max_over_ranks(dist, local_rank, ms)
+    stats = part.solver_stats()
+    if rank != 0:
+        return 0
+    line = {"metric": "arap_iterations_per_sec_partitioned_grid", "value": args.steps / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"one {nx} x {nx} grid mesh ({nx * nx} vertices) in {world} strips (BASELINE.json configs[4])",
+                       "transport": args.transport if world > 1 else "none", "halo_vertices_rank0": int(part.part.n_local - part.part.n_owned),
+                       "preconditioner": "global multigrid hierarchy, rows partitioned" if stats["mg_global"] else "per-rank multigrid",
+                       "mg_levels": stats["mg_levels"], "cg_graph": bool(stats["cg_graph"])},
+            "cg_iterations_per_step": stats["cg_iterations_total"] / max(1, stats["global_steps"]),
+            "prepare_ms": prepare_ms, "hierarchy_setup_host_ms": stats["setup_host_ms"]}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,8 +319,10 @@ def main():
     ap.add_argument("--cg-tol", type=float, default=0.0)
     ap.add_argument("--pos-tol", type=float, default=0.0, help="position_tolerance of the multigrid solver (0 = engine default)")
     ap.add_argument("--solver", default="auto", choices=["auto", "jacobi", "mg"])
-    ap.add_argument("--workload", default="icosphere", choices=["icosphere", "batch_spheres"])
+    ap.add_argument("--workload", default="icosphere", choices=["icosphere", "batch_spheres", "partitioned_grid"])
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--nx", type=int, default=4000, help="partitioned_grid: the grid is nx x nx vertices (4000 -> 16M, BASELINE.json configs[4])")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"], help="partitioned_grid: halo exchange transport")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -278,6 +330,8 @@ def main():
         return reference_arm(args)
     if args.workload == "batch_spheres":
         return batch_arm(args)
+    if args.workload == "partitioned_grid":
+        return partitioned_arm(args)
 
     rank, world, local_rank, dist = dist_setup(args.gpus)
     import torch  # plumbing only: device selection, barrier, max-over-ranks

@@ -298,6 +298,7 @@ public:
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
     // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
+    double length_scale = 0;                       // bbox diagonal of the first rest pose (position-error stopping rule)
     MgTailArgs tail_args;
     int tail_first = 0;                            // 0 = no tail kernel
     int tail_cluster = 8;
@@ -586,8 +587,10 @@ public:
         if (use_mg && (opt.position_tolerance > 0 || !(opt.cg_tolerance > 0))) {
             const double ptol = opt.position_tolerance > 0 ? opt.position_tolerance : kDefaultPositionTolerance;
             init.z8_tol = std::pow(ptol, 8.0);
-            const double len = rest_bbox_diagonal(rest_host, scalar_bytes);
-            init.inv_len2 = len > 0 ? 1.0 / (len * len) : 1.0;
+            // a length SCALE: measured on the first prepare of the handle and kept (later rest poses are deformed states of
+            // the same mesh; walking 3V host values again would cost the per-frame dirty cycle milliseconds at 1M vertices)
+            if (!(length_scale > 0)) length_scale = rest_bbox_diagonal(rest_host, scalar_bytes);
+            init.inv_len2 = length_scale > 0 ? 1.0 / (length_scale * length_scale) : 1.0;
         }
         init.distributed = transport ? 1 : 0;
         cg_host[0] = init;
@@ -810,6 +813,7 @@ public:
             m.constrained[(size_t)g->constrained[k]] = 1;
         }
         have_global = true;
+        length_scale = 0;              // re-measure on the global box
         dirty = true;
         return ARAP_OK;
     }
