@@ -880,6 +880,18 @@ public:
         return ARAP_OK;
     }
 
+    // Coarsening stops at the first level with at most 2048 rows (ARAP_MG_COARSE_ROWS): up to 256 rows are inverted on the
+    // host, larger ones on the device. A 1234-row coarsest level instead of 1234 -> 125 saves four launches per V-cycle.
+    static MgSetupOptions engine_mg_options() {
+        MgSetupOptions mo;
+        const char *env = getenv("ARAP_MG_COARSE_ROWS");
+        mo.coarse_size = env ? atoi(env) : 2048;
+        if (mo.coarse_size > mo.max_dense) mo.coarse_size = mo.max_dense;
+        if (mo.coarse_size < 16) mo.coarse_size = 16;
+        mo.host_dense_max = 256;
+        return mo;
+    }
+
     // ---- multigrid setup: host analysis of L (the reference's _solver.compute(_L), arap.h:337) ------------
     int setup_multigrid() {
         const int V = n_vertices;
@@ -902,7 +914,7 @@ public:
         for (int v = 0; v < V; ++v) h_con[(size_t)v] = h_con_user[(size_t)h_perm[(size_t)v]];
         for (int v = n_rows; v < V; ++v) h_con[(size_t)v] = 1;      // partitioned mode: block-Jacobi across ranks, halo = Dirichlet
         MgHierarchyHost H;
-        MgSetupOptions mo;
+        MgSetupOptions mo = engine_mg_options();
         mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H,
                               (int)mg_visit_order.size() == V ? mg_visit_order.data() : nullptr);
         mg.clear();
@@ -938,11 +950,54 @@ public:
         }
         mg_dense = !H.coarse_inv.empty();
         if (mg_dense) ARAP_CUDA(upload_as_float(mg_coarse_inv, H.coarse_inv, stream, fscratch));
+        else if (H.coarse_dense_on_device) { int rc = invert_coarsest_on_device(H.levels.back().A); if (rc) return rc; }
         ARAP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
         { int rc = plan_tail(); if (rc) return rc; }
         stats.mg_levels = (int)mg.size();
         stats.mg_operator_complexity = H.operator_complexity;
         stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return ARAP_OK;
+    }
+
+    // Dense fp32 inverse of the coarsest operator A (host CSR) into mg_coarse_inv, inverted on the device (mg_kernels.cuh).
+    // Sets mg_dense; on a bad pivot the level simply stays a smoothing level (mg_dense = false).
+    int invert_coarsest_on_device(const HostCsr &A) {
+        const int n = A.n_rows;
+        mg_dense = false;
+        if (n <= 0) return ARAP_OK;
+        const auto t0 = std::chrono::steady_clock::now();
+        DeviceBuffer<int> d_rowptr, d_colidx, d_bad;
+        DeviceBuffer<double> d_val, d_M, d_col;
+        ARAP_CUDA(upload_vector(d_rowptr, A.rowptr, stream));
+        ARAP_CUDA(upload_vector(d_colidx, A.colidx, stream));
+        ARAP_CUDA(upload_vector(d_val, A.val, stream));
+        ARAP_CUDA(d_M.ensure((size_t)n * n));
+        ARAP_CUDA(d_col.ensure((size_t)n));
+        ARAP_CUDA(d_bad.ensure(1));
+        ARAP_CUDA(cudaMemsetAsync(d_M.ptr, 0, sizeof(double) * (size_t)n * n, stream));
+        ARAP_CUDA(cudaMemsetAsync(d_bad.ptr, 0, sizeof(int), stream));
+        double trace = 0;
+        for (int i = 0; i < n; ++i)
+            for (int k = A.rowptr[(size_t)i]; k < A.rowptr[(size_t)i + 1]; ++k) if (A.colidx[(size_t)k] == i) trace += A.val[(size_t)k];
+        const double shift = 1e-13 * trace / n;             // keeps a pure-Neumann component invertible (as mg_setup.cpp does)
+        begin_launch(ARAP_K_MISC);
+        dense_from_csr_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, d_rowptr.ptr, d_colidx.ptr, d_val.ptr, shift, d_M.ptr);
+        const dim3 ugrid((unsigned)grid_for((size_t)n), (unsigned)n, 1);
+        for (int c = 0; c < n; ++c) {
+            gj_pivot_kernel<<<1, 1024, 0, stream>>>(n, c, d_M.ptr, d_col.ptr, d_bad.ptr);
+            gj_update_kernel<<<ugrid, kBlock, 0, stream>>>(n, c, d_M.ptr, d_col.ptr);
+        }
+        ARAP_CUDA(mg_coarse_inv.ensure((size_t)n * n));
+        dense_to_float_kernel<<<grid_for((size_t)n * n), kBlock, 0, stream>>>((size_t)n * n, d_M.ptr, mg_coarse_inv.ptr);
+        end_launch();
+        int bad = 0;
+        ARAP_CUDA(cudaMemcpyAsync(&bad, d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        mg_dense = (bad == 0);
+        if (getenv("ARAP_MG_TIMING"))
+            std::fprintf(stderr, "[mg setup] dense inverse of %d rows on the device %7.1f ms%s\n", n,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), bad ? " (bad pivot)" : "");
         return ARAP_OK;
     }
 
@@ -959,11 +1014,11 @@ public:
             std::vector<double> g_w;
             build_global_csr(gm.n_vertices, gm.n_faces, gm.faces.data(), gm.rest.data(), g_rowptr, g_colidx, g_w);
             morton_sequence(gm.n_vertices, gm.rest.data(), visit);
-            MgSetupOptions mo;
+            MgSetupOptions mo = engine_mg_options();
             mg_build_hierarchy<double>(gm.n_vertices, g_rowptr.data(), g_colidx.data(), g_w.data(), gm.constrained.data(), mo, H,
                                        visit.data(), gm.owner.data());
         }
-        if (H.levels.size() < 2 || H.coarse_inv.empty()) return ARAP_OK;
+        if (H.levels.size() < 2 || (H.coarse_inv.empty() && !H.coarse_dense_on_device)) return ARAP_OK;
         const int V = n_vertices;
         std::vector<int> h_perm((size_t)V), global_of_local((size_t)V);
         if (V > 0) ARAP_CUDA(cudaMemcpyAsync(h_perm.data(), perm.ptr, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, stream));
@@ -1017,7 +1072,13 @@ public:
         }
         ARAP_CUDA(mg_sendbuf.ensure(max_send * sizeof(MgVec)));
         mg_dense = true;
-        ARAP_CUDA(upload_as_float(mg_coarse_inv, LH.coarse_inv, stream, fscratch));
+        if (LH.coarse_dense_on_device) {
+            int rc = invert_coarsest_on_device(LH.coarse_A);
+            if (rc) return rc;
+            if (!mg_dense) return fail(ARAP_ERR_SOLVER, "global multigrid: the coarsest operator could not be inverted");
+        } else {
+            ARAP_CUDA(upload_as_float(mg_coarse_inv, LH.coarse_inv, stream, fscratch));
+        }
         ARAP_CUDA(cudaStreamSynchronize(stream));
         stats.mg_levels = (int)mg.size();
         stats.mg_operator_complexity = LH.operator_complexity;

@@ -367,6 +367,53 @@ __global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const MgTailAr
     prolong_add(args.lv[0], args.lv[1]);
 }
 
+// ---- dense inverse of the coarsest operator on the device (setup, once per hierarchy) ---------------------------------
+// The host inverts coarsest levels of up to a few hundred rows; with up to 2048 rows the hierarchy is one or two levels
+// shorter (4-8 launches less per V-cycle), but O(n^3) scalar host code would take seconds. In-place Gauss-Jordan without
+// pivoting in fp64 (the operator is SPD after the same tiny diagonal shift the host code applies): two launches per pivot.
+__global__ void __launch_bounds__(kBlock) dense_from_csr_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                const double *__restrict__ val, double shift, double *__restrict__ M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double diag = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        M[(size_t)i * n + colidx[k]] += val[k];
+        if (colidx[k] == i) diag += val[k];
+    }
+    if (diag == 0.0) M[(size_t)i * n + i] = 1.0;            // empty row: identity
+    else M[(size_t)i * n + i] += shift;
+}
+// pivot c, part 1 (one CTA): save column c, scale row c by 1/pivot, put 1/pivot on the diagonal
+__global__ void __launch_bounds__(1024) gj_pivot_kernel(int n, int c, double *__restrict__ M, double *__restrict__ colbuf, int *__restrict__ bad) {
+    __shared__ double dinv;
+    if (threadIdx.x == 0) {
+        const double p = M[(size_t)c * n + c];
+        if (!(p > 0.0) || !(p < 1e300)) { *bad = 1; dinv = 0.0; }
+        else dinv = 1.0 / p;
+    }
+    __syncthreads();
+    const double d = dinv;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        colbuf[k] = M[(size_t)k * n + c];
+        const double v = M[(size_t)c * n + k];
+        M[(size_t)c * n + k] = (k == c) ? d : v * d;
+    }
+}
+// pivot c, part 2: every other row r: M[r][k] -= f M[c][k] (k != c), M[r][c] = -f / pivot, f = the saved M[r][c]
+__global__ void __launch_bounds__(kBlock) gj_update_kernel(int n, int c, double *__restrict__ M, const double *__restrict__ colbuf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (k >= n || r == c) return;
+    const double f = colbuf[r];
+    if (f == 0.0) return;
+    const double rc = M[(size_t)c * n + k];                 // row c is already scaled; its entry at k == c is 1/pivot
+    M[(size_t)r * n + k] = (k == c) ? -f * rc : M[(size_t)r * n + k] - f * rc;
+}
+__global__ void __launch_bounds__(kBlock) dense_to_float_kernel(size_t n2, const double *__restrict__ in, float *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) out[i] = (float)in[i];
+}
+
 // single-level hierarchies (tiny meshes): the V-cycle input/output live in fp64 CG vectors
 __global__ void __launch_bounds__(kBlock) mg_to_float_kernel(int n, const Vec3d *__restrict__ in, MgVec *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

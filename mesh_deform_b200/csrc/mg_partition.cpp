@@ -109,13 +109,15 @@ bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_
                         MgLocalHierarchy &out, std::string &error) {
     const int L = (int)H.levels.size();
     if (L < 2) { error = "global multigrid: the hierarchy has a single level"; return false; }
-    if (H.coarse_inv.empty()) { error = "global multigrid: no dense coarsest level"; return false; }
+    if (H.coarse_inv.empty() && !H.coarse_dense_on_device) { error = "global multigrid: no dense coarsest level"; return false; }
     for (int l = 0; l < L; ++l)
         if ((int)H.levels[(size_t)l].block.size() != H.levels[(size_t)l].A.n_rows) { error = "global multigrid: hierarchy was built without blocks"; return false; }
     out = MgLocalHierarchy();
     out.levels.resize((size_t)L);
     out.n_coarse = H.n_coarse;
     out.coarse_inv = H.coarse_inv;
+    out.coarse_dense_on_device = H.coarse_dense_on_device;
+    if (H.coarse_dense_on_device) out.coarse_A = H.levels.back().A;
     out.operator_complexity = H.operator_complexity;
 
     std::vector<std::vector<int>> g2l((size_t)L), own((size_t)L);

@@ -42,7 +42,9 @@ struct MgLocalLevel {
 struct MgLocalHierarchy {
     std::vector<MgLocalLevel> levels;   // the last one is the coarsest: replicated on every rank, global numbering
     int n_coarse = 0;
-    std::vector<double> coarse_inv;     // dense inverse of the coarsest operator
+    std::vector<double> coarse_inv;     // dense inverse of the coarsest operator, or empty when ...
+    bool coarse_dense_on_device = false;   // ... the engine is to invert coarse_A on the device (see MgHierarchyHost)
+    HostCsr coarse_A;
     double operator_complexity = 0;
 };
 

@@ -380,8 +380,11 @@ void mg_build_hierarchy(int V, const int *rowptr, const int *colidx, const S *we
         // coarsest level: keep A in a final pseudo-level without P
         lvl.omega = 4.0 / (3.0 * estimate_rho(lvl.A, lvl.inv_diag));
         out.n_coarse = lvl.A.n_rows;
-        if (lvl.A.n_rows <= opt.max_dense) {
+        out.coarse_dense_on_device = false;
+        if (lvl.A.n_rows <= opt.host_dense_max && lvl.A.n_rows <= opt.max_dense) {
             if (!dense_inverse(lvl.A, out.coarse_inv)) out.coarse_inv.clear();
+        } else if (lvl.A.n_rows <= opt.max_dense) {
+            out.coarse_dense_on_device = true;
         }
         timer.lap("dense inverse", (int)out.levels.size());
         out.levels.push_back(std::move(lvl));

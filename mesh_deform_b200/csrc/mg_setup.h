@@ -35,7 +35,9 @@ struct MgLevelHost {
 struct MgHierarchyHost {
     std::vector<MgLevelHost> levels; // levels[l] for l = 0 .. L-1 (each has a P to the next level)
     int n_coarse = 0;                // size of the coarsest level
-    std::vector<double> coarse_inv;  // dense n_coarse x n_coarse inverse (row-major)
+    std::vector<double> coarse_inv;  // dense n_coarse x n_coarse inverse (row-major); empty if not computed here
+    bool coarse_dense_on_device = false;   // the coarsest level is small enough for a dense inverse, but too large to invert on
+                                           // the host in reasonable time: the engine inverts levels.back().A on the device
     double operator_complexity = 0;
 };
 
@@ -44,6 +46,7 @@ struct MgSetupOptions {
     int coarse_size = 256;
     int max_levels = 12;
     int max_dense = 2048;
+    int host_dense_max = 2048;       // largest coarsest level inverted on the host (O(n^3) scalar code: 256 rows = 10 ms, 1234 = seconds)
 };
 
 // w may be float or double (the handle precision); it is widened to double.
