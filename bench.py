@@ -448,7 +448,7 @@ def main():
         kernels[name] = entry
     dominant = max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["share"])
     # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
-    ncu_path = os.path.join(ROOT, "profiles", "r01_g_ncu_summary.json")
+    ncu_path = os.path.join(ROOT, "profiles", "r01_h_ncu_summary.json")
     ncu = json.load(open(ncu_path)) if os.path.exists(ncu_path) and args.nu == 316 and args.precision == "f64" else {}
     for name, entry in kernels.items():
         if name in ncu and "traffic_bytes" in ncu[name]:
@@ -456,7 +456,7 @@ def main():
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak_gbs,
                 "unit": "GB/s", "frac": kernels[dominant]["frac_of_peak"],
                 "traffic": kernels[dominant].get("ncu_dram_traffic_bytes"), "algorithmic_bytes": kernels[dominant]["algorithmic_bytes"],
-                "traffic_source": "profiles/r01_g_ncu_summary.json (ncu --set full, dram__bytes_read+write per launch)" if ncu else None,
+                "traffic_source": "profiles/r01_h_ncu_summary.json (ncu --set full, dram__bytes_read+write per launch)" if ncu else None,
                 "peak_source": peak_src,
                 "share_of_step": kernels[dominant]["share"], "avg_launch_us": kernels[dominant]["avg_us"]}
     local = kernels.get("local_step", {})

@@ -271,7 +271,8 @@ public:
     DeviceBuffer<unsigned char> staging;           // uploads / downloads in a foreign scalar type
 
     std::vector<std::unique_ptr<MgLevelDev>> mg;   // multigrid hierarchy (empty -> Jacobi preconditioner)
-    DeviceBuffer<float> mg_coarse_inv;
+    DeviceBuffer<float> mg_coarse_inv;             // dense inverse of the coarsest operator, rows padded to mg_coarse_ld floats
+    int mg_coarse_ld = 0;
     bool mg_dense = false;
     bool use_mg = false;
     std::vector<unsigned char> mg_mask;            // constrained(+halo) mask the hierarchy was built for
@@ -949,13 +950,25 @@ public:
             mg.push_back(std::move(d));
         }
         mg_dense = !H.coarse_inv.empty();
-        if (mg_dense) ARAP_CUDA(upload_as_float(mg_coarse_inv, H.coarse_inv, stream, fscratch));
+        if (mg_dense) { int rc = upload_coarse_inverse(H.coarse_inv, H.n_coarse); if (rc) return rc; }
         else if (H.coarse_dense_on_device) { int rc = invert_coarsest_on_device(H.levels.back().A); if (rc) return rc; }
         ARAP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
         { int rc = plan_tail(); if (rc) return rc; }
         stats.mg_levels = (int)mg.size();
         stats.mg_operator_complexity = H.operator_complexity;
         stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return ARAP_OK;
+    }
+
+    // the host-computed dense inverse (n x n doubles) -> mg_coarse_inv (floats, rows padded to a multiple of 4)
+    int upload_coarse_inverse(const std::vector<double> &inv, int n) {
+        mg_coarse_ld = (n + 3) & ~3;
+        std::vector<float> padded((size_t)n * mg_coarse_ld, 0.f);
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c) padded[(size_t)r * mg_coarse_ld + c] = (float)inv[(size_t)r * n + c];
+        ARAP_CUDA(mg_coarse_inv.ensure(padded.size()));
+        ARAP_CUDA(cudaMemcpyAsync(mg_coarse_inv.ptr, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
         return ARAP_OK;
     }
 
@@ -987,8 +1000,9 @@ public:
             gj_pivot_kernel<<<1, 1024, 0, stream>>>(n, c, d_M.ptr, d_col.ptr, d_bad.ptr);
             gj_update_kernel<<<ugrid, kBlock, 0, stream>>>(n, c, d_M.ptr, d_col.ptr);
         }
-        ARAP_CUDA(mg_coarse_inv.ensure((size_t)n * n));
-        dense_to_float_kernel<<<grid_for((size_t)n * n), kBlock, 0, stream>>>((size_t)n * n, d_M.ptr, mg_coarse_inv.ptr);
+        mg_coarse_ld = (n + 3) & ~3;
+        ARAP_CUDA(mg_coarse_inv.ensure((size_t)n * mg_coarse_ld));
+        dense_to_float_kernel<<<grid_for((size_t)n * mg_coarse_ld), kBlock, 0, stream>>>(n, mg_coarse_ld, d_M.ptr, mg_coarse_inv.ptr);
         end_launch();
         int bad = 0;
         ARAP_CUDA(cudaMemcpyAsync(&bad, d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1077,7 +1091,8 @@ public:
             if (rc) return rc;
             if (!mg_dense) return fail(ARAP_ERR_SOLVER, "global multigrid: the coarsest operator could not be inverted");
         } else {
-            ARAP_CUDA(upload_as_float(mg_coarse_inv, LH.coarse_inv, stream, fscratch));
+            int rc = upload_coarse_inverse(LH.coarse_inv, LH.n_coarse);
+            if (rc) return rc;
         }
         ARAP_CUDA(cudaStreamSynchronize(stream));
         stats.mg_levels = (int)mg.size();
@@ -1113,8 +1128,7 @@ public:
         // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
         MgLevelDev &cl = *mg[L - 1];
         if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
-        LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
-               cl.b.ptr, cl.x2.ptr, cg.ptr);
+        launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
@@ -1156,6 +1170,7 @@ public:
         tail_args.n_levels = L - t + 1;
         tail_args.dense = mg_dense ? 1 : 0;
         tail_args.coarse_inv = mg_coarse_inv.ptr;
+        tail_args.coarse_ld = mg_coarse_ld;
         for (int l = t - 1; l < L; ++l) {
             MgLevelDev &d = *mg[(size_t)l];
             MgTailLevel &a = tail_args.lv[l - (t - 1)];
@@ -1190,6 +1205,13 @@ public:
         return ARAP_OK;
     }
 
+    void launch_dense_solve(int n, const MgVec *b, MgVec *x) {
+        begin_launch(ARAP_K_MG_DENSE_SOLVE);
+        mg_dense_solve_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kBlock, sizeof(MgVec) * (size_t)mg_coarse_ld, stream>>>(
+            n, mg_coarse_ld, mg_coarse_inv.ptr, b, x, cg.ptr);
+        end_launch();
+    }
+
     // z = M^-1 r by one V(1,1) cycle; the last kernel also produces rho = r.z and beta.
     // Buffer roles are fixed (no pointer swapping) so that the launch sequence can be captured in a CUDA graph:
     // on every level x = iterate before post-smoothing, x2 = the level's result; level 0's result is z = mg[0]->x2.
@@ -1203,8 +1225,7 @@ public:
             // tiny meshes: the whole system is the "coarsest level"; b = the fp64 CG residual converted to fp32
             LAUNCH(ARAP_K_MISC, mg_to_float_kernel, grid_for((size_t)m0.n), m0.n, cg_r.ptr, m0.x.ptr);
             if (mg_dense) {
-                LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (m0.n + kWarpsPerBlock - 1) / kWarpsPerBlock, m0.n, mg_coarse_inv.ptr,
-                       m0.x.ptr, z, cg.ptr);
+                launch_dense_solve(m0.n, m0.x.ptr, z);
             } else {      // no dense inverse (singular coarse operator): plain Jacobi, z = omega D^-1 r
                 LAUNCH(ARAP_K_MISC, mg_jacobi_kernel, grid_for((size_t)m0.n), m0.n, m0.inv_diag.ptr, (float)m0.omega, m0.x.ptr, z);
             }
@@ -1234,8 +1255,7 @@ public:
             int rc = launch_tail();
             if (rc) return rc;
         } else if (mg_dense) {
-            LAUNCH(ARAP_K_MG_DENSE_SOLVE, mg_dense_solve_kernel, (cl.n + kWarpsPerBlock - 1) / kWarpsPerBlock, cl.n, mg_coarse_inv.ptr,
-                   cl.b.ptr, cl.x2.ptr, cg.ptr);
+            launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
         } else {
             ARAP_DISPATCH_LANES(cl.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)cl.n * LN), cl.n,
                                                    cl.a_rowptr.ptr, cl.a_colidx.ptr, cl.a_val.ptr, cl.inv_diag.ptr, (float)cl.omega, cl.b.ptr,
