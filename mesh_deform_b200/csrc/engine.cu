@@ -100,6 +100,9 @@ public:
     virtual int energy(double *e) = 0;
     virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
     virtual int set_global_mesh(const arap_global_mesh *g) = 0;
+    // arap_batch_*: the mesh is `members` disjoint copies of a `member_vertices`-vertex mesh, member-major
+    void set_batch_layout(int members, int member_vertices_) { batch_members = members; member_vertices = member_vertices_; }
+    int batch_members = 1, member_vertices = 0;
 
     int fail(int code, const std::string &msg) {
         last_error = msg;
@@ -299,6 +302,7 @@ public:
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
     // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
+    bool mg_batch_dense = false;                   // batches: one member's dense inverse is the whole preconditioner (mg_batch_dense_kernel)
     double length_scale = 0;                       // bbox diagonal of the first rest pose (position-error stopping rule)
     MgTailArgs tail_args;
     int tail_first = 0;                            // 0 = no tail kernel
@@ -647,7 +651,7 @@ public:
         std::vector<int> h_perm((size_t)V);
         for (int i = 0; i < V; ++i) h_perm[(size_t)i] = i;
         const char *env = getenv("ARAP_REORDER");
-        if (!(env && atoi(env) == 0) && owned > 1) {
+        if (!(env && atoi(env) == 0) && owned > 1 && batch_members <= 1) {     // batches keep their member-major order
             auto coord = [&](int v, int d) -> double {
                 return scalar_bytes == 4 ? (double)((const float *)rest_host)[3 * (size_t)v + d] : ((const double *)rest_host)[3 * (size_t)v + d];
             };
@@ -894,6 +898,42 @@ public:
     }
 
     // ---- multigrid setup: host analysis of L (the reference's _solver.compute(_L), arap.h:337) ------------
+    // Batches of small meshes: every member has the same operator, so the preconditioner is member 0's dense inverse applied to
+    // all members (mg_kernels.cuh, mg_batch_dense_kernel). Returns with mg_batch_dense == false if that is not possible.
+    int setup_batch_dense(const std::vector<int> &h_rowptr, const std::vector<int> &h_colidx, const std::vector<S> &h_w,
+                          const std::vector<unsigned char> &h_con) {
+        mg_batch_dense = false;
+        const int Vm = member_vertices;
+        if (batch_members <= 1 || transport || Vm <= 0 || Vm > 2048 || (long long)Vm * batch_members != n_vertices) return ARAP_OK;
+        if (getenv("ARAP_BATCH_DENSE") && atoi(getenv("ARAP_BATCH_DENSE")) == 0) return ARAP_OK;
+        const int e = h_rowptr[(size_t)Vm];
+        for (int k = 0; k < e; ++k) if (h_colidx[(size_t)k] >= Vm) return ARAP_OK;            // not block diagonal after all
+        MgHierarchyHost H;
+        MgSetupOptions mo = engine_mg_options();
+        mo.coarse_size = std::max(mo.coarse_size, Vm);
+        mg_build_hierarchy<S>(Vm, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H, nullptr);
+        if (H.levels.size() != 1) return ARAP_OK;
+        if (!H.coarse_inv.empty()) { int rc = upload_coarse_inverse(H.coarse_inv, H.n_coarse); if (rc) return rc; mg_dense = true; }
+        else if (H.coarse_dense_on_device) { int rc = invert_coarsest_on_device(H.levels.back().A); if (rc) return rc; }
+        else return ARAP_OK;
+        if (!mg_dense) return ARAP_OK;
+        mg.clear();
+        std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+        d->n = n_vertices;
+        d->omega = H.levels[0].omega;
+        ARAP_CUDA(d->x.ensure((size_t)n_vertices));
+        ARAP_CUDA(d->x2.ensure((size_t)n_vertices));
+        ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
+        ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
+        mg.push_back(std::move(d));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        tail_first = 0;
+        stats.mg_levels = 1;
+        stats.mg_operator_complexity = 1.0;
+        mg_batch_dense = true;
+        return ARAP_OK;
+    }
+
     int setup_multigrid() {
         const int V = n_vertices;
         auto t0 = std::chrono::steady_clock::now();
@@ -914,6 +954,11 @@ public:
         ARAP_CUDA(cudaStreamSynchronize(stream));
         for (int v = 0; v < V; ++v) h_con[(size_t)v] = h_con_user[(size_t)h_perm[(size_t)v]];
         for (int v = n_rows; v < V; ++v) h_con[(size_t)v] = 1;      // partitioned mode: block-Jacobi across ranks, halo = Dirichlet
+        { int rc = setup_batch_dense(h_rowptr, h_colidx, h_w, h_con); if (rc) return rc; }
+        if (mg_batch_dense) {
+            stats.setup_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            return ARAP_OK;
+        }
         MgHierarchyHost H;
         MgSetupOptions mo = engine_mg_options();
         mg_build_hierarchy<S>(V, h_rowptr.data(), h_colidx.data(), h_w.data(), h_con.data(), mo, H,
@@ -1223,6 +1268,14 @@ public:
         MgVec *z = m0.x2.ptr;
         if (L == 1) {
             // tiny meshes: the whole system is the "coarsest level"; b = the fp64 CG residual converted to fp32
+            if (mg_batch_dense) {       // Z = Inv . R over all members at once, straight from the fp64 residual
+                const dim3 grid((unsigned)((member_vertices + kBgM - 1) / kBgM), (unsigned)((batch_members + kBgMembers - 1) / kBgMembers), 1);
+                begin_launch(ARAP_K_MG_DENSE_SOLVE);
+                mg_batch_dense_kernel<<<grid, 256, 0, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_coarse_inv.ptr, cg_r.ptr, z, cg.ptr);
+                end_launch();
+                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                return reduce_stage(CG_STAGE_RHO, 4);
+            }
             LAUNCH(ARAP_K_MISC, mg_to_float_kernel, grid_for((size_t)m0.n), m0.n, cg_r.ptr, m0.x.ptr);
             if (mg_dense) {
                 launch_dense_solve(m0.n, m0.x.ptr, z);
@@ -1699,6 +1752,7 @@ int arap_batch_create(const int32_t *faces, int32_t n_faces, int32_t n_vertices,
     if (rc != ARAP_OK) return rc;
     arap_batch *bt = new (std::nothrow) arap_batch;
     if (!bt) { arap_destroy(h); return ARAP_ERR_ALLOC; }
+    h->engine->set_batch_layout(batch_size, n_vertices);
     bt->handle = h;
     bt->n_vertices = n_vertices;
     bt->n_faces = n_faces;

@@ -231,6 +231,86 @@ __global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, int ld, c
     if (lane == 0) x[row] = MgVec{s0, s1, s2, 0.f};
 }
 
+// ---- batches: one member's dense inverse applied to every member (a GEMM) --------------------------------------------
+// arap_batch_*: K members share topology, rest pose and the constrained SET, so they share the operator L. For members of
+// up to 2048 vertices the preconditioner is therefore ONE dense fp32 inverse (V x V, inverted once on the device) applied
+// to all K residuals at once:  Z (V x 3K) = Inv (V x V) . R (V x 3K)  -- the one place on this path that is a dense
+// contraction. SIMT fp32 tiles (128 rows x 32 members x 16 k), 8 x 6 accumulators per thread; the right-hand side is read
+// straight from the fp64 CG residual (member-major Vec3d) and converted on the fly, the result is written as float4.
+constexpr int kBgM = 128, kBgMembers = 32, kBgK = 16, kBgN = kBgMembers * 3;
+__global__ void __launch_bounds__(256) mg_batch_dense_kernel(int V, int ld, int K, const float *__restrict__ inv, const Vec3d *__restrict__ r,
+                                                             MgVec *__restrict__ z, const CgScalars *__restrict__ cg) {
+    if (cg->converged) return;
+    __shared__ __align__(16) float As[2][kBgK][kBgM];        // As[k][i]
+    __shared__ __align__(16) float Bs[2][kBgK][kBgN];        // Bs[k][member * 3 + c]
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * kBgM, m0 = blockIdx.y * kBgMembers;
+    const int ti = tid & 15, tn = tid >> 4;                  // thread tile: rows ti*8 .. +8, members tn*2 .. +2
+    float acc[8][6];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[a][b] = 0.f;
+    // global -> registers for one k-tile
+    float4 a_reg[2];
+    Vec3d b_reg[2];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = (tid >> 2) + 64 * j, q = tid & 3;                // 128 rows x 4 float4
+            const int gi = i0 + row, gk = k0 + 4 * q;
+            a_reg[j] = (gi < V && gk < ld) ? __ldg(reinterpret_cast<const float4 *>(inv + (size_t)gi * ld + gk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int ml = (tid >> 4) + 16 * j, kl = tid & 15;              // 32 members x 16 k
+            const int gm = m0 + ml, kk = k0 + kl;
+            b_reg[j] = (gm < K && kk < V) ? r[(size_t)gm * V + kk] : Vec3d{0.0, 0.0, 0.0};
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = (tid >> 2) + 64 * j, q = tid & 3;
+            As[buf][4 * q + 0][row] = a_reg[j].x; As[buf][4 * q + 1][row] = a_reg[j].y;
+            As[buf][4 * q + 2][row] = a_reg[j].z; As[buf][4 * q + 3][row] = a_reg[j].w;
+            const int ml = (tid >> 4) + 16 * j, kl = tid & 15;
+            Bs[buf][kl][3 * ml + 0] = (float)b_reg[j].x; Bs[buf][kl][3 * ml + 1] = (float)b_reg[j].y; Bs[buf][kl][3 * ml + 2] = (float)b_reg[j].z;
+        }
+    };
+    const int n_tiles = (V + kBgK - 1) / kBgK;
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) load_tile((t + 1) * kBgK);
+#pragma unroll
+        for (int k = 0; k < kBgK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ti * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ti * 8 + 4]);
+            const float2 b0 = *reinterpret_cast<const float2 *>(&Bs[buf][k][tn * 6]);
+            const float2 b1 = *reinterpret_cast<const float2 *>(&Bs[buf][k][tn * 6 + 2]);
+            const float2 b2 = *reinterpret_cast<const float2 *>(&Bs[buf][k][tn * 6 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) acc[a][b] += av[a] * bv[b];
+        }
+        if (t + 1 < n_tiles) store_tile(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+        const int gm = m0 + tn * 2 + mm;
+        if (gm >= K) continue;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int gi = i0 + ti * 8 + a;
+            if (gi < V) z[(size_t)gm * V + gi] = MgVec{acc[a][3 * mm], acc[a][3 * mm + 1], acc[a][3 * mm + 2], 0.f};
+        }
+    }
+}
+
 // ---- the tail of the V-cycle in ONE kernel -----------------------------------------------------------------------
 // On the coarse levels (a few thousand rows and fewer) every kernel above is pure launch latency: ~11 dependent launches of
 // ~3-5 us each per CG iteration, a quarter of the iteration at 1M vertices. This kernel runs the whole tail -- restriction
