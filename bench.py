@@ -250,7 +250,7 @@ def batch_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{K} independent deformations of sphere.obj (642 vertices), trajectory key-frame handle poses (BASELINE.json configs[3])",
                        "members_per_rank": end - begin, "vertices_total": int(K * P.shape[0]),
-                       "preconditioner": "one member's dense inverse applied to all members (fp32 GEMM)" if stats["mg_levels"] == 1 else
+                       "preconditioner": "one member's dense inverse applied to all members (tcgen05 3xTF32 GEMM)" if stats["mg_levels"] == 1 else
                        "multigrid over the block-diagonal batch, %d levels" % stats["mg_levels"]},
             "deformations_of_10_iterations_per_sec": K / (10 * ms / args.steps * 1e-3),
             "cg_iterations_per_step": stats["cg_iterations_total"] / max(1, stats["global_steps"]), "prepare_ms": prepare_ms}

@@ -12,6 +12,7 @@
 #include "mg_partition.h"
 #include "partition.cuh"
 #include "peer_transport.cuh"
+#include "batch_gemm_tc.cuh"
 #include "../../inc/deform/detail/se3_spline.h"
 
 #include <cuda_runtime.h>
@@ -302,6 +303,8 @@ public:
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
     // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
+    DeviceBuffer<float> mg_inv_hi, mg_inv_lo;      // the batch inverse split for 3xTF32 (batch_gemm_tc.cuh)
+    bool mg_batch_tc = false;                      // batches: the GEMM runs on the tensor cores (tcgen05), else SIMT fp32
     bool mg_batch_dense = false;                   // batches: one member's dense inverse is the whole preconditioner (mg_batch_dense_kernel)
     double length_scale = 0;                       // bbox diagonal of the first rest pose (position-error stopping rule)
     MgTailArgs tail_args;
@@ -926,7 +929,19 @@ public:
         ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
         ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
         mg.push_back(std::move(d));
+        // tensor-core path: split the inverse once into hi + lo TF32 parts (ARAP_BATCH_TC=0 keeps the SIMT fp32 GEMM)
+        mg_batch_tc = !(getenv("ARAP_BATCH_TC") && atoi(getenv("ARAP_BATCH_TC")) == 0);
+        if (mg_batch_tc) {
+            const size_t n_inv = (size_t)Vm * mg_coarse_ld;
+            ARAP_CUDA(mg_inv_hi.ensure(n_inv));
+            ARAP_CUDA(mg_inv_lo.ensure(n_inv));
+            begin_launch(ARAP_K_MISC);
+            tf32_split_kernel<<<grid_for(n_inv), kBlock, 0, stream>>>(n_inv, mg_coarse_inv.ptr, mg_inv_hi.ptr, mg_inv_lo.ptr);
+            end_launch();
+            ARAP_CUDA(cudaFuncSetAttribute(mg_batch_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        }
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
         tail_first = 0;
         stats.mg_levels = 1;
         stats.mg_operator_complexity = 1.0;
@@ -1269,9 +1284,15 @@ public:
         if (L == 1) {
             // tiny meshes: the whole system is the "coarsest level"; b = the fp64 CG residual converted to fp32
             if (mg_batch_dense) {       // Z = Inv . R over all members at once, straight from the fp64 residual
-                const dim3 grid((unsigned)((member_vertices + kBgM - 1) / kBgM), (unsigned)((batch_members + kBgMembers - 1) / kBgMembers), 1);
                 begin_launch(ARAP_K_MG_DENSE_SOLVE);
-                mg_batch_dense_kernel<<<grid, 256, 0, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_coarse_inv.ptr, cg_r.ptr, z, cg.ptr);
+                if (mg_batch_tc) {
+                    const dim3 grid((unsigned)((member_vertices + kTcM - 1) / kTcM), (unsigned)((batch_members + kTcMembers - 1) / kTcMembers), 1);
+                    mg_batch_dense_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_inv_hi.ptr,
+                                                                                         mg_inv_lo.ptr, cg_r.ptr, z, cg.ptr);
+                } else {
+                    const dim3 grid((unsigned)((member_vertices + kBgM - 1) / kBgM), (unsigned)((batch_members + kBgMembers - 1) / kBgMembers), 1);
+                    mg_batch_dense_kernel<<<grid, 256, 0, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_coarse_inv.ptr, cg_r.ptr, z, cg.ptr);
+                }
                 end_launch();
                 LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
                 return reduce_stage(CG_STAGE_RHO, 4);
