@@ -303,7 +303,7 @@ public:
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
     // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
-    DeviceBuffer<float> mg_inv_hi, mg_inv_lo;      // the batch inverse split for 3xTF32 (batch_gemm_tc.cuh)
+    DeviceBuffer<float> mg_a_pack, mg_b_pack;      // batch GEMM operands as shared-memory stage images (batch_gemm_tc.cuh)
     bool mg_batch_tc = false;                      // batches: the GEMM runs on the tensor cores (tcgen05), else SIMT fp32
     bool mg_batch_dense = false;                   // batches: one member's dense inverse is the whole preconditioner (mg_batch_dense_kernel)
     double length_scale = 0;                       // bbox diagonal of the first rest pose (position-error stopping rule)
@@ -929,14 +929,15 @@ public:
         ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
         ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)n_vertices, stream));
         mg.push_back(std::move(d));
-        // tensor-core path: split the inverse once into hi + lo TF32 parts (ARAP_BATCH_TC=0 keeps the SIMT fp32 GEMM)
+        // tensor-core path: pack the inverse once into stage images, hi + lo TF32 parts (ARAP_BATCH_TC=0 keeps the SIMT fp32 GEMM)
         mg_batch_tc = !(getenv("ARAP_BATCH_TC") && atoi(getenv("ARAP_BATCH_TC")) == 0);
         if (mg_batch_tc) {
-            const size_t n_inv = (size_t)Vm * mg_coarse_ld;
-            ARAP_CUDA(mg_inv_hi.ensure(n_inv));
-            ARAP_CUDA(mg_inv_lo.ensure(n_inv));
+            const int n_mt = (Vm + kTcM - 1) / kTcM, n_nt = (batch_members + kTcMembers - 1) / kTcMembers, n_ks = (Vm + kTcK - 1) / kTcK;
+            ARAP_CUDA(mg_a_pack.ensure((size_t)n_mt * n_ks * 2 * kTcAFloats));
+            ARAP_CUDA(mg_b_pack.ensure((size_t)n_nt * n_ks * 2 * kTcBFloats));
+            const size_t items = (size_t)n_mt * n_ks * kTcKcores * kTcM;
             begin_launch(ARAP_K_MISC);
-            tf32_split_kernel<<<grid_for(n_inv), kBlock, 0, stream>>>(n_inv, mg_coarse_inv.ptr, mg_inv_hi.ptr, mg_inv_lo.ptr);
+            batch_pack_a_kernel<<<grid_for(items), kBlock, 0, stream>>>(Vm, mg_coarse_ld, n_mt, n_ks, mg_coarse_inv.ptr, mg_a_pack.ptr);
             end_launch();
             ARAP_CUDA(cudaFuncSetAttribute(mg_batch_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
         }
@@ -1286,9 +1287,12 @@ public:
             if (mg_batch_dense) {       // Z = Inv . R over all members at once, straight from the fp64 residual
                 begin_launch(ARAP_K_MG_DENSE_SOLVE);
                 if (mg_batch_tc) {
-                    const dim3 grid((unsigned)((member_vertices + kTcM - 1) / kTcM), (unsigned)((batch_members + kTcMembers - 1) / kTcMembers), 1);
-                    mg_batch_dense_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_inv_hi.ptr,
-                                                                                         mg_inv_lo.ptr, cg_r.ptr, z, cg.ptr);
+                    const int n_mt = (member_vertices + kTcM - 1) / kTcM, n_nt = (batch_members + kTcMembers - 1) / kTcMembers;
+                    const int n_ks = (member_vertices + kTcK - 1) / kTcK;
+                    const size_t items = (size_t)n_nt * n_ks * kTcKcores * kTcN;
+                    batch_pack_b_kernel<<<grid_for(items), kBlock, 0, stream>>>(member_vertices, batch_members, n_nt, n_ks, cg_r.ptr, mg_b_pack.ptr, cg.ptr);
+                    mg_batch_dense_tc_kernel<<<dim3((unsigned)n_mt, (unsigned)n_nt, 1), 128, kTcSmemBytes, stream>>>(member_vertices, batch_members, n_ks,
+                                                                                                                  mg_a_pack.ptr, mg_b_pack.ptr, z, cg.ptr);
                 } else {
                     const dim3 grid((unsigned)((member_vertices + kBgM - 1) / kBgM), (unsigned)((batch_members + kBgMembers - 1) / kBgMembers), 1);
                     mg_batch_dense_kernel<<<grid, 256, 0, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_coarse_inv.ptr, cg_r.ptr, z, cg.ptr);
