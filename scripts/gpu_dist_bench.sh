@@ -13,7 +13,7 @@ tail -5 gpurun_out/pytest_nccl.log
 run() {   # nproc nx env...
   local np=$1 nx=$2; shift 2
   env "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 29531 \
-      scripts/dist_partitioned_check.py $nx $nx 5 > gpurun_out/dist_run.log 2>&1
+      tests/tools/dist_partitioned_check.py $nx $nx 5 > gpurun_out/dist_run.log 2>&1
   echo "exit $? np=$np nx=$nx $*"
   grep "^PARTITIONED " gpurun_out/dist_run.log | sed 's/^PARTITIONED //' >> gpurun_out/dist_bench.jsonl
   grep -v "^PARTITIONED" gpurun_out/dist_run.log | tail -5

@@ -7,7 +7,7 @@ NGPU=${NGPU:-2}
 for nx in ${SIZES:-2000 4000}; do
   for tr in peer nccl; do
     ARAP_DIST_TRANSPORT=$tr timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29551 \
-        scripts/dist_partitioned_check.py $nx $nx ${ITERS:-5} > gpurun_out/dist_run_$tr.log 2>&1
+        tests/tools/dist_partitioned_check.py $nx $nx ${ITERS:-5} > gpurun_out/dist_run_$tr.log 2>&1
     echo "exit $? nx=$nx transport=$tr"
     grep "^PARTITIONED " gpurun_out/dist_run_$tr.log | sed 's/^PARTITIONED //' >> gpurun_out/dist_peer.jsonl
     grep -v "^PARTITIONED" gpurun_out/dist_run_$tr.log | grep -v "OMP_NUM\|^\*\*\*\*\|^$" | tail -6

@@ -8,7 +8,7 @@ tail -15 gpurun_out/pytest_nccl.log
 : > gpurun_out/dist_quick.jsonl
 for nx in ${SIZES:-2000 4000}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29541 \
-      scripts/dist_partitioned_check.py $nx $nx 5 > gpurun_out/dist_run.log 2>&1
+      tests/tools/dist_partitioned_check.py $nx $nx 5 > gpurun_out/dist_run.log 2>&1
   echo "exit $? nx=$nx"
   grep "^PARTITIONED " gpurun_out/dist_run.log | sed 's/^PARTITIONED //' >> gpurun_out/dist_quick.jsonl
   grep -v "^PARTITIONED" gpurun_out/dist_run.log | tail -8

@@ -1,4 +1,4 @@
-"""Partitioned mode over NCCL on 2 GPUs (skipped on boxes with fewer). Launches torchrun on scripts/dist_partitioned_check.py."""
+"""Partitioned mode over NCCL on 2 GPUs (skipped on boxes with fewer). Launches torchrun on tests/tools/dist_partitioned_check.py."""
 import json
 import os
 import subprocess
@@ -20,7 +20,7 @@ def test_partitioned_mesh_over_nccl_two_gpus(transport):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     env = dict(os.environ, ARAP_DIST_TRANSPORT=transport)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517" if transport == "nccl" else "29518", os.path.join(ROOT, "scripts", "dist_partitioned_check.py"), "96", "64", "4"]
+           "--master-port", "29517" if transport == "nccl" else "29518", os.path.join(ROOT, "tests", "tools", "dist_partitioned_check.py"), "96", "64", "4"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("PARTITIONED ")]
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]

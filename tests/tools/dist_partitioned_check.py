@@ -1,13 +1,13 @@
 """Partitioned mode over NCCL, one process per GPU (launch with torchrun). Rank 0 checks the gathered result against
 the CPU oracle (small mesh) and prints timing for a larger one.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_partitioned_check.py [nx nz iters]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tools/dist_partitioned_check.py [nx nz iters]
 """
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import torch.distributed as dist

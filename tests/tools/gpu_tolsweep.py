@@ -1,6 +1,6 @@
 """CG tolerance sweep: parity of the GPU engine vs the oracle as a function of cg_tolerance (run on the GPU box)."""
-import sys, time, json
-sys.path.insert(0, ".")
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from mesh_deform_b200 import meshgen as G, capi
 from oracle import oracle as O
