@@ -502,6 +502,41 @@ def _run_partitioned(P, F, idx, tgt, world, key, iters, transport=None, **kw):
     return pos, parts[0].solver_stats()
 
 
+@pytest.mark.parametrize("transport", ["host", "peer"])
+def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
+    """A 2 x 2 block partition instead of strips: every rank has three neighbours (one only across a corner), the halo plans of
+    the multigrid levels differ from rank to rank. Same parity bar against the unpartitioned oracle."""
+    nx, nz, iters = 72, 60, 4
+    P, F = G.grid_plane(nx, nz)
+    idx, tgt = G.grid_constraints(nx, nz, P)
+    owner = ((P[:, 0] > np.median(P[:, 0])).astype(np.int32) + 2 * (P[:, 2] > np.median(P[:, 2])).astype(np.int32)).astype(np.int32)
+    kind = capi.TRANSPORT_PEER_IN_PROCESS if transport == "peer" else capi.TRANSPORT_IN_PROCESS
+    key = 3001 if transport == "peer" else 3002
+    parts = [capi.PartitionedDeformation(P, F, owner, r, 4, kind, key, np.float64) for r in range(4)]
+    assert all(len(p.part.neighbor_rank) == 3 for p in parts)
+
+    def work(p):
+        def run():
+            p.setConstraints(idx, tgt)
+            assert p.prepare() == capi.ARAP_OK
+            p.iterate(iters)
+        return run
+    capi.run_partitions_in_process([work(p) for p in parts])
+    pos = np.zeros_like(P)
+    for p in parts:
+        gid, xyz = p.owned_positions()
+        pos[gid] = xyz
+    omesh = P.copy()
+    o = O.ArapOracle(omesh, F, np.float64)
+    constrain(o, idx, tgt)
+    assert o.deform(iters)
+    err = np.abs(pos - omesh).max() / bbox_diag(P)
+    de = abs(sum(p.local_energy() for p in parts) - o.energy()) / o.energy()
+    st = parts[0].solver_stats()
+    print("quadrants", transport, "err/diag", err, "rel dE", de, "levels", st["mg_levels"], "global", st["mg_global"])
+    assert err <= POS_TOL and de <= E_TOL and st["mg_global"] == 1
+
+
 def test_partitioned_global_multigrid_keeps_the_iteration_count():
     """The point of the global hierarchy (arap_partition_set_global_mesh): partitioning must not cost CG iterations.
     Block-Jacobi across ranks (each rank preconditioning only its own block) is the baseline it replaces."""

@@ -122,13 +122,19 @@ def test_vcycle_preconditioned_cg_converges_fast(shim):
     assert it < 25, it
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_partitioned_vcycle_equals_global_vcycle(shim, world):
+def quadrant_owner(P):
+    """A 2 x 2 block partition (every rank has three neighbours, one of them only across a corner)."""
+    cx, cz = np.median(P[:, 0]), np.median(P[:, 2])
+    return ((P[:, 0] > cx).astype(np.int32) + 2 * (P[:, 2] > cz).astype(np.int32)).astype(np.int32)
+
+
+@pytest.mark.parametrize("world,kind", [(1, "strips"), (2, "strips"), (3, "strips"), (4, "quadrants")])
+def test_partitioned_vcycle_equals_global_vcycle(shim, world, kind):
     """Every rank's slice + the exchange sequence of Engine::vcycle_partitioned == the V-cycle of the whole hierarchy."""
     nx, nz = 40, 36
     P, F = G.grid_plane(nx, nz)
     idx, _ = G.grid_constraints(nx, nz, P)
-    owner = PT.strip_owner(P, world)
+    owner = PT.strip_owner(P, world) if kind == "strips" else quadrant_owner(P)
     levels, inv, _ = build_global(shim, P, F, idx, owner)
     nl = len(levels)
     assert nl >= 3
