@@ -506,7 +506,7 @@ def _run_partitioned(P, F, idx, tgt, world, key, iters, transport=None, **kw):
 def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
     """A 2 x 2 block partition instead of strips: two ranks have three neighbours (one of them only across the corner), the halo plans of
     the multigrid levels differ from rank to rank. Same parity bar against the unpartitioned oracle."""
-    nx, nz, iters = 72, 60, 4
+    nx, nz, iters = 200, 160, 4            # 32k vertices: three multigrid levels, so a partitioned intermediate level
     P, F = G.grid_plane(nx, nz)
     idx, tgt = G.grid_constraints(nx, nz, P)
     owner = ((P[:, 0] > np.median(P[:, 0])).astype(np.int32) + 2 * (P[:, 2] > np.median(P[:, 2])).astype(np.int32)).astype(np.int32)
@@ -534,7 +534,7 @@ def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
     de = abs(sum(p.local_energy() for p in parts) - o.energy()) / o.energy()
     st = parts[0].solver_stats()
     print("quadrants", transport, "err/diag", err, "rel dE", de, "levels", st["mg_levels"], "global", st["mg_global"])
-    assert err <= POS_TOL and de <= E_TOL and st["mg_global"] == 1
+    assert err <= POS_TOL and de <= E_TOL and st["mg_global"] == 1 and st["mg_levels"] >= 3
 
 
 def test_partitioned_global_multigrid_keeps_the_iteration_count():
