@@ -512,7 +512,9 @@ def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
     owner = ((P[:, 0] > np.median(P[:, 0])).astype(np.int32) + 2 * (P[:, 2] > np.median(P[:, 2])).astype(np.int32)).astype(np.int32)
     kind = capi.TRANSPORT_PEER_IN_PROCESS if transport == "peer" else capi.TRANSPORT_IN_PROCESS
     key = 3001 if transport == "peer" else 3002
-    parts = [capi.PartitionedDeformation(P, F, owner, r, 4, kind, key, np.float64) for r in range(4)]
+    # (position_tolerance 1e-8: with the default 3e-8 this gently bent, fine grid lands at 7.8e-7 relative energy -- inside the
+    #  1e-6 bar, but this test is about the partition plumbing, not about the margin of the stopping rule)
+    parts = [capi.PartitionedDeformation(P, F, owner, r, 4, kind, key, np.float64, position_tolerance=1e-8) for r in range(4)]
     assert sorted(len(p.part.neighbor_rank) for p in parts) == [2, 2, 3, 3]      # the quad diagonals join only one pair of opposite quadrants
 
     def work(p):
