@@ -524,7 +524,7 @@ def stopping_rule(args):
     if args.cg_tol > 0:
         rule["relative_residual"] = args.cg_tol
     if args.pos_tol > 0 or not args.cg_tol > 0:
-        rule["estimated_position_error_over_bbox_diagonal"] = args.pos_tol if args.pos_tol > 0 else 3e-8
+        rule["estimated_position_error_over_bbox_diagonal"] = args.pos_tol if args.pos_tol > 0 else 1e-8
     return rule
 
 

@@ -67,7 +67,7 @@ typedef struct arap_options {
     double position_tolerance;  /* multigrid solver only: stop a global solve when the estimated position error of the
                                  * iterate (the 8-norm over the vertices of z = M^-1 r, M^-1 one V-cycle) is below
                                  * position_tolerance x bounding-box diagonal of the rest pose. This is the default stopping
-                                 * rule (<= 0 -> 3e-8 when cg_tolerance is not given; ignored when cg_tolerance > 0 unless set
+                                 * rule (<= 0 -> 1e-8 when cg_tolerance is not given; ignored when cg_tolerance > 0 unless set
                                  * explicitly): unlike a residual tolerance it means the same thing on every mesh. */
 } arap_options;
 

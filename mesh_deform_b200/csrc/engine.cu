@@ -30,10 +30,11 @@
 
 namespace arap {
 
-// Default stopping rule of the multigrid solver (include/arap_b200.h, position_tolerance); chosen from the
-// sweep in profiles/r01_h_stopping_rule.txt: 20 ARAP iterations stay within 5e-7 x bbox diagonal and 2e-7 relative energy of
-// the direct solve on regular AND badly conditioned meshes, 20x / 5x inside the parity bar.
-static const double kDefaultPositionTolerance = 3e-8;
+// Default stopping rule of the multigrid solver (include/arap_b200.h, position_tolerance); chosen from the sweep in
+// profiles/r01_h_stopping_rule.txt and the margins of the GPU tests: positions stay ~100x inside the parity bar on regular AND badly
+// conditioned meshes; the relative ENERGY is the tighter bar on gently bent fine grids (3e-8 left a 200 x 160 grid at 7.8e-7 of the
+// allowed 1e-6 after 4 iterations, 1e-8 at 7.9e-8), which is what decided between the two.
+static const double kDefaultPositionTolerance = 1e-8;
 
 static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "weights_count", "weights_fill", "row_sort_merge", "csr_compact", "scan",
