@@ -912,6 +912,10 @@ public:
         if (getenv("ARAP_BATCH_DENSE") && atoi(getenv("ARAP_BATCH_DENSE")) == 0) return ARAP_OK;
         const int e = h_rowptr[(size_t)Vm];
         for (int k = 0; k < e; ++k) if (h_colidx[(size_t)k] >= Vm) return ARAP_OK;            // not block diagonal after all
+        // one operator for all members only if every member has member 0's constrained SET (arap_batch_set_constraints guarantees
+        // it; constraints set through the raw handle might not): otherwise the general hierarchy over the whole batch
+        for (int m = 1; m < batch_members; ++m)
+            if (std::memcmp(&h_con[(size_t)m * Vm], &h_con[0], (size_t)Vm) != 0) return ARAP_OK;
         MgHierarchyHost H;
         MgSetupOptions mo = engine_mg_options();
         mo.coarse_size = std::max(mo.coarse_size, Vm);

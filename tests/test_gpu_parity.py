@@ -395,6 +395,34 @@ def test_batch_of_sphere_deformations_matches_oracle(meshes):
         assert np.abs(pos[k] - mesh).max() <= POS_TOL * diag, k
 
 
+def test_batch_with_member_specific_constraints_falls_back_to_the_general_solver(meshes):
+    """The shared-operator shortcut of batches (one member's dense inverse for all) is only valid when every member has the
+    same constrained SET. Constraints added through the raw handle can break that; the engine must notice and still be right."""
+    import ctypes as C
+    P, F = meshes["sphere"]
+    K, V = 3, P.shape[0]
+    idx = np.array([G.SPHERE_ANCHOR, G.SPHERE_HANDLE], np.int32)
+    tg = np.stack([P[idx] + np.array([[0, 0, 0], [0, 0, 0.1 * (m + 1)]]) for m in range(K)])
+    extra_vertex = 100
+    extra_target = P[extra_vertex] + np.array([0.05, 0.0, 0.0])
+    b = capi.BatchDeformation(P, F, K, np.float64)
+    b.setConstraints(idx, tg)
+    one = np.array([1 * V + extra_vertex], np.int32)                        # member 1 only, super-mesh numbering
+    xyz = np.ascontiguousarray(extra_target[None], np.float64)
+    b._check(capi.lib().arap_set_constraints(b._h, 1, one.ctypes.data_as(C.c_void_p), xyz.ctypes.data_as(C.c_void_p), 8))
+    assert b.prepare() == capi.ARAP_OK
+    b.iterate(6)
+    pos = b.positions()
+    for m in range(K):
+        mesh = P.copy()
+        o = O.ArapOracle(mesh, F, np.float64)
+        constrain(o, idx, tg[m])
+        if m == 1:
+            o.setConstraint(extra_vertex, extra_target)
+        assert o.deform(6)
+        assert np.abs(pos[m] - mesh).max() <= POS_TOL * bbox_diag(P), m
+
+
 def test_rigid_constraint_front_end_matches_per_vertex_constraints(meshes):
     """DeformationUtil::updateConstraints in one call (arap_set_rigid_constraints / arap_batch_set_rigid_constraints,
     targets computed on the device) against setConstraint with the oracle's targets (deformation_util.h:48-57)."""
