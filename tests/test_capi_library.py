@@ -185,3 +185,17 @@ def test_rigid_conjugate_matches_oracle():
     M = capi.rigid_conjugate(origin, t)
     got = pts @ M[:3, :3].T + M[:3, 3]
     assert np.abs(got - O.handle_targets(origin, t, pts)).max() < 1e-13
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/arap_b200.h is the drop-in boundary: a C header (C99, pedantic), usable from any FFI, no C++ or torch types."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "arap_b200.h"\n'
+                   'int main(void) { arap_options o; arap_global_mesh g; arap_partition_plan p; arap_solver_stats s; arap_profile q;\n'
+                   '  (void)g; (void)p; (void)s; (void)q; arap_default_options(&o); return arap_abi_version() == ARAP_B200_ABI_VERSION ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+    # and it links against the library without any C++ runtime symbols leaking into the interface
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", os.path.join(ROOT, "mesh_deform_b200"),
+                           "-larap_b200", "-Wl,-rpath," + os.path.join(ROOT, "mesh_deform_b200")])
+    assert subprocess.run([str(exe)]).returncode == 0
