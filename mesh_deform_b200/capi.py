@@ -459,6 +459,18 @@ class BatchDeformation:
         self._check(lib().arap_get_solver_stats(self._h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in SolverStats._fields_}
 
+    def profile_enable(self, on=True):
+        self._check(lib().arap_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(lib().arap_profile_reset(self._h))
+
+    def profile(self):
+        p = Profile()
+        self._check(lib().arap_profile_get(self._h, C.byref(p)))
+        return {lib().arap_kernel_name(k).decode(): {"launches": int(p.launches[k]), "ms": float(p.milliseconds[k])}
+                for k in range(K_COUNT_MAX) if p.launches[k] and lib().arap_kernel_name(k)}
+
     def timer_start(self):
         self._check(lib().arap_timer_start(self._h))
 
