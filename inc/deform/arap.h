@@ -94,10 +94,11 @@ public:
 
         if (_dirty) {
             if (!_pendingIdx.empty()) {
-                if (arap_set_constraints(_handle, (int32_t)_pendingIdx.size(), _pendingIdx.data(), _pendingLoc.data(), (int32_t)sizeof(Scalar)) != ARAP_OK)
-                    return false;
-                _pendingIdx.clear();
+                // one call for everything queued since the last deform(); a vertex named twice keeps its LAST location (arap.h:83)
+                const int rc = arap_set_constraints(_handle, (int32_t)_pendingIdx.size(), _pendingIdx.data(), _pendingLoc.data(), (int32_t)sizeof(Scalar));
+                _pendingIdx.clear();                         // also on failure: a bad index must not poison every later deform()
                 _pendingLoc.clear();
+                if (rc != ARAP_OK) return false;
             }
             readVertices(xyz, bulk);                         // initializeMeshGeometry (arap.h:162-168)
             const int rc = arap_prepare(_handle, xyz, (int32_t)sizeof(MeshScalar));
@@ -106,11 +107,12 @@ public:
             _dirty = false;
         }
 
-        if (arap_iterate(_handle, numberOfIterations) != ARAP_OK) return false;
+        const int it = arap_iterate(_handle, numberOfIterations);
+        if (it < 0) return false;
 
         if (arap_get_positions(_handle, xyz, (int32_t)sizeof(MeshScalar)) != ARAP_OK) return false;
         writeVertices(xyz, bulk);                            // write-back (arap.h:133-135)
-        return true;
+        return it == ARAP_OK;                                // ARAP_NOT_CONVERGED: unusable system, the reference's `false` (arap.h:116-117)
     }
 
     /** ARAP energy of the current state (not part of the reference API; Sorkine & Alexa 2007, eq. 3). */
@@ -130,8 +132,9 @@ private:
 
     // ---- mesh ingest / write-back: bulk pointers when the mesh offers them, the five-member concept otherwise ----
     void createHandle(detail::bool_tag<true>) {
-        arap_create(reinterpret_cast<const int32_t *>(_mesh.faceData()), _mesh.numberOfFaces(), _mesh.numberOfVertices(),
-                    (int32_t)sizeof(Scalar), nullptr, &_handle);
+        if (arap_create(reinterpret_cast<const int32_t *>(_mesh.faceData()), _mesh.numberOfFaces(), _mesh.numberOfVertices(),
+                        (int32_t)sizeof(Scalar), nullptr, &_handle) != ARAP_OK)
+            _handle = nullptr;                               // deform() then returns false; lastError() has arap_create_error()
     }
     void createHandle(detail::bool_tag<false>) {             // initializeMeshTopology (arap.h:149-155)
         const Index nF = _mesh.numberOfFaces();
@@ -142,7 +145,8 @@ private:
             faces[3 * (size_t)f + 1] = vids(1);
             faces[3 * (size_t)f + 2] = vids(2);
         }
-        arap_create(faces.data(), nF, _mesh.numberOfVertices(), (int32_t)sizeof(Scalar), nullptr, &_handle);
+        if (arap_create(faces.data(), nF, _mesh.numberOfVertices(), (int32_t)sizeof(Scalar), nullptr, &_handle) != ARAP_OK)
+            _handle = nullptr;
     }
     typename Mesh::Scalar *vertexBuffer(detail::bool_tag<true>) { return _mesh.vertexData(); }
     typename Mesh::Scalar *vertexBuffer(detail::bool_tag<false>) {

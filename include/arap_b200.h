@@ -41,6 +41,10 @@ extern "C" {
 enum {
     ARAP_OK = 0,
     ARAP_UNCONSTRAINED = 1,   /* prepare(): no vertex is constrained -> nothing to solve (arap.h:113-114) */
+    ARAP_NOT_CONVERGED = 2,   /* iterate()/deform(): a global solve hit max_cg_iterations before its stopping rule was met (e.g. a free
+                               * component without any constrained vertex makes L singular -- the case in which the reference's
+                               * factorisation fails, arap.h:116-117). The iterations still ran and the positions are the best
+                               * iterate; the C++ facade maps this to `false`. */
     ARAP_ERR_INVALID = -1,    /* bad argument / call order */
     ARAP_ERR_CUDA = -2,       /* CUDA runtime failure (message in arap_last_error) */
     ARAP_ERR_SOLVER = -3,     /* linear system unusable: the reference's `return false` (arap.h:116-117) */
@@ -90,7 +94,9 @@ int arap_is_dirty(const arap_handle *h);
  * Returns ARAP_OK, ARAP_UNCONSTRAINED (weights/CSR are still built; handle stays dirty) or an error. */
 int arap_prepare(arap_handle *h, const void *rest_xyz, int32_t rest_scalar_bytes);
 
-/* n x (local step, global step) on the device (arap.h:122-129). Requires a successful arap_prepare. */
+/* n x (local step, global step) on the device (arap.h:122-129). Requires a successful arap_prepare that is still current:
+ * after arap_set_constraints / arap_set_rigid_constraints the handle is dirty and this call fails with ARAP_ERR_INVALID
+ * until arap_prepare (or arap_deform) has run again. Returns ARAP_OK, ARAP_NOT_CONVERGED or an error. */
 int arap_iterate(arap_handle *h, int32_t n_iterations);
 
 /* Current p' (V x 3) cast to scalars of out_scalar_bytes (arap.h:133-135). */
@@ -111,6 +117,10 @@ int arap_get_free_map(arap_handle *h, int32_t *free_idx /*V*/, int32_t *n_free);
 /* _rotations (arap.h:454) as V x 9 row-major 3x3 matrices in handle precision. */
 int arap_get_rotations(arap_handle *h, void *rot9);
 
+/* _b (arap.h:393-414: bFixed + sum_j w_ij/2 (R_i + R_j)(p_i - p_j)) for the current rotations: n_free x 3 doubles, row f =
+ * the vertex with free index f (arap_get_free_map). Runs the engine's right-hand-side kernel once; for tests / inspection. */
+int arap_get_rhs(arap_handle *h, double *rhs /* n_free x 3 */);
+
 /* ARAP energy sum_i sum_j w_ij |(p'_i-p'_j) - R_i (p_i-p_j)|^2 (Sorkine & Alexa eq. 3; the reference has none). */
 int arap_energy(arap_handle *h, double *energy);
 
@@ -124,7 +134,8 @@ typedef struct arap_solver_stats {
     int32_t mg_levels;             /* 0 when the Jacobi preconditioner is in use */
     double mg_operator_complexity;
     double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare */
-    int32_t cg_graph;              /* 1: a CG iteration (with its exchanges, if partitioned) is replayed from a CUDA graph */
+    int32_t cg_graph;              /* 1: a CG iteration (with its exchanges, if partitioned) is replayed from a CUDA graph;
+                                    * 2: the whole ARAP iteration is one graph whose CG loop runs on the device (WHILE node) */
     int32_t mg_global;             /* 1: partitioned mode with the global hierarchy (arap_partition_set_global_mesh) */
     double last_position_error;    /* multigrid: the estimate the stopping rule used, as a fraction of the bbox diagonal */
 } arap_solver_stats;

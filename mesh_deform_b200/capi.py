@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("ARAP_B200_LIB") or os.path.join(_HERE, "libarap_b200.
 
 ARAP_OK = 0
 ARAP_UNCONSTRAINED = 1
+ARAP_NOT_CONVERGED = 2
 ARAP_ERR_INVALID = -1
 ARAP_ERR_CUDA = -2
 ARAP_ERR_SOLVER = -3
@@ -28,7 +29,7 @@ K_COUNT_MAX = 32
 EXPORTED_SYMBOLS = (
     "arap_default_options", "arap_create", "arap_destroy", "arap_set_constraints", "arap_is_dirty",
     "arap_prepare", "arap_iterate", "arap_get_positions", "arap_deform", "arap_get_csr_nnz", "arap_get_csr",
-    "arap_get_free_map", "arap_get_rotations", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
+    "arap_get_free_map", "arap_get_rotations", "arap_get_rhs", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
     "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
     "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
@@ -102,6 +103,7 @@ def lib():
     L.arap_get_csr.argtypes = [vp, vp, vp, vp]
     L.arap_get_free_map.argtypes = [vp, vp, C.POINTER(i32)]
     L.arap_get_rotations.argtypes = [vp, vp]
+    L.arap_get_rhs.argtypes = [vp, vp]
     L.arap_energy.argtypes = [vp, C.POINTER(C.c_double)]
     L.arap_get_solver_stats.argtypes = [vp, C.POINTER(SolverStats)]
     L.arap_profile_enable.argtypes = [vp, i32]
@@ -243,7 +245,7 @@ class AsRigidAsPossibleDeformation:
         rc = lib().arap_deform(self._h, _ptr(self.mesh), self.mesh.dtype.itemsize, int(numberOfIterations))
         if rc in (ARAP_ERR_INVALID, ARAP_ERR_CUDA, ARAP_ERR_ALLOC):
             raise ArapError(rc, lib().arap_last_error(self._h).decode())
-        return rc >= 0
+        return rc in (ARAP_OK, ARAP_UNCONSTRAINED)     # ARAP_NOT_CONVERGED / ARAP_ERR_SOLVER: the reference's `false`
 
     # -- split protocol (what deform() is made of) ----------------------------------------------
     @property
@@ -282,6 +284,13 @@ class AsRigidAsPossibleDeformation:
     def rotations(self):
         out = np.zeros((self.nV, 3, 3), self.real)
         self._check(lib().arap_get_rotations(self._h, _ptr(out)))
+        return out
+
+    def rhs(self):
+        """_b of the reference (arap.h:393-414) for the current rotations: (n_free, 3) float64 in free-index order."""
+        _, n_free = self.freeIdxMap()
+        out = np.zeros((n_free, 3), np.float64)
+        self._check(lib().arap_get_rhs(self._h, _ptr(out)))
         return out
 
     def energy(self):

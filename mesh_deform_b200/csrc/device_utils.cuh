@@ -9,6 +9,16 @@ namespace arap {
 constexpr int kBlock = 256;           // threads per CTA for the vertex/row-parallel kernels
 constexpr int kWarpsPerBlock = kBlock / 32;
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor is still running. pdl_wait() blocks until the predecessor grid has completed and
+// its writes are visible -- every kernel of the iteration calls it before touching any global memory; pdl_trigger() lets
+// the NEXT kernel's CTAs be scheduled as soon as all CTAs of this one have started (they then sit in their own
+// pdl_wait()), which hides the launch latency of the ~20 small dependent kernels of a CG iteration. Both are no-ops
+// for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

@@ -26,6 +26,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace arap {
@@ -93,12 +94,14 @@ public:
     virtual int set_rigid_constraints(int n, int batch, int member_stride, const int *idx, const void *rest, int scalar_bytes,
                                       const double *transforms16) = 0;
     virtual int prepare(const void *rest_xyz, int scalar_bytes) = 0;
-    virtual int iterate(int n) = 0;
+    virtual int iterate(int n, bool defer_sync = false) = 0;
+    virtual int finish_iterate() = 0;
     virtual int get_positions(void *out, int scalar_bytes) = 0;
     virtual int get_csr_nnz(int *nnz) = 0;
     virtual int get_csr(int *rowptr, int *colidx, void *weights) = 0;
     virtual int get_free_map(int *free_idx, int *n_free) = 0;
     virtual int get_rotations(void *rot9) = 0;
+    virtual int get_rhs(double *out) = 0;
     virtual int energy(double *e) = 0;
     virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
     virtual int set_global_mesh(const arap_global_mesh *g) = 0;
@@ -142,6 +145,29 @@ public:
         pending.clear();
     }
 
+    // Launch of an iteration kernel (every one of them starts with pdl_wait(), device_utils.cuh) with programmatic stream
+    // serialisation: inside a captured graph this becomes a programmatic edge, and the kernel's CTAs are scheduled while the
+    // previous kernel drains. Not used while per-launch events are being recorded (they would sit between the two kernels)
+    // and not for the first kernel after something that is not one of these kernels (pdl_next_plain).
+    template <typename... Exp, typename... Act>
+    void launch_pdl(void (*kernel)(Exp...), unsigned grid, unsigned block, size_t smem, Act &&... args) {
+        cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(block, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        const bool pdl = use_pdl && !pdl_next_plain && !profile_events;
+        cfg.attrs = pdl ? &attr : nullptr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        pdl_next_plain = false;
+        cudaLaunchKernelEx(&cfg, kernel, std::forward<Act>(args)...);
+    }
+    bool use_pdl = !(getenv("ARAP_PDL") && atoi(getenv("ARAP_PDL")) == 0);
+    bool pdl_next_plain = true;
+
     int n_vertices = 0, n_faces = 0;
     int device = 0;
     int sm_count = 148;
@@ -180,6 +206,13 @@ public:
     do {                                                                             \
         begin_launch(id);                                                            \
         kernel<<<(grid), kBlock, 0, stream>>>(__VA_ARGS__);                          \
+        end_launch();                                                                \
+    } while (0)
+
+#define LAUNCH_PDL(id, kernel, grid, ...)                                            \
+    do {                                                                             \
+        begin_launch(id);                                                            \
+        launch_pdl(kernel, (unsigned)(grid), (unsigned)kBlock, 0, __VA_ARGS__);      \
         end_launch();                                                                \
     } while (0)
 
@@ -262,7 +295,7 @@ public:
     std::vector<int> mg_visit_order;               // Morton sequence of internal indices: aggregation order of the fine level
     DeviceBuffer<Vec4T<S>> rest4, cur4, quat;      // _p, _pprime, _rotations
     DeviceBuffer<double> inv_diag;
-    DeviceBuffer<Vec3d> cg_r, cg_d, cg_ad, cg_x;
+    DeviceBuffer<Vec3d> cg_r, cg_d, cg_ad, cg_x, cg_w;      // residual, direction, A d (s), solution, and w = A z (multigrid CG)
     DeviceBuffer<double> partials;
     DeviceBuffer<unsigned> counter;
     DeviceBuffer<CgScalars> cg;
@@ -331,6 +364,7 @@ public:
     ~Engine() override {
         collect_profile();
         destroy_cg_graph();
+        destroy_step_graph();
         if (cg_host) cudaFreeHost(cg_host);
         for (auto &e : poll_event) if (e) cudaEventDestroy(e);
         if (timer_start) cudaEventDestroy(timer_start);
@@ -416,6 +450,23 @@ public:
         return ARAP_OK;
     }
 
+    // setConstraint overwrites the map entry of a vertex (arap.h:83): when one call names a vertex several times the LAST
+    // occurrence wins. The scatter kernels write one entry per thread, so duplicates are removed here (the kept entries stay
+    // in call order). Returns false when `idx` has no duplicates (the common case: nothing is copied).
+    static bool last_occurrences(int n, const int *idx, std::vector<int> &keep) {
+        std::vector<std::pair<int, int>> order((size_t)n);
+        for (int k = 0; k < n; ++k) order[(size_t)k] = {idx[k], k};
+        std::sort(order.begin(), order.end());
+        bool dup = false;
+        for (int k = 0; k + 1 < n && !dup; ++k) dup = order[(size_t)k].first == order[(size_t)k + 1].first;
+        if (!dup) return false;
+        keep.clear();
+        for (int k = 0; k < n; ++k)
+            if (k + 1 == n || order[(size_t)k].first != order[(size_t)k + 1].first) keep.push_back(order[(size_t)k].second);
+        std::sort(keep.begin(), keep.end());
+        return true;
+    }
+
     int set_constraints(int n, const int *idx, const void *xyz, int scalar_bytes) override {
         if (n < 0 || (n > 0 && (!idx || !xyz)) || (scalar_bytes != 4 && scalar_bytes != 8))
             return fail(ARAP_ERR_INVALID, "set_constraints: bad arguments");
@@ -423,6 +474,20 @@ public:
             if (idx[k] < 0 || idx[k] >= n_vertices) return fail(ARAP_ERR_INVALID, "set_constraints: vertex index out of range");
         dirty = true;                                                    // arap.h:84
         if (n == 0) return ARAP_OK;
+        std::vector<int> keep, idx_unique;
+        std::vector<unsigned char> xyz_unique;
+        if (last_occurrences(n, idx, keep)) {
+            const size_t eb = 3 * (size_t)scalar_bytes;
+            idx_unique.resize(keep.size());
+            xyz_unique.resize(keep.size() * eb);
+            for (size_t q = 0; q < keep.size(); ++q) {
+                idx_unique[q] = idx[keep[q]];
+                std::memcpy(&xyz_unique[q * eb], (const unsigned char *)xyz + (size_t)keep[q] * eb, eb);
+            }
+            n = (int)keep.size();
+            idx = idx_unique.data();
+            xyz = xyz_unique.data();
+        }
         const size_t idx_bytes = sizeof(int) * (size_t)n, xyz_bytes = (size_t)scalar_bytes * 3 * (size_t)n;
         const size_t xyz_off = (idx_bytes + 15) & ~(size_t)15;
         ARAP_CUDA(staging.ensure(xyz_off + xyz_bytes));
@@ -450,6 +515,20 @@ public:
                 return fail(ARAP_ERR_INVALID, "set_rigid_constraints: vertex index out of range");
         dirty = true;                                                    // arap.h:84
         if (n == 0) return ARAP_OK;
+        std::vector<int> keep, idx_unique;
+        std::vector<unsigned char> rest_unique;
+        if (last_occurrences(n, idx, keep)) {                            // the same handle listed twice: the last entry wins
+            const size_t eb = 3 * (size_t)scalar_bytes;
+            idx_unique.resize(keep.size());
+            rest_unique.resize(keep.size() * eb);
+            for (size_t q = 0; q < keep.size(); ++q) {
+                idx_unique[q] = idx[keep[q]];
+                std::memcpy(&rest_unique[q * eb], (const unsigned char *)rest + (size_t)keep[q] * eb, eb);
+            }
+            n = (int)keep.size();
+            idx = idx_unique.data();
+            rest = rest_unique.data();
+        }
         std::vector<double> rows(12 * (size_t)batch);                    // top three rows of each 4x4
         for (int m = 0; m < batch; ++m) std::memcpy(&rows[12 * (size_t)m], transforms16 + 16 * (size_t)m, 12 * sizeof(double));
         const size_t idx_bytes = sizeof(int) * (size_t)n, xyz_bytes = (size_t)scalar_bytes * 3 * (size_t)n, tr_bytes = rows.size() * sizeof(double);
@@ -498,9 +577,15 @@ public:
         if (F > 0)
             LAUNCH(ARAP_K_WEIGHTS_FILL, weights_fill_kernel<S>, grid_for((size_t)F), faces.ptr, F, rest_xyz.ptr, raw_rowptr.ptr,
                    row_cursor.ptr, raw_col.ptr, raw_val.ptr, raw_tag.ptr);
-        if (V > 0)
+        if (V > 0) {
+            // rows of more than kLongRow raw triplets (very high valence) are listed in row_cursor -- free again after
+            // weights_fill -- with the count in its last slot, and sorted by one CTA each
+            ARAP_CUDA(cudaMemsetAsync(row_cursor.ptr + V, 0, sizeof(int), stream));
             LAUNCH(ARAP_K_ROW_SORT_MERGE, row_sort_merge_kernel<S>, grid_for((size_t)V), V, raw_rowptr.ptr, raw_col.ptr, raw_val.ptr,
-                   raw_tag.ptr, unique_count.ptr);
+                   raw_tag.ptr, unique_count.ptr, row_cursor.ptr, row_cursor.ptr + V);
+            LAUNCH(ARAP_K_ROW_SORT_MERGE, row_sort_long_kernel<S>, sm_count, row_cursor.ptr, row_cursor.ptr + V, raw_rowptr.ptr, raw_col.ptr,
+                   raw_val.ptr, raw_tag.ptr, unique_count.ptr);
+        }
         { int rc = exclusive_scan(unique_count.ptr, V, rowptr.ptr); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&nnz, rowptr.ptr + V, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
@@ -545,7 +630,8 @@ public:
         ARAP_CUDA(cg_d.ensure((size_t)V));
         ARAP_CUDA(cg_ad.ensure((size_t)V));
         ARAP_CUDA(cg_x.ensure((size_t)V));
-        for (Vec3d *vec : {cg_r.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr})                                  // halo slots must start finite
+        ARAP_CUDA(cg_w.ensure((size_t)V));
+        for (Vec3d *vec : {cg_r.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_w.ptr})                                  // halo slots must start finite
             ARAP_CUDA(cudaMemsetAsync(vec, 0, sizeof(Vec3d) * (size_t)(V > 0 ? V : 1), stream));
         use_mg = (opt.solver != ARAP_SOLVER_PCG_JACOBI);
         if (use_mg) {
@@ -602,11 +688,16 @@ public:
             init.inv_len2 = length_scale > 0 ? 1.0 / (length_scale * length_scale) : 1.0;
         }
         init.distributed = transport ? 1 : 0;
+        init.max_iterations = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
         cg_host[0] = init;
         ARAP_CUDA(cudaMemcpyAsync(cg.ptr, &cg_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
         if (transport) { int rc = configure_transport(); if (rc) return rc; }
-        if (!transport) { int rc = build_cg_graph(); if (rc) return rc; }
+        destroy_step_graph();
+        if (!transport) {
+            { int rc = build_cg_graph(); if (rc) return rc; }
+            { int rc = build_step_graph(); if (rc) return rc; }
+        }
         else if (transport->capturable()) {
             // NCCL calls and the peer transport's kernels are stream operations and can sit inside the graph, which removes
             // ~70 host-side enqueues per CG iteration. NCCL opens connections on first use, which must not happen during
@@ -620,7 +711,8 @@ public:
         // Partitions that share one GPU and wait on each other inside kernels (in-process peer transport) must not start
         // iterating while another one is still allocating: cudaFree waits for ALL device work, spinning kernels included.
         if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
-        stats.cg_graph = cg_graph_exec ? 1 : 0;
+        stats.cg_graph = step_graph_exec ? 2 : (cg_graph_exec ? 1 : 0);
+        pdl_next_plain = true;
         stats.mg_global = (use_mg && mg_global) ? 1 : 0;
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
@@ -740,6 +832,16 @@ public:
     int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) override {
         if (!p || p->n_owned < 0 || p->n_owned > n_vertices || p->n_neighbors < 0 || world <= 0 || rank < 0 || rank >= world)
             return fail(ARAP_ERR_INVALID, "attach_partition: bad arguments");
+        if (!p->send_offset || !p->recv_offset || (p->n_neighbors > 0 && !p->neighbor_rank))
+            return fail(ARAP_ERR_INVALID, "attach_partition: null plan arrays");
+        for (int k = 0; k < p->n_neighbors; ++k) {
+            if (p->neighbor_rank[k] < 0 || p->neighbor_rank[k] >= world || p->neighbor_rank[k] == rank)
+                return fail(ARAP_ERR_INVALID, "attach_partition: neighbour rank out of range");
+            if (p->send_offset[k] < 0 || p->send_offset[k + 1] < p->send_offset[k] || p->recv_offset[k] < 0 || p->recv_offset[k + 1] < p->recv_offset[k])
+                return fail(ARAP_ERR_INVALID, "attach_partition: offsets must start at >= 0 and ascend");
+        }
+        if (p->send_offset[0] != 0 || p->recv_offset[0] != 0) return fail(ARAP_ERR_INVALID, "attach_partition: offsets must start at 0");
+        if (p->send_offset[p->n_neighbors] > 0 && !p->send_index) return fail(ARAP_ERR_INVALID, "attach_partition: null send_index");
         my_rank = rank;
         world_size = world;
         plan = HaloPlan();
@@ -792,6 +894,7 @@ public:
     // refresh the halo slots of a per-vertex array from their owners (no-op on a single GPU)
     int exchange_halo(void *array, size_t elem_bytes, int site) {
         if (!transport) return ARAP_OK;
+        pdl_next_plain = true;
         begin_launch(ARAP_K_HALO_PACK);
         const int rc = transport->exchange(stream, site, plan, send_index_dev.ptr, (char *)halo_sendbuf.ptr, (char *)array, elem_bytes);
         end_launch();
@@ -830,6 +933,7 @@ public:
     // refresh the halo slots of one multigrid level's vector (global hierarchy, partitioned mode); which: see SITE_LEVEL_BASE
     int exchange_level(int level, int which, MgVec *array) {
         MgLevelDev &lv = *mg[(size_t)level];
+        pdl_next_plain = true;
         begin_launch(ARAP_K_HALO_PACK);
         const int rc = transport->exchange(stream, SITE_LEVEL_BASE + 4 * level + which, lv.plan, lv.send_index.ptr, (char *)mg_sendbuf.ptr,
                                            (char *)array, sizeof(MgVec));
@@ -844,8 +948,8 @@ public:
         auto ex = [&](int site, const HaloPlan *pl, int bytes) { sites[(size_t)site].kind = SiteSpec::EXCHANGE; sites[(size_t)site].plan = pl; sites[(size_t)site].elem_bytes = bytes; };
         ex(SITE_CUR4, &plan, (int)sizeof(Vec4T<S>));
         ex(SITE_QUAT, &plan, (int)sizeof(Vec4T<S>));
-        ex(SITE_CG_D, &plan, (int)sizeof(Vec3d));
-        for (int st = 0; st <= CG_STAGE_RHO; ++st) { sites[(size_t)(SITE_RED_BASE + st)].kind = SiteSpec::REDUCE_F64; sites[(size_t)(SITE_RED_BASE + st)].n = 8; }
+        ex(SITE_CG_D, &plan, use_mg ? (int)sizeof(MgVec) : (int)sizeof(Vec3d));       // what the CG's matrix-vector product gathers: z (fp32) or d
+        for (int st = 0; st <= CG_STAGE_MERGED; ++st) { sites[(size_t)(SITE_RED_BASE + st)].kind = SiteSpec::REDUCE_F64; sites[(size_t)(SITE_RED_BASE + st)].n = 8; }
         if (use_mg && mg_global) {
             ex(SITE_MG0_X_PRE, &plan, (int)sizeof(MgVec));
             ex(SITE_MG0_R, &plan, (int)sizeof(MgVec));
@@ -863,7 +967,8 @@ public:
     }
 
     int warm_up_transport() {
-        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
+        if (use_mg) { int rc = exchange_halo(mg[0]->x2.ptr, sizeof(MgVec), SITE_CG_D); if (rc) return rc; }
+        else { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
         { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>), SITE_CUR4); if (rc) return rc; }
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
         if (transport->allreduce_sum(stream, SITE_RED_BASE, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
@@ -883,6 +988,7 @@ public:
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
         (void)n_values;             // always the whole red[8] block: one site layout for every stage
         if (transport->allreduce_sum(stream, SITE_RED_BASE + stage, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
+        pdl_next_plain = true;
         begin_launch(ARAP_K_CG_FINALIZE);
         cg_finalize_kernel<<<1, 1, 0, stream>>>(cg.ptr, stage);
         end_launch();
@@ -1046,12 +1152,14 @@ public:
         if (n <= 0) return ARAP_OK;
         const auto t0 = std::chrono::steady_clock::now();
         DeviceBuffer<int> d_rowptr, d_colidx, d_bad;
-        DeviceBuffer<double> d_val, d_M, d_col;
+        DeviceBuffer<double> d_val, d_M, d_D, d_C, d_R;
         ARAP_CUDA(upload_vector(d_rowptr, A.rowptr, stream));
         ARAP_CUDA(upload_vector(d_colidx, A.colidx, stream));
         ARAP_CUDA(upload_vector(d_val, A.val, stream));
         ARAP_CUDA(d_M.ensure((size_t)n * n));
-        ARAP_CUDA(d_col.ensure((size_t)n));
+        ARAP_CUDA(d_D.ensure((size_t)kGjB * kGjB));
+        ARAP_CUDA(d_C.ensure((size_t)n * kGjB));
+        ARAP_CUDA(d_R.ensure((size_t)n * kGjB));
         ARAP_CUDA(d_bad.ensure(1));
         ARAP_CUDA(cudaMemsetAsync(d_M.ptr, 0, sizeof(double) * (size_t)n * n, stream));
         ARAP_CUDA(cudaMemsetAsync(d_bad.ptr, 0, sizeof(int), stream));
@@ -1061,10 +1169,13 @@ public:
         const double shift = 1e-13 * trace / n;             // keeps a pure-Neumann component invertible (as mg_setup.cpp does)
         begin_launch(ARAP_K_MISC);
         dense_from_csr_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, d_rowptr.ptr, d_colidx.ptr, d_val.ptr, shift, d_M.ptr);
-        const dim3 ugrid((unsigned)grid_for((size_t)n), (unsigned)n, 1);
-        for (int c = 0; c < n; ++c) {
-            gj_pivot_kernel<<<1, 1024, 0, stream>>>(n, c, d_M.ptr, d_col.ptr, d_bad.ptr);
-            gj_update_kernel<<<ugrid, kBlock, 0, stream>>>(n, c, d_M.ptr, d_col.ptr);
+        const dim3 ugrid((unsigned)((n + 15) / 16), (unsigned)((n + 15) / 16), 1);
+        const int copy_ctas = std::max(1, std::min(64, (n * kGjB + 1023) / 1024));
+        for (int k0 = 0; k0 < n; k0 += kGjB) {                  // blocked Gauss-Jordan: three launches per panel of 32 pivots
+            const int nb = std::min(kGjB, n - k0);
+            gj_panel_kernel<<<1 + copy_ctas, 1024, 0, stream>>>(n, k0, nb, d_M.ptr, d_D.ptr, d_C.ptr, d_bad.ptr);
+            gj_row_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, k0, nb, d_M.ptr, d_D.ptr, d_R.ptr);
+            gj_update_kernel<<<ugrid, 256, 0, stream>>>(n, k0, nb, d_M.ptr, d_C.ptr, d_R.ptr, d_D.ptr);
         }
         mg_coarse_ld = (n + 3) & ~3;
         ARAP_CUDA(mg_coarse_inv.ensure((size_t)n * mg_coarse_ld));
@@ -1177,43 +1288,44 @@ public:
         MgVec *z = m0.x2.ptr;
         // down
         { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
-        LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
+        LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
                free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
         { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec), SITE_MG0_R); if (rc) return rc; }
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
-            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH_PDL(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
                                                   c.x.ptr, cg.ptr));
             if (l + 1 == L - 1) break;
             { int rc = exchange_level(l + 1, 0, c.x.ptr); if (rc) return rc; }
-            ARAP_DISPATCH_LANES(c.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+            ARAP_DISPATCH_LANES(c.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   c.a_rowptr.ptr, c.a_colidx.ptr, c.a_val.ptr, c.b.ptr, c.x.ptr, c.r.ptr, cg.ptr));
             { int rc = exchange_level(l + 1, 1, c.r.ptr); if (rc) return rc; }
         }
         // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
         MgLevelDev &cl = *mg[L - 1];
         if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
+        pdl_next_plain = true;
         launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             const int rows = (l == 0) ? R : f.n;
             if (l + 1 < L - 1) { int rc = exchange_level(l + 1, 2, c.x2.ptr); if (rc) return rc; }
-            LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+            LAUNCH_PDL(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                    c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
                 { int rc = exchange_halo(f.x.ptr, sizeof(MgVec), SITE_MG0_X_POST); if (rc) return rc; }
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
+                LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
                        hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
                 { int rc = exchange_level(l, 3, f.x.ptr); if (rc) return rc; }
-                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
-        return reduce_stage(CG_STAGE_RHO, 4);
+        return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg (one GPU) / cg->red (partitioned: CG_STAGE_MERGED)
     }
 
     // Which levels the one-kernel tail covers: from the first level with at most ARAP_TAIL_ROWS rows down to the coarsest,
@@ -1273,8 +1385,8 @@ public:
 
     void launch_dense_solve(int n, const MgVec *b, MgVec *x) {
         begin_launch(ARAP_K_MG_DENSE_SOLVE);
-        mg_dense_solve_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kBlock, sizeof(MgVec) * (size_t)mg_coarse_ld, stream>>>(
-            n, mg_coarse_ld, mg_coarse_inv.ptr, b, x, cg.ptr);
+        launch_pdl(mg_dense_solve_kernel, (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)kBlock, sizeof(MgVec) * (size_t)mg_coarse_ld,
+                   n, mg_coarse_ld, (const float *)mg_coarse_inv.ptr, b, x, (const CgScalars *)cg.ptr);
         end_launch();
     }
 
@@ -1303,8 +1415,8 @@ public:
                     mg_batch_dense_kernel<<<grid, 256, 0, stream>>>(member_vertices, mg_coarse_ld, batch_members, mg_coarse_inv.ptr, cg_r.ptr, z, cg.ptr);
                 }
                 end_launch();
-                LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
-                return reduce_stage(CG_STAGE_RHO, 4);
+                LAUNCH_PDL(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg (one GPU) / cg->red (partitioned: CG_STAGE_MERGED)
             }
             LAUNCH(ARAP_K_MISC, mg_to_float_kernel, grid_for((size_t)m0.n), m0.n, cg_r.ptr, m0.x.ptr);
             if (mg_dense) {
@@ -1312,8 +1424,8 @@ public:
             } else {      // no dense inverse (singular coarse operator): plain Jacobi, z = omega D^-1 r
                 LAUNCH(ARAP_K_MISC, mg_jacobi_kernel, grid_for((size_t)m0.n), m0.n, m0.inv_diag.ptr, (float)m0.omega, m0.x.ptr, z);
             }
-            LAUNCH(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
-            return reduce_stage(CG_STAGE_RHO, 4);
+            LAUNCH_PDL(ARAP_K_CG_DOT, cg_dot_rho_f_kernel, reduce_grid(cg_dot_rho_f_kernel, (size_t)R), R, cg_r.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+            return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg (one GPU) / cg->red (partitioned: CG_STAGE_MERGED)
         }
         // down
         // levels [tail_first, L) run inside mg_tail_kernel, which also restricts into and prolongates out of them
@@ -1321,14 +1433,14 @@ public:
         for (int l = 0; l <= top && l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
+                LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
                        free_mask.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
             } else {
-                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.b.ptr, f.x.ptr, f.r.ptr, cg.ptr));
             }
             if (l == top) break;                                       // the tail kernel restricts out of this level itself
-            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
+            ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH_PDL(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
                                                   f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
                                                   c.x.ptr, cg.ptr));
         }
@@ -1340,7 +1452,7 @@ public:
         } else if (mg_dense) {
             launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
         } else {
-            ARAP_DISPATCH_LANES(cl.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)cl.n * LN), cl.n,
+            ARAP_DISPATCH_LANES(cl.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)cl.n * LN), cl.n,
                                                    cl.a_rowptr.ptr, cl.a_colidx.ptr, cl.a_val.ptr, cl.inv_diag.ptr, (float)cl.omega, cl.b.ptr,
                                                    cl.x.ptr, cl.x2.ptr, cg.ptr));
         }
@@ -1349,18 +1461,18 @@ public:
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             const int rows = (l == 0) ? R : f.n;
             if (!(tail_first > 0 && l == top))                         // the tail kernel already prolongated into its parent
-                LAUNCH(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
+                LAUNCH_PDL(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                        c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
+                LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
                        hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
+                ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
                                                       f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
-        return reduce_stage(CG_STAGE_RHO, 4);
+        return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg (one GPU) / cg->red (partitioned: CG_STAGE_MERGED)
     }
 
     bool use_tma = getenv("ARAP_TMA") != nullptr && atoi(getenv("ARAP_TMA")) != 0;
@@ -1373,7 +1485,7 @@ public:
                 R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
             end_launch();
         } else {
-            LAUNCH(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr,
+            LAUNCH_PDL(ARAP_K_CG_SPMV, cg_spmv_kernel<S>, reduce_grid(cg_spmv_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr,
                    cg_d.ptr, cg_ad.ptr, partials.ptr, counter.ptr, cg.ptr);
         }
     }
@@ -1383,25 +1495,30 @@ public:
         { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
         launch_spmv();
         { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)R), R, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
+        LAUNCH_PDL(ARAP_K_CG_UPDATE, cg_update_kernel, reduce_grid(cg_update_kernel, (size_t)R), R, inv_diag.ptr, cg_d.ptr, cg_ad.ptr, cg_x.ptr, cg_r.ptr, partials.ptr,
                counter.ptr, cg.ptr);
         { int rc = reduce_stage(CG_STAGE_UPDATE_JACOBI, 4); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_DIRECTION, cg_direction_kernel, grid_for((size_t)R), R, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
+        LAUNCH_PDL(ARAP_K_CG_DIRECTION, cg_direction_kernel, grid_for((size_t)R), R, inv_diag.ptr, cg_r.ptr, cg_d.ptr, cg.ptr);
         return ARAP_OK;
     }
 
-    int cg_iteration_mg() {
+    // One iteration of the multigrid-preconditioned CG in its single-reduction form (kernels.cuh, CgStage):
+    //   z = V-cycle(r) [gamma = r.z, position-error norm]; halo of z; w = A z [delta = z.w]; ONE all-reduce (partitioned);
+    //   d = z + beta d, s = w + beta s, x += alpha d, r -= alpha s, x0 = omega D^-1 r for the next V-cycle [|r|^2].
+    // `loop`: the conditional handle of the step graph's WHILE node when this is captured as its body, else 0.
+    int cg_iteration_mg(unsigned long long loop = 0) {
         const int R = n_rows;
-        const int n3 = 3 * R, G3 = grid_for(((size_t)n3 + 1) / 2);
+        const int n3 = 3 * R;
         MgLevelDev &m0 = *mg[0];
         { int rc = vcycle(); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_DIRECTION_MG, cg_direction_mg_kernel, G3, n3, (const float *)m0.x2.ptr, (double *)cg_d.ptr, cg.ptr);
-        { int rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D); if (rc) return rc; }
-        launch_spmv();
-        { int rc = reduce_stage(CG_STAGE_ALPHA, 3); if (rc) return rc; }
-        LAUNCH(ARAP_K_CG_UPDATE_MG, cg_update_mg_kernel, reduce_grid(cg_update_mg_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega, (const double *)cg_d.ptr,
-               (const double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr, (float *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
-        return reduce_stage(CG_STAGE_UPDATE_MG, 1);
+        { int rc = exchange_halo(m0.x2.ptr, sizeof(MgVec), SITE_CG_D); if (rc) return rc; }
+        LAUNCH_PDL(ARAP_K_CG_SPMV, cg_spmv_z_kernel<S>, reduce_grid(cg_spmv_z_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
+                   free_mask.ptr, (const float4 *)m0.x2.ptr, cg_w.ptr, partials.ptr, counter.ptr, cg.ptr);
+        { int rc = reduce_stage(CG_STAGE_MERGED, 8); if (rc) return rc; }
+        LAUNCH_PDL(ARAP_K_CG_UPDATE_MG, cg_fused_update_kernel, reduce_grid(cg_fused_update_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega,
+                   (const float *)m0.x2.ptr, (const double *)cg_w.ptr, (double *)cg_d.ptr, (double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr,
+                   (float *)m0.x.ptr, partials.ptr, counter.ptr, cg.ptr, loop);
+        return ARAP_OK;
     }
 
     // Capture one CG iteration into a CUDA graph: ~20 small launches collapse into one graph launch.
@@ -1410,17 +1527,115 @@ public:
         std::memset(graph_counts, 0, sizeof(graph_counts));
         ARAP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         capturing = true;
+        pdl_next_plain = true;
         const int rc_body = use_mg ? cg_iteration_mg() : cg_iteration_jacobi();
         capturing = false;
+        pdl_next_plain = true;
         cudaError_t e = cudaStreamEndCapture(stream, &cg_graph);
         if (e != cudaSuccess || rc_body) { cg_graph = nullptr; return fail(ARAP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+        std::memcpy(graph_counts_iter, graph_counts, sizeof(graph_counts_iter));
         ARAP_CUDA(cudaGraphInstantiate(&cg_graph_exec, cg_graph, 0));
+        return ARAP_OK;
+    }
+    int64_t graph_counts_iter[ARAP_K_COUNT_MAX] = {0};
+
+    // ---- the whole ARAP iteration as ONE graph with a device-side loop ---------------------------------------------------
+    //   local step, redo list, right-hand side + residual   ->   WHILE (not converged) { one CG iteration }   ->   p' += x
+    // The WHILE node's condition is set on the device by the kernel that ends the CG iteration (cg_fused_update_kernel), so a
+    // global step needs no host round trip at all: arap_iterate(n) is n graph launches and one synchronisation at the end
+    // (reference loop: arap.h:122-129). Single GPU + multigrid solver; everything else keeps the host-driven loop below.
+    cudaGraph_t step_graph = nullptr;
+    cudaGraphExec_t step_graph_exec = nullptr;
+    int64_t step_counts[ARAP_K_COUNT_MAX] = {0}, body_counts[ARAP_K_COUNT_MAX] = {0};
+    void destroy_step_graph() {
+        if (step_graph_exec) cudaGraphExecDestroy(step_graph_exec);
+        if (step_graph) cudaGraphDestroy(step_graph);
+        step_graph_exec = nullptr;
+        step_graph = nullptr;
+    }
+
+    void launch_step_head() {
+        const int R = n_rows, G = grid_for((size_t)R);
+        MgLevelDev &m0 = *mg[0];
+        // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the hot kernel
+        // certifies convergence to the SVD's rotation per vertex and lists the vertices that need the Jacobi SVD.
+        LAUNCH_PDL(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+                   redo_list.ptr, redo_count.ptr);
+        LAUNCH_PDL(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                   quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
+        LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
+                   hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+    }
+
+    int build_step_graph() {
+        destroy_step_graph();
+        if (transport || !use_mg || mg.empty()) return ARAP_OK;
+        if (getenv("ARAP_STEP_GRAPH") && atoi(getenv("ARAP_STEP_GRAPH")) == 0) return ARAP_OK;
+        const int R = n_rows, G = grid_for((size_t)R);
+        cudaGraphConditionalHandle handle = 0;
+        cudaGraph_t body = nullptr, captured = nullptr;
+        bool ok = cudaGraphCreate(&step_graph, 0) == cudaSuccess &&
+                  cudaGraphConditionalHandleCreate(&handle, step_graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        // head: local step + right-hand side
+        if (ok) ok = cudaStreamBeginCaptureToGraph(stream, step_graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            capturing = true;
+            std::memset(graph_counts, 0, sizeof(graph_counts));
+            pdl_next_plain = true;
+            launch_step_head();
+            // the WHILE node hangs off whatever the capture currently ends in; the capture then continues behind it
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            const cudaGraphNode_t *deps = nullptr;
+            const cudaGraphEdgeData *edges = nullptr;
+            size_t n_deps = 0;
+            ok = cudaStreamGetCaptureInfo_v3(stream, &st, nullptr, nullptr, &deps, &edges, &n_deps) == cudaSuccess && st == cudaStreamCaptureStatusActive;
+            cudaGraphNode_t cond = nullptr;
+            if (ok) {
+                cudaGraphNodeParams np = {};
+                np.type = cudaGraphNodeTypeConditional;
+                np.conditional.handle = handle;
+                np.conditional.type = cudaGraphCondTypeWhile;
+                np.conditional.size = 1;
+                std::vector<cudaGraphNode_t> dep_nodes(deps, deps + n_deps);
+                ok = cudaGraphAddNode(&cond, step_graph, dep_nodes.data(), n_deps, &np) == cudaSuccess && np.conditional.phGraph_out != nullptr;
+                if (ok) body = np.conditional.phGraph_out[0];
+            }
+            if (ok) ok = cudaStreamUpdateCaptureDependencies(stream, &cond, 1, cudaStreamSetCaptureDependencies) == cudaSuccess;
+            if (ok) {
+                pdl_next_plain = true;                                  // no programmatic edge out of a conditional node
+                LAUNCH_PDL(ARAP_K_APPLY, apply_update_kernel<S>, G, R, free_mask.ptr, cg_x.ptr, cur4.ptr, cg.ptr, 1);
+            }
+            std::memcpy(step_counts, graph_counts, sizeof(step_counts));
+            capturing = false;
+            pdl_next_plain = true;
+            const cudaError_t e = cudaStreamEndCapture(stream, &captured);
+            ok = ok && e == cudaSuccess;
+        }
+        // body: one CG iteration, closed by the kernel that sets the loop condition
+        if (ok) ok = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            capturing = true;
+            std::memset(graph_counts, 0, sizeof(graph_counts));
+            pdl_next_plain = true;
+            const int rc_body = cg_iteration_mg((unsigned long long)handle);
+            std::memcpy(body_counts, graph_counts, sizeof(body_counts));
+            capturing = false;
+            pdl_next_plain = true;
+            cudaGraph_t body_out = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(stream, &body_out);
+            ok = e == cudaSuccess && rc_body == ARAP_OK;
+        }
+        if (ok) ok = cudaGraphInstantiate(&step_graph_exec, step_graph, 0) == cudaSuccess;
+        if (!ok) {                                                       // not fatal: the host-driven loop does the same work
+            cudaGetLastError();
+            destroy_step_graph();
+        }
         return ARAP_OK;
     }
 
     inline int issue_cg_iteration() {
         if (cg_graph_exec && !profile_events) {
-            for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) profile.launches[k] += graph_counts[k];
+            for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) profile.launches[k] += graph_counts_iter[k];
             ARAP_CUDA(cudaGraphLaunch(cg_graph_exec, stream));
         } else if (use_mg) {
             return cg_iteration_mg();
@@ -1430,16 +1645,17 @@ public:
         return ARAP_OK;
     }
 
+    // Host-driven global step (partitioned mode, Jacobi-PCG, profiling passes, or when the step graph is unavailable).
     int global_step() {
         const int R = n_rows, G = grid_for((size_t)R);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                       quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
             { int rc = reduce_stage(CG_STAGE_START_MG, 5); if (rc) return rc; }
         } else {
-            LAUNCH(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                       quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
             { int rc = reduce_stage(CG_STAGE_START_JACOBI, 5); if (rc) return rc; }
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
@@ -1461,6 +1677,7 @@ public:
             issued += batch;
             ARAP_CUDA(cudaMemcpyAsync(&cg_host[slot], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
             ARAP_CUDA(cudaEventRecord(poll_event[slot], stream));
+            pdl_next_plain = true;
             have_poll[slot] = true;
             const int prev = slot ^ 1;
             if (have_poll[prev]) {
@@ -1470,42 +1687,81 @@ public:
             if (issued >= max_it || batch == 0) done = true;
             slot ^= 1;
         }
-        LAUNCH(ARAP_K_APPLY, apply_update_kernel<S>, G, R, free_mask.ptr, cg_x.ptr, cur4.ptr);
+        LAUNCH_PDL(ARAP_K_APPLY, apply_update_kernel<S>, G, R, free_mask.ptr, cg_x.ptr, cur4.ptr, cg.ptr, 1);
         { int rc = exchange_halo(cur4.ptr, sizeof(Vec4T<S>), SITE_CUR4); if (rc) return rc; }
         ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        pdl_next_plain = true;
         if (transport && transport->poll_error()) return fail(ARAP_ERR_CUDA, transport->error);
         ARAP_CUDA(cudaGetLastError());
-        stats.global_steps += 1;
-        stats.cg_iterations_total += cg_host[0].iterations;
         stats.last_cg_iterations = cg_host[0].iterations;
-        stats.last_converged = cg_host[0].converged;
-        if (use_mg) {
-            if (mg_fresh && mg_fresh_iterations == 0) mg_fresh_iterations = cg_host[0].iterations > 0 ? cg_host[0].iterations : 1;
-            else if (!mg_fresh && mg_fresh_iterations > 0 && cg_host[0].iterations > (3 * mg_fresh_iterations) / 2 + 3) mg_stale = true;
-        }
-        stats.last_relative_residual = cg_host[0].ref2 > 0 ? sqrt(cg_host[0].rr / cg_host[0].ref2) : 0.0;
-        stats.last_position_error = cg_host[0].z8_tol > 0 ? std::pow(cg_host[0].z8, 0.125) : 0.0;
-        if (!(cg_host[0].rr == cg_host[0].rr)) return fail(ARAP_ERR_SOLVER, "global step: CG residual is NaN");
         return ARAP_OK;
     }
 
-    int iterate(int n) override {
+    // Fold the device-side bookkeeping of the global steps since the last call (CgScalars::steps ...) into `stats`.
+    // cg_host[0] must hold a copy of *cg taken after the last step; the device counters are reset for the next batch.
+    int book_steps() {
+        const CgScalars &c = cg_host[0];
+        if (c.steps > 0) {
+            if (use_mg) {
+                if (mg_fresh && mg_fresh_iterations == 0) mg_fresh_iterations = c.first_step_iterations > 0 ? c.first_step_iterations : 1;
+                else if (!mg_fresh && mg_fresh_iterations > 0 && c.iterations > (3 * mg_fresh_iterations) / 2 + 3) mg_stale = true;
+            }
+            stats.global_steps += c.steps;
+            stats.cg_iterations_total += c.iterations_total;
+            stats.last_cg_iterations = c.iterations;
+            stats.last_converged = c.converged;
+            unconverged_steps += c.unconverged_steps;
+            stats.last_relative_residual = c.ref2 > 0 ? sqrt(c.rr / c.ref2) : 0.0;
+            stats.last_position_error = c.z8_tol > 0 ? std::pow(c.z8, 0.125) : 0.0;
+            if (step_graph_exec && !profile_events)                  // launches the step graphs made (body runs: one per CG iteration +
+                for (int k = 0; k < ARAP_K_COUNT_MAX; ++k)           // the pass that notices convergence)
+                    profile.launches[k] += (int64_t)c.steps * step_counts[k] + c.body_runs_total * body_counts[k];
+        }
+        ARAP_CUDA(cudaMemsetAsync((char *)cg.ptr + offsetof(CgScalars, iterations_total), 0, sizeof(CgScalars) - offsetof(CgScalars, iterations_total), stream));
+        if (!(c.rr == c.rr)) return fail(ARAP_ERR_SOLVER, "global step: CG residual is NaN");
+        return ARAP_OK;
+    }
+    int unconverged_steps = 0;
+
+    // `defer_sync`: leave the final synchronisation to the caller (arap_deform: the write-back's copy synchronises anyway);
+    // finish_iterate() must follow once the stream is known to be idle.
+    bool iterate_pending = false;
+    int iterate(int n, bool defer_sync = false) override {
         if (!prepared) return fail(ARAP_ERR_INVALID, "iterate: arap_prepare has not succeeded");
+        if (dirty) return fail(ARAP_ERR_INVALID, "iterate: the handle is dirty (constraints changed since the last arap_prepare): call arap_prepare or arap_deform");
         const int R = n_rows, G = grid_for((size_t)R);
+        unconverged_steps = 0;
+        if (n <= 0) return ARAP_OK;
+        if (step_graph_exec && !profile_events) {
+            for (int it = 0; it < n; ++it) ARAP_CUDA(cudaGraphLaunch(step_graph_exec, stream));
+            ARAP_CUDA(cudaMemcpyAsync(&cg_host[0], cg.ptr, sizeof(CgScalars), cudaMemcpyDeviceToHost, stream));
+            pdl_next_plain = true;
+            iterate_pending = true;
+            if (defer_sync) return ARAP_OK;
+            return finish_iterate();
+        }
         for (int it = 0; it < n; ++it) {
-            // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the hot kernel
-            // certifies convergence to the SVD's rotation per vertex and lists the vertices that need the Jacobi SVD.
-            LAUNCH(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
-                   redo_list.ptr, redo_count.ptr);
-            LAUNCH(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
+            LAUNCH_PDL(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+                       redo_list.ptr, redo_count.ptr);
+            LAUNCH_PDL(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                       quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
             { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>), SITE_QUAT); if (rc) return rc; }
             int rc = global_step();
             if (rc) return rc;
         }
         ARAP_CUDA(cudaGetLastError());
-        return ARAP_OK;
+        { int rc = book_steps(); if (rc) return rc; }
+        return unconverged_steps > 0 ? ARAP_NOT_CONVERGED : ARAP_OK;
+    }
+
+    int finish_iterate() override {
+        if (!iterate_pending) return ARAP_OK;
+        iterate_pending = false;
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        { int rc = book_steps(); if (rc) return rc; }
+        return unconverged_steps > 0 ? ARAP_NOT_CONVERGED : ARAP_OK;
     }
 
     int get_positions(void *out, int scalar_bytes) override {
@@ -1550,6 +1806,30 @@ public:
         LAUNCH(ARAP_K_MISC, export_rotations_kernel<S>, grid_for((size_t)V), V, perm.ptr, quat.ptr, (S *)staging.ptr);
         ARAP_CUDA(cudaMemcpyAsync(rot9, staging.ptr, sizeof(S) * 9 * (size_t)V, cudaMemcpyDeviceToHost, stream));
         ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+    // _b (arap.h:393-414) for the current rotations, nF x 3 doubles in free-index order: runs the hot right-hand-side kernel
+    // exactly as a global step would and rebuilds b from its output (export_rhs_kernel). Inspection / tests only.
+    int get_rhs(double *out) override {
+        if (!prepared || dirty) return fail(ARAP_ERR_INVALID, "get_rhs: call arap_prepare first");
+        if (transport) return fail(ARAP_ERR_INVALID, "get_rhs: not available on a partitioned handle");
+        const int R = n_rows;
+        pdl_next_plain = true;
+        if (use_mg) {
+            MgLevelDev &m0 = *mg[0];
+            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
+                       hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
+                       hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+        }
+        pdl_next_plain = true;
+        ARAP_CUDA(staging.ensure(sizeof(double) * 3 * (size_t)(n_free > 0 ? n_free : 1)));
+        LAUNCH(ARAP_K_MISC, export_rhs_kernel<S>, grid_for((size_t)R), R, perm.ptr, free_idx.ptr, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
+               free_mask.ptr, cur4.ptr, cg_r.ptr, (double *)staging.ptr);
+        ARAP_CUDA(cudaMemcpyAsync(out, staging.ptr, sizeof(double) * 3 * (size_t)n_free, cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
         return ARAP_OK;
     }
     int energy(double *e) override {
@@ -1676,9 +1956,13 @@ int arap_deform(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32
         int rc = h->engine->prepare(mesh_xyz, mesh_scalar_bytes);
         if (rc != ARAP_OK) return rc;                                     /* UNCONSTRAINED -> true, no write-back (:113-114) */
     }
-    int rc = h->engine->iterate(n_iterations);
-    if (rc != ARAP_OK) return rc;
-    return h->engine->get_positions(mesh_xyz, mesh_scalar_bytes);         /* arap.h:133-135 */
+    int rc = h->engine->iterate(n_iterations, /*defer_sync=*/true);      /* the write-back below synchronises once for both */
+    if (rc < 0) return rc;
+    const int rc_pos = h->engine->get_positions(mesh_xyz, mesh_scalar_bytes);   /* arap.h:133-135 */
+    const int rc_fin = h->engine->finish_iterate();
+    if (rc_fin < 0) return rc_fin;
+    if (rc_pos != ARAP_OK) return rc_pos;
+    return rc_fin > 0 ? rc_fin : rc;                                       /* ARAP_NOT_CONVERGED */
 }
 
 int arap_get_csr_nnz(arap_handle *h, int32_t *nnz) {
@@ -1699,6 +1983,11 @@ int arap_get_rotations(arap_handle *h, void *rot9) {
     ARAP_ENGINE_OR_FAIL(h);
     if (!rot9) return ARAP_ERR_INVALID;
     return h->engine->get_rotations(rot9);
+}
+int arap_get_rhs(arap_handle *h, double *rhs) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!rhs) return ARAP_ERR_INVALID;
+    return h->engine->get_rhs(rhs);
 }
 int arap_energy(arap_handle *h, double *energy) {
     ARAP_ENGINE_OR_FAIL(h);
@@ -1764,6 +2053,10 @@ int arap_batch_create(const int32_t *faces, int32_t n_faces, int32_t n_vertices,
                       const arap_options *opt, arap_batch **out) {
     if (!out) return ARAP_ERR_INVALID;
     *out = nullptr;
+    if ((n_faces > 0 && !faces)) {
+        arap::g_create_error = "arap_batch_create: null face array";
+        return ARAP_ERR_INVALID;
+    }
     if (batch_size <= 0 || n_vertices < 0 || n_faces < 0 || (long long)batch_size * n_vertices > 2000000000LL ||
         (long long)batch_size * n_faces * 6 > 2000000000LL) {
         arap::g_create_error = "arap_batch_create: bad sizes (batch x vertices must fit int32)";

@@ -110,15 +110,22 @@ __global__ void __launch_bounds__(kBlock) weights_fill_kernel(const int *__restr
     }
 }
 
+constexpr int kLongRow = 64;     // raw triplets per row above which one thread's insertion sort (O(d^2)) is handed to a CTA
+
 // K2a: setFromTriplets for one row (arap.h:238): sort the row's raw triplets by (column, insertion order),
 // sum duplicates in insertion order, leave the unique entries at the front of the raw segment.
 template <typename S>
 __global__ void __launch_bounds__(kBlock) row_sort_merge_kernel(int n_rows, const int *__restrict__ raw_rowptr, int *__restrict__ raw_col,
                                                                 S *__restrict__ raw_val, unsigned *__restrict__ raw_tag,
-                                                                int *__restrict__ unique_count) {
+                                                                int *__restrict__ unique_count, int *__restrict__ long_rows,
+                                                                int *__restrict__ long_count) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int lo = raw_rowptr[r], hi = raw_rowptr[r + 1];
+    if (hi - lo > kLongRow) {                                        // fan centre / pole: sorted by a whole CTA (row_sort_long_kernel)
+        long_rows[atomicAdd(long_count, 1)] = r;
+        return;
+    }
     for (int a = lo + 1; a < hi; ++a) {                              // insertion sort: rows are ~12 entries long
         const int cj = raw_col[a]; const S cv = raw_val[a]; const unsigned ct = raw_tag[a];
         int b = a - 1;
@@ -137,6 +144,55 @@ __global__ void __launch_bounds__(kBlock) row_sort_merge_kernel(int n_rows, cons
         raw_col[out] = cj; raw_val[out] = s; ++out;
     }
     unique_count[r] = out - lo;
+}
+
+// K2a for the rows row_sort_merge_kernel skipped (vertices of very high valence: the centre of a triangle fan, the pole
+// of a UV sphere): one CTA per row sorts the row's triplets by (column, insertion order) with a bitonic network whose
+// comparators all point the same way ("flip" variant), so a row of any length is sorted as if it were padded with +inf
+// to the next power of two; then one thread sums the duplicates in insertion order, as above. O(d log^2 d / 256).
+template <typename S>
+__global__ void __launch_bounds__(kBlock) row_sort_long_kernel(const int *__restrict__ long_rows, const int *__restrict__ long_count,
+                                                               const int *__restrict__ raw_rowptr, int *__restrict__ raw_col,
+                                                               S *__restrict__ raw_val, unsigned *__restrict__ raw_tag,
+                                                               int *__restrict__ unique_count) {
+    for (int t = blockIdx.x; t < *long_count; t += gridDim.x) {
+        const int r = long_rows[t];
+        const int lo = raw_rowptr[r], n = raw_rowptr[r + 1] - lo;
+        int *col = raw_col + lo;
+        S *val = raw_val + lo;
+        unsigned *tag = raw_tag + lo;
+        int pow2 = 1;
+        while (pow2 < n) pow2 <<= 1;
+        for (int k = 2; k <= pow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const bool flip = (j == (k >> 1));
+                for (int i = threadIdx.x; i < pow2; i += blockDim.x) {
+                    const int l = flip ? (i ^ (k - 1)) : (i ^ j);
+                    if (l > i && l < n) {
+                        const int ci = col[i], cl = col[l];
+                        const unsigned ti = tag[i], tl = tag[l];
+                        if (ci > cl || (ci == cl && ti > tl)) {
+                            col[i] = cl; col[l] = ci; tag[i] = tl; tag[l] = ti;
+                            const S v = val[i]; val[i] = val[l]; val[l] = v;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            int out = 0;
+            for (int a = 0; a < n;) {
+                const int cj = col[a];
+                S sum = val[a];
+                ++a;
+                while (a < n && col[a] == cj) { sum = add_rn(sum, val[a]); ++a; }
+                col[out] = cj; val[out] = sum; ++out;
+            }
+            unique_count[r] = out;
+        }
+        __syncthreads();
+    }
 }
 
 // K2b: pack the unique entries into the final CSR.
@@ -344,6 +400,7 @@ __global__ void __launch_bounds__(kBlock, ARAP_LOCAL_MIN_BLOCKS) local_step_kern
                                                             const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
                                                             const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
                                                             int *__restrict__ redo_list, int *__restrict__ redo_count) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     S cov[9];
@@ -376,6 +433,7 @@ __global__ void __launch_bounds__(kBlock) local_step_redo_kernel(const int *__re
                                                                  const Vec4T<S> *__restrict__ cur4, Vec4T<S> *__restrict__ quat,
                                                                  const int *__restrict__ redo_list, int *__restrict__ redo_count,
                                                                  unsigned *__restrict__ done_counter) {
+    pdl_enter();
     const int count = *redo_count;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
         const int i = redo_list[t];
@@ -402,9 +460,10 @@ __global__ void __launch_bounds__(kBlock) local_step_redo_kernel(const int *__re
 // Also starts the CG: x = 0, d = z = r / L_ii, rho = r.z, and the reference norm |rhs|^2.
 // =================================================================================================
 struct CgScalars {
-    double rho[3];       // r.z per coordinate
+    double rho[3];       // r.z per coordinate (of the previous iteration once gamma[] holds the current one)
     double alpha[3];
     double beta[3];
+    double gamma[3];     // multigrid CG: r.z of the V-cycle just finished (becomes rho when the iteration's alpha is made)
     double rr;           // |r|^2 over the three coordinates
     double ref2;         // |rhs|^2 over the three coordinates
     double tol2;         // tolerance^2 on |r| / |rhs| (0 = residual criterion off)
@@ -415,22 +474,40 @@ struct CgScalars {
     int converged;
     int iterations;
     int distributed;     // != 0: reduction kernels only deposit their sums in red[]; cg_finalize_kernel finishes the stage
-    int pad;
+    int max_iterations;  // per global step (the device-side loop of the step graph stops there)
+    // bookkeeping of the global steps since the host last read it (one host round trip per arap_iterate, not per step)
+    long long iterations_total;
+    long long body_runs_total;   // executions of the CG iteration's kernel sequence (iterations + the passes that only noticed convergence)
+    int steps, unconverged_steps, first_step_iterations, pad;
 };
 
 // What each grid-wide reduction of the CG turns into. On one GPU the last CTA of the reducing kernel calls this
 // directly; in partitioned mode the sums first go through an all-reduce over the ranks (see partition.cuh).
-enum CgStage { CG_STAGE_START_JACOBI = 0, CG_STAGE_START_MG, CG_STAGE_ALPHA, CG_STAGE_UPDATE_JACOBI, CG_STAGE_UPDATE_MG, CG_STAGE_RHO };
+//
+// Multigrid-preconditioned CG in the single-reduction form (Chronopoulos & Gear 1989): per iteration
+//   z = M^-1 r (V-cycle) ; w = A z ; gamma = r.z ; delta = z.w ;
+//   beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old) ;
+//   d = z + beta d ; s = w + beta s ; x += alpha d ; r -= alpha s
+// so the only matrix-vector product gathers the fp32 V-cycle output (one aligned 16-byte load per neighbour), every
+// vector update is ONE streaming kernel, and all scalars of an iteration come from sums that can travel in one all-reduce
+// (gamma, the position-error norm, delta, and |r|^2 of the previous update: CG_STAGE_MERGED).
+enum CgStage { CG_STAGE_START_JACOBI = 0, CG_STAGE_START_MG, CG_STAGE_ALPHA, CG_STAGE_UPDATE_JACOBI, CG_STAGE_UPDATE_MG, CG_STAGE_GAMMA,
+               CG_STAGE_DELTA, CG_STAGE_MERGED };
 
 __device__ __forceinline__ void cg_finalize(CgScalars *cg, int stage, const double *t) {
     switch (stage) {
         case CG_STAGE_START_JACOBI:      // t = rho x,y,z ; |r|^2 ; |rhs|^2
         case CG_STAGE_START_MG:
-            for (int c = 0; c < 3; ++c) cg->rho[c] = (stage == CG_STAGE_START_MG) ? 0.0 : t[c];
+            for (int c = 0; c < 3; ++c) {
+                cg->rho[c] = (stage == CG_STAGE_START_MG) ? 0.0 : t[c];
+                cg->alpha[c] = 0.0;
+                cg->beta[c] = 0.0;
+            }
             cg->rr = t[3];
             cg->ref2 = t[4];
             cg->iterations = 0;
             cg->converged = (t[3] <= cg->tol2 * t[4]) ? 1 : 0;
+            cg->red[7] = -1.0;           // CG_STAGE_MERGED: no |r|^2 of a previous update yet
             break;
         case CG_STAGE_ALPHA:             // t = d.Ad per coordinate
             for (int c = 0; c < 3; ++c) cg->alpha[c] = (t[c] > 0.0) ? cg->rho[c] / t[c] : 0.0;
@@ -446,14 +523,10 @@ __device__ __forceinline__ void cg_finalize(CgScalars *cg, int stage, const doub
             break;
         case CG_STAGE_UPDATE_MG:         // t = |r|^2
             cg->rr = t[0];
-            cg->iterations += 1;
             if (t[0] <= cg->tol2 * cg->ref2) cg->converged = 1;
             break;
-        case CG_STAGE_RHO:               // t = r.z per coordinate ; sum_i (|z_i| / length)^8
-            for (int c = 0; c < 3; ++c) {
-                cg->beta[c] = (cg->rho[c] > 0.0) ? t[c] / cg->rho[c] : 0.0;
-                cg->rho[c] = t[c];
-            }
+        case CG_STAGE_GAMMA:             // t = r.z per coordinate ; sum_i (|z_i| / length)^8
+            for (int c = 0; c < 3; ++c) cg->gamma[c] = t[c];
             // z = M^-1 r with M^-1 one multigrid V-cycle is, up to the quality of the preconditioner (~ +-40 %), the ERROR
             // A^-1 r of the current iterate, in position units. Its 8-norm is a smooth stand-in for the largest per-vertex
             // error (max <= 8-norm <= V^(1/8) max) that can be summed -- and all-reduced -- like every other CG scalar.
@@ -465,26 +538,49 @@ __device__ __forceinline__ void cg_finalize(CgScalars *cg, int stage, const doub
             cg->z8 = t[3];
             if (cg->z8_tol > 0.0 && t[3] <= cg->z8_tol) cg->converged = 1;
             break;
+        case CG_STAGE_DELTA:             // t = z.w per coordinate -> beta, alpha of this iteration
+            for (int c = 0; c < 3; ++c) {
+                const double g = cg->gamma[c], a_old = cg->alpha[c];
+                const double beta = (cg->rho[c] > 0.0 && a_old != 0.0) ? g / cg->rho[c] : 0.0;
+                const double denom = t[c] - (beta != 0.0 ? beta * g / a_old : 0.0);      // = d.Ad of the new direction
+                cg->beta[c] = beta;
+                cg->alpha[c] = (denom > 0.0) ? g / denom : 0.0;
+                cg->rho[c] = g;
+            }
+            cg->iterations += 1;
+            break;
+        case CG_STAGE_MERGED:            // partitioned mode: t = gamma[3], z8, delta[3], |r|^2 after the previous update (< 0: none)
+            if (t[7] >= 0.0) {
+                cg->rr = t[7];
+                if (t[7] <= cg->tol2 * cg->ref2) cg->converged = 1;
+            }
+            if (!cg->converged) {
+                cg_finalize(cg, CG_STAGE_GAMMA, t);
+                if (!cg->converged) cg_finalize(cg, CG_STAGE_DELTA, t + 4);
+            }
+            break;
     }
 }
 
+// `slot`: where a distributed stage keeps its sums in red[] until the all-reduce (CG_STAGE_MERGED packs three kernels' sums)
 template <int N>
-__device__ __forceinline__ void cg_finish_reduction(CgScalars *cg, int stage, const double (&total)[N]) {
+__device__ __forceinline__ void cg_finish_reduction(CgScalars *cg, int stage, const double (&total)[N], int slot = 0) {
     if (cg->distributed) {
 #pragma unroll
-        for (int c = 0; c < N; ++c) cg->red[c] = total[c];
+        for (int c = 0; c < N; ++c) cg->red[slot + c] = total[c];
     } else {
         cg_finalize(cg, stage, total);
     }
 }
 
 __global__ void cg_finalize_kernel(CgScalars *cg, int stage) {
+    pdl_enter();
     if (cg->converged && stage != CG_STAGE_START_JACOBI && stage != CG_STAGE_START_MG) return;
     cg_finalize(cg, stage, cg->red);
 }
 
 // MG = false: Jacobi-preconditioned start (d = z = D^-1 r, rho = r.z).
-// MG = true : multigrid start (d = 0, rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
+// MG = true : multigrid start (rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
 // (A variant with 8 lanes per vertex and a shuffle reduction of the nine partial sums measured 4x slower: 383 us.)
 template <typename S, bool MG>
 __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
@@ -495,6 +591,7 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                                                               Vec3d *__restrict__ x_out, float4 *__restrict__ x0_out,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
+    pdl_enter();
     double red[5] = {0, 0, 0, 0, 0};   // rho x,y,z ; rr ; ref2
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Vec4T<S> pi = load4<S>(&rest4[i]);
@@ -554,11 +651,10 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
             red[4] += rhs0 * rhs0 + rhs1 * rhs1 + rhs2 * rhs2;
         }
         r_out[i] = r;
-        x_out[i] = Vec3d{0, 0, 0};
-        if (MG) {
-            d_out[i] = Vec3d{0, 0, 0};
+        if (MG) {      // x, d, s need no reset: the first update of a solve overwrites them (cg_fused_update_kernel)
             x0_out[i] = make_float4((float)(omega0 * z.x), (float)(omega0 * z.y), (float)(omega0 * z.z), 0.f);
         } else {
+            x_out[i] = Vec3d{0, 0, 0};
             d_out[i] = z;
         }
     }
@@ -578,6 +674,7 @@ __global__ void __launch_bounds__(kBlock, ARAP_SPMV_MIN_BLOCKS) cg_spmv_kernel(i
                                                          const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
                                                          double *__restrict__ partials, unsigned *__restrict__ counter,
                                                          CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     double red[3] = {0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -628,6 +725,7 @@ __global__ void __launch_bounds__(kBlock) cg_spmv_tma_kernel(int n, const int *_
                                                              const Vec3d *__restrict__ d, Vec3d *__restrict__ ad,
                                                              double *__restrict__ partials, unsigned *__restrict__ counter,
                                                              CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     extern __shared__ __align__(16) unsigned char tma_smem[];
     S *const s_w0 = reinterpret_cast<S *>(tma_smem);                                                       // [2][kTmaStageEntries]
@@ -697,6 +795,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
                                                            const Vec3d *__restrict__ ad, Vec3d *__restrict__ x, Vec3d *__restrict__ r,
                                                            double *__restrict__ partials, unsigned *__restrict__ counter,
                                                            CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     double red[4] = {0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -714,23 +813,10 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(int n, const double *
     if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_UPDATE_JACOBI, total);
 }
 
-// rho_new = r . z (per coordinate) and beta = rho_new / rho: used when the preconditioner's last kernel cannot fuse it.
-__global__ void __launch_bounds__(kBlock) cg_dot_rho_kernel(int n, const Vec3d *__restrict__ r, const Vec3d *__restrict__ z,
-                                                            double *__restrict__ partials, unsigned *__restrict__ counter,
-                                                            CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
-    double red[4] = {0, 0, 0, 1e300};      // [3]: the position-error sum of CG_STAGE_RHO; this (unpreconditioned) path has none
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Vec3d ri = r[i], zi = z[i];
-        red[0] += ri.x * zi.x; red[1] += ri.y * zi.y; red[2] += ri.z * zi.z;
-    }
-    double total[4];
-    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
-}
-
 // d = z + beta d. Launched after cg_update; skipped (like everything else) once converged.
 __global__ void __launch_bounds__(kBlock) cg_direction_kernel(int n, const double *__restrict__ inv_diag, const Vec3d *__restrict__ r,
                                                               Vec3d *__restrict__ d, const CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -743,12 +829,148 @@ __global__ void __launch_bounds__(kBlock) cg_direction_kernel(int n, const doubl
     d[i] = di;
 }
 
+
+// ---- multigrid-preconditioned CG, single-reduction form (see CgStage above) -----------------------------------------
+// w = A z on the free rows, A matrix-free on the one-ring CSR with the exact (handle precision) weights; z is the fp32
+// V-cycle output, so every neighbour is ONE aligned 16-byte gather; the sum runs in fp64. Fused delta = z . w.
+template <typename S>
+__global__ void __launch_bounds__(kBlock, ARAP_SPMV_MIN_BLOCKS) cg_spmv_z_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                           const S *__restrict__ weight, const unsigned char *__restrict__ free_mask,
+                                                           const float4 *__restrict__ z, Vec3d *__restrict__ w_out,
+                                                           double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                           CgScalars *__restrict__ cg) {
+    pdl_enter();
+    if (cg->converged) return;
+    double red[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Vec3d out = {0, 0, 0};
+        if (free_mask[i]) {
+            constexpr int CH = kSpmvChunk;
+            const int k0 = rowptr[i], k1 = rowptr[i + 1];
+            const float4 zi = z[i];
+            for (int k = k0; k < k1; k += CH) {
+                int j[CH];
+                double w[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const bool valid = k + u < k1;
+                    j[u] = valid ? __ldg(&colidx[k + u]) : i;
+                    w[u] = valid ? (double)__ldg(&weight[k + u]) : 0.0;
+                }
+                float4 zj[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) zj[u] = z[j[u]];
+                float gate = zj[0].x;
+#pragma unroll
+                for (int u = 1; u < CH; ++u) gate += zj[u].x;
+                const double g = (double)(0.0f * gate);      // load-batching gate, see gather_gate()
+#pragma unroll
+                for (int u = 0; u < CH; ++u) w[u] += g;
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    out.x += w[u] * ((double)zi.x - (double)zj[u].x);
+                    out.y += w[u] * ((double)zi.y - (double)zj[u].y);
+                    out.z += w[u] * ((double)zi.z - (double)zj[u].z);
+                }
+            }
+            red[0] += (double)zi.x * out.x; red[1] += (double)zi.y * out.y; red[2] += (double)zi.z * out.z;
+        }
+        w_out[i] = out;
+    }
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) cg_finish_reduction<3>(cg, CG_STAGE_DELTA, total, 4);
+}
+
+__device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
+
+// d = z + beta d ; s = w + beta s ; x += alpha d ; r -= alpha s ; x0 = omega_0 D^-1 r (the next V-cycle's pre-smoothed fine
+// iterate) ; |r|^2. The CG vectors are flat arrays of 3V doubles streamed with one coalesced 16-byte access per thread and
+// array (element e = vertex e/3, coordinate e%3). The first update of a solve (iterations == 1) overwrites d, s and x
+// instead of accumulating, so nobody has to zero them. `loop` != 0: this kernel closes the body of the step graph's
+// device-side WHILE node and decides whether the body runs again.
+__global__ void __launch_bounds__(kBlock) cg_fused_update_kernel(int n3, const double *__restrict__ inv_diag, double omega0,
+                                                                 const float *__restrict__ z, const double *__restrict__ w,
+                                                                 double *__restrict__ d, double *__restrict__ s, double *__restrict__ x,
+                                                                 double *__restrict__ r, float *__restrict__ x0,
+                                                                 double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                                 CgScalars *__restrict__ cg, unsigned long long loop) {
+    pdl_enter();
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg->body_runs_total += 1;
+    if (cg->converged) {
+        if (loop && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)loop, 0u);
+        return;
+    }
+    double red[1] = {0};
+    const bool first = cg->iterations == 1;
+    const double al0 = cg->alpha[0], al1 = cg->alpha[1], al2 = cg->alpha[2];
+    const double be0 = cg->beta[0], be1 = cg->beta[1], be2 = cg->beta[2];
+    for (int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x); e < n3; e += 2 * gridDim.x * blockDim.x) {
+        if (e + 1 < n3) {
+            const int c0 = e % 3, c1 = (e + 1) % 3;
+            const int v0 = e / 3, v1 = (e + 1) / 3;
+            const double a0 = pick3(c0, al0, al1, al2), a1 = pick3(c1, al0, al1, al2);
+            const double b0 = pick3(c0, be0, be1, be2), b1 = pick3(c1, be0, be1, be2);
+            const double z0 = (double)z[4 * v0 + c0], z1 = (double)z[4 * v1 + c1];      // z is a float4 per vertex
+            const double2 wv = *reinterpret_cast<const double2 *>(w + e);
+            double2 dv, sv, xv;
+            if (first) {
+                dv = make_double2(z0, z1);
+                sv = wv;
+                xv = make_double2(a0 * z0, a1 * z1);
+            } else {
+                dv = *reinterpret_cast<const double2 *>(d + e);
+                sv = *reinterpret_cast<const double2 *>(s + e);
+                xv = *reinterpret_cast<const double2 *>(x + e);
+                dv.x = z0 + b0 * dv.x; dv.y = z1 + b1 * dv.y;
+                sv.x = wv.x + b0 * sv.x; sv.y = wv.y + b1 * sv.y;
+                xv.x += a0 * dv.x; xv.y += a1 * dv.y;
+            }
+            double2 rv = *reinterpret_cast<const double2 *>(r + e);
+            rv.x -= a0 * sv.x; rv.y -= a1 * sv.y;
+            *reinterpret_cast<double2 *>(d + e) = dv;
+            *reinterpret_cast<double2 *>(s + e) = sv;
+            *reinterpret_cast<double2 *>(x + e) = xv;
+            *reinterpret_cast<double2 *>(r + e) = rv;
+            x0[4 * v0 + c0] = (float)(omega0 * inv_diag[v0] * rv.x);
+            x0[4 * v1 + c1] = (float)(omega0 * inv_diag[v1] * rv.y);
+            red[0] += rv.x * rv.x + rv.y * rv.y;
+        } else {
+            const int c0 = e % 3, v0 = e / 3;
+            const double a0 = pick3(c0, al0, al1, al2), b0 = pick3(c0, be0, be1, be2);
+            const double z0 = (double)z[4 * v0 + c0];
+            const double dv = first ? z0 : z0 + b0 * d[e];
+            const double sv = first ? w[e] : w[e] + b0 * s[e];
+            const double xv = first ? a0 * dv : x[e] + a0 * dv;
+            const double rv = r[e] - a0 * sv;
+            d[e] = dv; s[e] = sv; x[e] = xv; r[e] = rv;
+            x0[4 * v0 + c0] = (float)(omega0 * inv_diag[v0] * rv);
+            red[0] += rv * rv;
+        }
+    }
+    double total[1];
+    if (grid_sum_last_block<1>(red, partials, counter, total)) {
+        cg_finish_reduction<1>(cg, CG_STAGE_UPDATE_MG, total, 7);
+        if (loop) cudaGraphSetConditional((cudaGraphConditionalHandle)loop, (!cg->converged && cg->iterations < cg->max_iterations) ? 1u : 0u);
+    }
+}
+
 // p' += x on the free vertices (the scatter of arap.h:423-428); constrained vertices keep their targets.
+// Also books the finished global step (iteration counts, convergence) in CgScalars, so that the host reads the solver's
+// statistics once per arap_iterate instead of once per step.
 template <typename S>
 __global__ void __launch_bounds__(kBlock) apply_update_kernel(int n, const unsigned char *__restrict__ free_mask, const Vec3d *__restrict__ x,
-                                                              Vec4T<S> *__restrict__ cur4) {
+                                                              Vec4T<S> *__restrict__ cur4, CgScalars *__restrict__ cg, int book) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int its = cg->iterations;
+    if (book && i == 0) {
+        if (cg->steps == 0) cg->first_step_iterations = its;
+        cg->steps += 1;
+        cg->iterations_total += its;
+        if (!cg->converged) cg->unconverged_steps += 1;
+    }
     if (i >= n) return;
+    if (its == 0) return;              // the start residual already met the stopping rule: x was never written
     if (!free_mask[i]) return;
     const Vec4T<S> c = cur4[i];
     const Vec3d xi = x[i];
@@ -786,6 +1008,32 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(int n, const int *__rest
     }
     double total[1];
     if (grid_sum_last_block<1>(red, partials, counter, total)) *energy_out = total[0];
+}
+
+// _b of the reference (arap.h:393-414: bFixed + the rotated edge sums) for the free vertices, in free-index order, rebuilt from
+// what the hot kernel computed: rhs_residual_kernel leaves r = b - L p' (with the constrained neighbours' targets folded into
+// the left-hand side), so b_i = r_i + sum_j w_ij p'_i - sum_{j free} w_ij p'_j.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) export_rhs_kernel(int n, const int *__restrict__ perm, const int *__restrict__ free_idx_user,
+                                                            const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const S *__restrict__ weight, const unsigned char *__restrict__ free_mask,
+                                                            const Vec4T<S> *__restrict__ cur4, const Vec3d *__restrict__ r,
+                                                            double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !free_mask[i]) return;
+    const Vec4T<S> ci = cur4[i];
+    Vec3d b = r[i];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        const double w = (double)weight[k];
+        b.x += w * (double)ci.x; b.y += w * (double)ci.y; b.z += w * (double)ci.z;
+        if (free_mask[j]) {
+            const Vec4T<S> cj = cur4[j];
+            b.x -= w * (double)cj.x; b.y -= w * (double)cj.y; b.z -= w * (double)cj.z;
+        }
+    }
+    const size_t f = (size_t)free_idx_user[perm[i]];
+    out[3 * f] = b.x; out[3 * f + 1] = b.y; out[3 * f + 2] = b.z;
 }
 
 // ---- readout helpers (internal order -> the user's numbering) -------------------------------------------------

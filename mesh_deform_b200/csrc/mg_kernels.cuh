@@ -25,7 +25,7 @@ __device__ __forceinline__ float gather_gate(const MgVec (&a)[kSpmvChunk]) {
     return 0.0f * s;
 }
 
-// (|z| / length)^8 of one vertex: the summand of the position-error stopping criterion (cg_finalize, CG_STAGE_RHO)
+// (|z| / length)^8 of one vertex: the summand of the position-error stopping criterion (cg_finalize, CG_STAGE_GAMMA)
 __device__ __forceinline__ double z_norm8(const MgVec &z, double inv_len2) {
     const double q = ((double)z.x * z.x + (double)z.y * z.y + (double)z.z * z.z) * inv_len2;
     const double q2 = q * q;
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kBlock) mg_fine_residual_kernel(int n, const i
                                                                   const float *__restrict__ weight, const unsigned char *__restrict__ free_mask,
                                                                   const Vec3d *__restrict__ b, const MgVec *__restrict__ x,
                                                                   MgVec *__restrict__ r, const CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
                                                                     const Vec3d *__restrict__ b, const MgVec *__restrict__ x,
                                                                     MgVec *__restrict__ z, double *__restrict__ partials,
                                                                     unsigned *__restrict__ counter, CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     double red[4] = {0, 0, 0, 0};
     const double inv_len2 = cg->inv_len2;
@@ -103,25 +105,50 @@ __global__ void __launch_bounds__(kBlock) mg_fine_postsmooth_kernel(int n, const
         z[i] = out;
     }
     double total[4];
-    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_GAMMA, total, 0);
 }
 
 // ---- generic CSR levels -------------------------------------------------------------------------------
 // LANES (a power of two <= 32) consecutive threads share one row and reduce with shuffles, so that
 // rows of ~10-25 entries (coarse operators, restriction) still spread over enough threads to fill the GPU.
+// These kernels are a few microseconds of dependent round trips each (rowptr -> colidx/val -> x gather), so the part of
+// the chain that does not depend on the previous kernel -- the matrix, which is constant across iterations -- is loaded
+// BEFORE the programmatic-dependency wait (CsrRowHead) and overlaps the predecessor's tail.
+constexpr int kCsrHead = 4;          // matrix entries per lane held in registers across the wait
+struct CsrRowHead {
+    int k0, k1;                      // this lane's first entry, the row's end
+    int j[kCsrHead];
+    float a[kCsrHead];
+};
 template <int LANES>
-__device__ __forceinline__ float3 csr_apply_row(int row, bool row_valid, const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                                                const float *__restrict__ val, const MgVec *__restrict__ x) {
+__device__ __forceinline__ CsrRowHead csr_row_head(int row, bool row_valid, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                   const float *__restrict__ val) {
+    CsrRowHead h;
+    h.k0 = 0; h.k1 = 0;
+    if (row_valid) { h.k0 = __ldg(&rowptr[row]) + (int)(threadIdx.x & (LANES - 1)); h.k1 = __ldg(&rowptr[row + 1]); }
+#pragma unroll
+    for (int u = 0; u < kCsrHead; ++u) {
+        const int k = h.k0 + u * LANES;
+        const bool valid = k < h.k1;
+        h.j[u] = valid ? __ldg(&colidx[k]) : 0;
+        h.a[u] = valid ? __ldg(&val[k]) : 0.f;
+    }
+    return h;
+}
+template <int LANES>
+__device__ __forceinline__ float3 csr_apply_row(const CsrRowHead &h, const int *__restrict__ colidx, const float *__restrict__ val,
+                                                const MgVec *__restrict__ x) {
     float3 out = {0.f, 0.f, 0.f};
-    const int sub = threadIdx.x & (LANES - 1);
-    if (row_valid) {
-        const int k0 = rowptr[row], k1 = rowptr[row + 1];
-        for (int k = k0 + sub; k < k1; k += LANES) {
-            const int j = __ldg(&colidx[k]);
-            const float a = __ldg(&val[k]);
-            const MgVec xj = __ldg(&x[j]);
-            out.x += a * xj.x; out.y += a * xj.y; out.z += a * xj.z;
-        }
+    MgVec xj[kCsrHead];
+#pragma unroll
+    for (int u = 0; u < kCsrHead; ++u) xj[u] = (h.k0 + u * LANES < h.k1) ? __ldg(&x[h.j[u]]) : MgVec{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < kCsrHead; ++u) { out.x += h.a[u] * xj[u].x; out.y += h.a[u] * xj[u].y; out.z += h.a[u] * xj[u].z; }
+    for (int k = h.k0 + kCsrHead * LANES; k < h.k1; k += LANES) {
+        const int j = __ldg(&colidx[k]);
+        const float a = __ldg(&val[k]);
+        const MgVec v = __ldg(&x[j]);
+        out.x += a * v.x; out.y += a * v.y; out.z += a * v.z;
     }
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) {
@@ -138,9 +165,12 @@ __global__ void __launch_bounds__(kBlock) mg_csr_residual_kernel(int n, const in
                                                                  const float *__restrict__ val, const MgVec *__restrict__ b,
                                                                  const MgVec *__restrict__ x, MgVec *__restrict__ r,
                                                                  const CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
+    pdl_trigger();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const float3 ax = csr_apply_row<LANES>(i, i < n, rowptr, colidx, val, x);
+    const CsrRowHead h = csr_row_head<LANES>(i, i < n, rowptr, colidx, val);
+    pdl_wait();
+    if (cg->converged) return;
+    const float3 ax = csr_apply_row<LANES>(h, colidx, val, x);
     if (i < n && (threadIdx.x & (LANES - 1)) == 0) {
         const MgVec bi = b[i];
         r[i] = MgVec{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z, 0.f};
@@ -154,12 +184,15 @@ __global__ void __launch_bounds__(kBlock) mg_restrict_presmooth_kernel(int nc, c
                                                                        const float *__restrict__ inv_diag_c, float omega_c,
                                                                        MgVec *__restrict__ b_c, MgVec *__restrict__ x_c,
                                                                        const CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
+    pdl_trigger();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const float3 bc = csr_apply_row<LANES>(i, i < nc, rowptr, colidx, val, r_fine);
+    const CsrRowHead h = csr_row_head<LANES>(i, i < nc, rowptr, colidx, val);
+    const float s = (i < nc) ? omega_c * __ldg(&inv_diag_c[i]) : 0.f;
+    pdl_wait();
+    if (cg->converged) return;
+    const float3 bc = csr_apply_row<LANES>(h, colidx, val, r_fine);
     if (i < nc && (threadIdx.x & (LANES - 1)) == 0) {
         b_c[i] = MgVec{bc.x, bc.y, bc.z, 0.f};
-        const float s = omega_c * inv_diag_c[i];
         x_c[i] = MgVec{s * bc.x, s * bc.y, s * bc.z, 0.f};
     }
 }
@@ -168,11 +201,13 @@ __global__ void __launch_bounds__(kBlock) mg_restrict_presmooth_kernel(int nc, c
 __global__ void __launch_bounds__(kBlock) mg_prolong_add_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                 const float *__restrict__ val, const MgVec *__restrict__ x_c,
                                                                 MgVec *__restrict__ x, const CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (rowptr[i] == rowptr[i + 1]) return;
-    const float3 c = csr_apply_row<1>(i, true, rowptr, colidx, val, x_c);
+    const CsrRowHead h = csr_row_head<1>(i, i < n, rowptr, colidx, val);
+    pdl_wait();
+    if (cg->converged) return;
+    if (i >= n || h.k0 == h.k1) return;
+    const float3 c = csr_apply_row<1>(h, colidx, val, x_c);
     MgVec xi = x[i];
     xi.x += c.x; xi.y += c.y; xi.z += c.z;
     x[i] = xi;
@@ -184,43 +219,58 @@ __global__ void __launch_bounds__(kBlock) mg_csr_postsmooth_kernel(int n, const 
                                                                    const float *__restrict__ val, const float *__restrict__ inv_diag,
                                                                    float omega, const MgVec *__restrict__ b, const MgVec *__restrict__ x,
                                                                    MgVec *__restrict__ x_out, const CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
+    pdl_trigger();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const float3 ax = csr_apply_row<LANES>(i, i < n, rowptr, colidx, val, x);
+    const CsrRowHead h = csr_row_head<LANES>(i, i < n, rowptr, colidx, val);
+    const float s = (i < n) ? omega * __ldg(&inv_diag[i]) : 0.f;
+    pdl_wait();
+    if (cg->converged) return;
+    const float3 ax = csr_apply_row<LANES>(h, colidx, val, x);
     if (i < n && (threadIdx.x & (LANES - 1)) == 0) {
         const MgVec bi = b[i], xi = x[i];
-        const float s = omega * inv_diag[i];
         x_out[i] = MgVec{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z), 0.f};
     }
 }
 
 // coarsest level: x = A^-1 b with the dense inverse; one warp per row. The right-hand side (n float4, <= 32 KB) is staged
 // in shared memory once per CTA: read per warp from L2 it was 4x the traffic of the matrix itself (13 us at 1170 rows).
+// The matrix row (<= 2048 floats = 16 float4 per lane) is loaded in batches of 8 independent 16-byte loads per lane BEFORE
+// any arithmetic: the kernel is one dependent L2 round trip long instead of one per 128 columns.
 __global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, int ld, const float *__restrict__ inv, const MgVec *__restrict__ b,
                                                                 MgVec *__restrict__ x, const CgScalars *__restrict__ cg) {
     extern __shared__ __align__(16) unsigned char dense_smem[];
     MgVec *sb = reinterpret_cast<MgVec *>(dense_smem);                   // ld entries, zero beyond n
+    pdl_trigger();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    // rows are padded to ld (a multiple of 4) floats
+    const float4 *arow = reinterpret_cast<const float4 *>(inv + (size_t)(row < n ? row : 0) * ld);
+    const int n4 = ld >> 2;
+    constexpr int B = 8;
+    float4 a[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) { const int q = lane + 32 * u; a[u] = q < n4 ? __ldg(&arow[q]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    pdl_wait();                    // the matrix is constant: its first batch is in flight while the producer of b finishes
     if (cg->converged) return;
     for (int c = threadIdx.x; c < ld; c += blockDim.x) sb[c] = c < n ? b[c] : MgVec{0.f, 0.f, 0.f, 0.f};
     __syncthreads();
-    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
     if (row >= n) return;
-    // rows are padded to ld (a multiple of 4) floats: 16-byte loads, two in flight per lane
-    const float4 *arow = reinterpret_cast<const float4 *>(inv + (size_t)row * ld);
-    const int n4 = ld >> 2;
     float s0 = 0, s1 = 0, s2 = 0;
-    for (int q = lane; q < n4; q += 64) {
-        const float4 a0 = __ldg(&arow[q]);
-        const bool two = q + 32 < n4;
-        const float4 a1 = two ? __ldg(&arow[q + 32]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const MgVec *b0 = sb + 4 * q, *b1 = sb + (two ? 4 * (q + 32) : 0);
-        s0 += a0.x * b0[0].x + a0.y * b0[1].x + a0.z * b0[2].x + a0.w * b0[3].x;
-        s1 += a0.x * b0[0].y + a0.y * b0[1].y + a0.z * b0[2].y + a0.w * b0[3].y;
-        s2 += a0.x * b0[0].z + a0.y * b0[1].z + a0.z * b0[2].z + a0.w * b0[3].z;
-        s0 += a1.x * b1[0].x + a1.y * b1[1].x + a1.z * b1[2].x + a1.w * b1[3].x;
-        s1 += a1.x * b1[0].y + a1.y * b1[1].y + a1.z * b1[2].y + a1.w * b1[3].y;
-        s2 += a1.x * b1[0].z + a1.y * b1[1].z + a1.z * b1[2].z + a1.w * b1[3].z;
+    for (int base = 0; base < n4; base += 32 * B) {
+        if (base > 0) {
+#pragma unroll
+            for (int u = 0; u < B; ++u) { const int q = base + lane + 32 * u; a[u] = q < n4 ? __ldg(&arow[q]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int q = base + lane + 32 * u;
+            if (q < n4) {
+                const MgVec *bq = sb + 4 * q;
+                s0 += a[u].x * bq[0].x + a[u].y * bq[1].x + a[u].z * bq[2].x + a[u].w * bq[3].x;
+                s1 += a[u].x * bq[0].y + a[u].y * bq[1].y + a[u].z * bq[2].y + a[u].w * bq[3].y;
+                s2 += a[u].x * bq[0].z + a[u].y * bq[1].z + a[u].z * bq[2].z + a[u].w * bq[3].z;
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -240,6 +290,7 @@ __global__ void __launch_bounds__(kBlock) mg_dense_solve_kernel(int n, int ld, c
 constexpr int kBgM = 128, kBgMembers = 32, kBgK = 16, kBgN = kBgMembers * 3;
 __global__ void __launch_bounds__(256) mg_batch_dense_kernel(int V, int ld, int K, const float *__restrict__ inv, const Vec3d *__restrict__ r,
                                                              MgVec *__restrict__ z, const CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     __shared__ __align__(16) float As[2][kBgK][kBgM];        // As[k][i]
     __shared__ __align__(16) float Bs[2][kBgK][kBgN];        // Bs[k][member * 3 + c]
@@ -365,6 +416,7 @@ __device__ __forceinline__ float3 tail_apply_row(int row, bool valid, int lanes,
 __global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const MgTailArgs args, const CgScalars *__restrict__ cg) {
     namespace cgrp = cooperative_groups;
     cgrp::cluster_group cluster = cgrp::this_cluster();
+    pdl_enter();
     if (cg->converged) return;                                  // uniform over the cluster: nobody reaches a barrier
     const int nt = (int)cluster.num_blocks() * kTailThreads;
     const int tid = (int)cluster.block_rank() * kTailThreads + (int)threadIdx.x;
@@ -466,7 +518,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const MgTailAr
 // ---- dense inverse of the coarsest operator on the device (setup, once per hierarchy) ---------------------------------
 // The host inverts coarsest levels of up to a few hundred rows; with up to 2048 rows the hierarchy is one or two levels
 // shorter (4-8 launches less per V-cycle), but O(n^3) scalar host code would take seconds. In-place Gauss-Jordan without
-// pivoting in fp64 (the operator is SPD after the same tiny diagonal shift the host code applies): two launches per pivot.
+// pivoting in fp64 (the operator is SPD after the same tiny diagonal shift the host code applies), blocked by panels.
 __global__ void __launch_bounds__(kBlock) dense_from_csr_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                 const double *__restrict__ val, double shift, double *__restrict__ M) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,31 +531,92 @@ __global__ void __launch_bounds__(kBlock) dense_from_csr_kernel(int n, const int
     if (diag == 0.0) M[(size_t)i * n + i] = 1.0;            // empty row: identity
     else M[(size_t)i * n + i] += shift;
 }
-// pivot c, part 1 (one CTA): save column c, scale row c by 1/pivot, put 1/pivot on the diagonal
-__global__ void __launch_bounds__(1024) gj_pivot_kernel(int n, int c, double *__restrict__ M, double *__restrict__ colbuf, int *__restrict__ bad) {
-    __shared__ double dinv;
-    if (threadIdx.x == 0) {
-        const double p = M[(size_t)c * n + c];
-        if (!(p > 0.0) || !(p < 1e300)) { *bad = 1; dinv = 0.0; }
-        else dinv = 1.0 / p;
+// Blocked in-place Gauss-Jordan, panels of kGjB pivots, three launches per panel K = [k0, k0 + nb):
+//   gj_panel_kernel   D = A[K,K]^-1 (one CTA, unblocked Gauss-Jordan in shared memory); C = the column panel A[:,K] saved
+//   gj_row_kernel     A[K,J] <- D A[K,J] for the columns J outside K; A[K,K] <- D
+//   gj_update_kernel  A[I,J] -= C[I,:] A[K,J] and A[I,K] <- -C[I,:] D for the rows I outside K
+// (n / 32 * 3 launches instead of the 2 n of the pivot-by-pivot version: 111 instead of 2,340 at 1,170 rows.)
+constexpr int kGjB = 32;
+__global__ void __launch_bounds__(1024) gj_panel_kernel(int n, int k0, int nb, const double *__restrict__ M, double *__restrict__ D,
+                                                        double *__restrict__ C, int *__restrict__ bad) {
+    if (blockIdx.x > 0) {                                       // every other CTA: save the column panel C[r][c] = M[r][k0 + c]
+        for (int t = (blockIdx.x - 1) * blockDim.x + threadIdx.x; t < n * nb; t += (gridDim.x - 1) * blockDim.x) {
+            const int r = t / nb, c = t - r * nb;
+            C[(size_t)r * kGjB + c] = M[(size_t)r * n + k0 + c];
+        }
+        return;
     }
+    __shared__ double a[kGjB][kGjB + 1];
+    __shared__ double colbuf[kGjB];
+    __shared__ double dinv;
+    const int r = threadIdx.x / kGjB, c = threadIdx.x % kGjB;   // 32 x 32 threads
+    if (r < nb && c < nb) a[r][c] = M[(size_t)(k0 + r) * n + k0 + c];
     __syncthreads();
-    const double d = dinv;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        colbuf[k] = M[(size_t)k * n + c];
-        const double v = M[(size_t)c * n + k];
-        M[(size_t)c * n + k] = (k == c) ? d : v * d;
+    for (int p = 0; p < nb; ++p) {
+        if (threadIdx.x == 0) {
+            const double piv = a[p][p];
+            if (!(piv > 0.0) || !(piv < 1e300)) { *bad = 1; dinv = 0.0; }
+            else dinv = 1.0 / piv;
+        }
+        if (r == 0 && c < nb) colbuf[c] = a[c][p];
+        __syncthreads();
+        const double d = dinv;
+        if (r == p && c < nb) a[p][c] = (c == p) ? d : a[p][c] * d;
+        __syncthreads();
+        if (r < nb && c < nb && r != p) {
+            const double f = colbuf[r];
+            a[r][c] = (c == p) ? -f * a[p][c] : a[r][c] - f * a[p][c];
+        }
+        __syncthreads();
+    }
+    if (r < nb && c < nb) D[r * kGjB + c] = a[r][c];
+}
+__global__ void __launch_bounds__(kBlock) gj_row_kernel(int n, int k0, int nb, double *__restrict__ M, const double *__restrict__ D,
+                                                        double *__restrict__ R) {
+    __shared__ double d[kGjB][kGjB];
+    for (int t = threadIdx.x; t < kGjB * kGjB; t += blockDim.x) d[t / kGjB][t % kGjB] = (t / kGjB < nb && t % kGjB < nb) ? D[t] : 0.0;
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;       // one column per thread
+    if (j >= n) return;
+    const bool inside = j >= k0 && j < k0 + nb;
+    double col[kGjB];
+#pragma unroll
+    for (int q = 0; q < kGjB; ++q) col[q] = (q < nb) ? M[(size_t)(k0 + q) * n + j] : 0.0;
+#pragma unroll 4
+    for (int r = 0; r < nb; ++r) {
+        double v;
+        if (inside) v = d[r][j - k0];
+        else {
+            v = 0.0;
+#pragma unroll
+            for (int q = 0; q < kGjB; ++q) v += d[r][q] * col[q];
+        }
+        M[(size_t)(k0 + r) * n + j] = v;
+        R[(size_t)r * n + j] = v;                                // the scaled row panel, read by the update kernel
     }
 }
-// pivot c, part 2: every other row r: M[r][k] -= f M[c][k] (k != c), M[r][c] = -f / pivot, f = the saved M[r][c]
-__global__ void __launch_bounds__(kBlock) gj_update_kernel(int n, int c, double *__restrict__ M, const double *__restrict__ colbuf) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (k >= n || r == c) return;
-    const double f = colbuf[r];
-    if (f == 0.0) return;
-    const double rc = M[(size_t)c * n + k];                 // row c is already scaled; its entry at k == c is 1/pivot
-    M[(size_t)r * n + k] = (k == c) ? -f * rc : M[(size_t)r * n + k] - f * rc;
+// 16 x 16 threads, each one entry of a 16 x 16 tile of the rows outside the panel
+__global__ void __launch_bounds__(256) gj_update_kernel(int n, int k0, int nb, double *__restrict__ M, const double *__restrict__ C,
+                                                        const double *__restrict__ R, const double *__restrict__ D) {
+    __shared__ double cs[16][kGjB + 1];
+    __shared__ double rs[kGjB][16 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+    for (int t = threadIdx.x; t < 16 * kGjB; t += 256) {
+        const int rr = t / kGjB, q = t % kGjB, gi = blockIdx.y * 16 + rr;
+        cs[rr][q] = (gi < n && q < nb) ? C[(size_t)gi * kGjB + q] : 0.0;
+        const int q2 = t / 16, cc = t % 16, gj = blockIdx.x * 16 + cc;
+        const bool in_panel = gj >= k0 && gj < k0 + nb;
+        // columns inside the panel use D (A[I,K] <- -C D); R holds D there as well, so one source serves both cases
+        rs[q2][cc] = (gj < n && q2 < nb) ? (in_panel ? D[q2 * kGjB + (gj - k0)] : R[(size_t)q2 * n + gj]) : 0.0;
+    }
+    __syncthreads();
+    if (i >= n || j >= n || (i >= k0 && i < k0 + nb)) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kGjB; ++q) acc += cs[ty][q] * rs[q][tx];
+    const bool in_panel = j >= k0 && j < k0 + nb;
+    M[(size_t)i * n + j] = in_panel ? -acc : M[(size_t)i * n + j] - acc;
 }
 __global__ void __launch_bounds__(kBlock) dense_to_float_kernel(int n, int ld, const double *__restrict__ in, float *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over n x ld, padding columns = 0
@@ -514,12 +627,14 @@ __global__ void __launch_bounds__(kBlock) dense_to_float_kernel(int n, int ld, c
 
 // single-level hierarchies (tiny meshes): the V-cycle input/output live in fp64 CG vectors
 __global__ void __launch_bounds__(kBlock) mg_to_float_kernel(int n, const Vec3d *__restrict__ in, MgVec *__restrict__ out) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const Vec3d v = in[i]; out[i] = MgVec{(float)v.x, (float)v.y, (float)v.z, 0.f}; }
 }
 // z = omega D^-1 b (plain damped Jacobi; fallback when a single-level hierarchy has no dense inverse)
 __global__ void __launch_bounds__(kBlock) mg_jacobi_kernel(int n, const float *__restrict__ inv_diag, float omega, const MgVec *__restrict__ b,
                                                            MgVec *__restrict__ z) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const MgVec v = b[i]; const float s = omega * inv_diag[i]; z[i] = MgVec{s * v.x, s * v.y, s * v.z, 0.f}; }
 }
@@ -527,6 +642,7 @@ __global__ void __launch_bounds__(kBlock) mg_jacobi_kernel(int n, const float *_
 __global__ void __launch_bounds__(kBlock) cg_dot_rho_f_kernel(int n, const Vec3d *__restrict__ r, const MgVec *__restrict__ z,
                                                               double *__restrict__ partials, unsigned *__restrict__ counter,
                                                               CgScalars *__restrict__ cg) {
+    pdl_enter();
     if (cg->converged) return;
     double red[4] = {0, 0, 0, 0};
     const double inv_len2 = cg->inv_len2;
@@ -537,67 +653,7 @@ __global__ void __launch_bounds__(kBlock) cg_dot_rho_f_kernel(int n, const Vec3d
         red[3] += z_norm8(zi, inv_len2);
     }
     double total[4];
-    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_RHO, total);
-}
-
-__device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
-
-// ---- CG pieces for a general preconditioner -------------------------------------------------------------
-// The CG vectors are (x,y,z) triples, i.e. flat arrays of 3V doubles. The update and direction kernels are
-// purely element-wise, so they stream those flat arrays with one coalesced 16-byte access per thread and array
-// (element e belongs to vertex e/3, coordinate e%3) instead of three strided 8-byte accesses per vertex.
-//
-// x += alpha d ; r -= alpha Ad ; x0 = omega_0 D^-1 r (the V-cycle's pre-smoothed fine iterate) ; |r|^2 -> convergence
-__global__ void __launch_bounds__(kBlock) cg_update_mg_kernel(int n3, const double *__restrict__ inv_diag, double omega0,
-                                                              const double *__restrict__ d, const double *__restrict__ ad,
-                                                              double *__restrict__ x, double *__restrict__ r, float *__restrict__ x0,
-                                                              double *__restrict__ partials, unsigned *__restrict__ counter,
-                                                              CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
-    double red[1] = {0};
-    const double al0 = cg->alpha[0], al1 = cg->alpha[1], al2 = cg->alpha[2];
-    for (int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x); e < n3; e += 2 * gridDim.x * blockDim.x) {
-        if (e + 1 < n3) {
-            const double2 dv = *reinterpret_cast<const double2 *>(d + e), av = *reinterpret_cast<const double2 *>(ad + e);
-            double2 xv = *reinterpret_cast<const double2 *>(x + e), rv = *reinterpret_cast<const double2 *>(r + e);
-            const int c0 = e % 3, c1 = (e + 1) % 3;
-            const double a0 = pick3(c0, al0, al1, al2), a1 = pick3(c1, al0, al1, al2);
-            xv.x += a0 * dv.x; xv.y += a1 * dv.y;
-            rv.x -= a0 * av.x; rv.y -= a1 * av.y;
-            *reinterpret_cast<double2 *>(x + e) = xv;
-            *reinterpret_cast<double2 *>(r + e) = rv;
-            const int v0 = e / 3, v1 = (e + 1) / 3;
-            x0[4 * v0 + c0] = (float)(omega0 * inv_diag[v0] * rv.x);          // x0 is a float4 per vertex: element (v, c) at 4 v + c
-            x0[4 * v1 + c1] = (float)(omega0 * inv_diag[v1] * rv.y);
-            red[0] += rv.x * rv.x + rv.y * rv.y;
-        } else {
-            const double a0 = pick3(e % 3, al0, al1, al2);
-            const double xv = x[e] + a0 * d[e], rv = r[e] - a0 * ad[e];
-            x[e] = xv; r[e] = rv;
-            x0[4 * (e / 3) + e % 3] = (float)(omega0 * inv_diag[e / 3] * rv);
-            red[0] += rv * rv;
-        }
-    }
-    double total[1];
-    if (grid_sum_last_block<1>(red, partials, counter, total)) cg_finish_reduction<1>(cg, CG_STAGE_UPDATE_MG, total);
-}
-
-// d = z + beta d
-__global__ void __launch_bounds__(kBlock) cg_direction_mg_kernel(int n3, const float *__restrict__ z, double *__restrict__ d,
-                                                                 const CgScalars *__restrict__ cg) {
-    if (cg->converged) return;
-    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (e >= n3) return;
-    const double b0 = cg->beta[0], b1 = cg->beta[1], b2 = cg->beta[2];
-    if (e + 1 < n3) {
-        const int c0 = e % 3, c1 = (e + 1) % 3;
-        double2 dv = *reinterpret_cast<const double2 *>(d + e);
-        dv.x = (double)z[4 * (e / 3) + c0] + pick3(c0, b0, b1, b2) * dv.x;      // z is a float4 per vertex
-        dv.y = (double)z[4 * ((e + 1) / 3) + c1] + pick3(c1, b0, b1, b2) * dv.y;
-        *reinterpret_cast<double2 *>(d + e) = dv;
-    } else {
-        d[e] = (double)z[4 * (e / 3) + e % 3] + pick3(e % 3, b0, b1, b2) * d[e];
-    }
+    if (grid_sum_last_block<4>(red, partials, counter, total)) cg_finish_reduction<4>(cg, CG_STAGE_GAMMA, total, 0);
 }
 
 }  // namespace arap
