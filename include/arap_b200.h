@@ -138,6 +138,10 @@ typedef struct arap_solver_stats {
                                     * 2: the whole ARAP iteration is one graph whose CG loop runs on the device (WHILE node) */
     int32_t mg_global;             /* 1: partitioned mode with the global hierarchy (arap_partition_set_global_mesh) */
     double last_position_error;    /* multigrid: the estimate the stopping rule used, as a fraction of the bbox diagonal */
+    /* partitioned mode: cross-GPU operations of ONE CG iteration (counted while it is captured / first issued) */
+    int32_t comm_exchanges_per_cg_iteration;    /* halo exchanges (one per gathered vector and partitioned multigrid level) */
+    int32_t comm_allreduces_per_cg_iteration;   /* all-reduces / all-gathers (CG scalars, replicated coarse levels) */
+    int64_t comm_halo_bytes_per_cg_iteration;   /* bytes this rank sends in those exchanges */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 
@@ -230,6 +234,11 @@ typedef struct arap_partition_plan {
 int arap_comm_unique_id(void *out_bytes, int32_t capacity /* >= 128 */);
 int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32_t rank, int32_t world_size, int32_t transport,
                           const void *id, int32_t id_bytes);
+
+/* Measurement aid (partitioned handles, after arap_prepare; collective: every rank must call it with the same `rounds`):
+ * device time per halo exchange of the CG's gathered vector and per all-reduce of the CG scalars, in microseconds, from
+ * `rounds` back-to-back operations bracketed by CUDA events on the handle's stream. */
+int arap_partition_comm_benchmark(arap_handle *h, int32_t rounds, double *us_per_exchange, double *us_per_allreduce);
 
 /* Optional, after arap_attach_partition and before arap_prepare: the GLOBAL mesh, so that every rank can build the same
  * multigrid hierarchy for the whole mesh (aggregates never straddle two ranks) and keep its share of every level. The

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "arap_batch_iterate", "arap_batch_get_positions", "arap_batch_handle", "arap_comm_unique_id", "arap_attach_partition",
     "arap_trajectory_create", "arap_trajectory_destroy", "arap_trajectory_add_key_pose", "arap_trajectory_evaluate",
     "arap_rigid_conjugate", "arap_set_rigid_constraints", "arap_batch_set_rigid_constraints",
-    "arap_partition_set_global_mesh",
+    "arap_partition_set_global_mesh", "arap_partition_comm_benchmark",
 )
 
 
@@ -49,7 +49,9 @@ class Options(C.Structure):
 class SolverStats(C.Structure):
     _fields_ = [("cg_iterations_total", C.c_int64), ("global_steps", C.c_int32), ("last_cg_iterations", C.c_int32),
                 ("last_relative_residual", C.c_double), ("last_converged", C.c_int32), ("mg_levels", C.c_int32),
-                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32), ("last_position_error", C.c_double)]
+                ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32), ("last_position_error", C.c_double),
+                ("comm_exchanges_per_cg_iteration", C.c_int32), ("comm_allreduces_per_cg_iteration", C.c_int32),
+                ("comm_halo_bytes_per_cg_iteration", C.c_int64)]
 
 
 class GlobalMesh(C.Structure):
@@ -134,6 +136,7 @@ def lib():
     L.arap_comm_unique_id.argtypes = [vp, i32]
     L.arap_attach_partition.argtypes = [vp, C.POINTER(PartitionPlan), i32, i32, i32, vp, i32]
     L.arap_partition_set_global_mesh.argtypes = [vp, C.POINTER(GlobalMesh)]
+    L.arap_partition_comm_benchmark.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.arap_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.arap_host_free.argtypes = [vp]
     L.arap_last_error.argtypes = [vp]
@@ -554,6 +557,12 @@ class PartitionedDeformation:
 
     def local_energy(self):
         return self.arap.energy()
+
+    def comm_benchmark(self, rounds=200):
+        """(microseconds per halo exchange, per all-reduce) on this rank's stream; collective."""
+        a, b = C.c_double(), C.c_double()
+        self.arap._check(lib().arap_partition_comm_benchmark(self.arap._h, int(rounds), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def solver_stats(self):
         return self.arap.solver_stats()

@@ -105,6 +105,7 @@ public:
     virtual int energy(double *e) = 0;
     virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
     virtual int set_global_mesh(const arap_global_mesh *g) = 0;
+    virtual int comm_benchmark(int rounds, double *us_exchange, double *us_allreduce) = 0;
     // arap_batch_*: the mesh is `members` disjoint copies of a `member_vertices`-vertex mesh, member-major
     void set_batch_layout(int members, int member_vertices_) { batch_members = members; member_vertices = member_vertices_; }
     int batch_members = 1, member_vertices = 0;
@@ -159,13 +160,17 @@ public:
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr.val.programmaticStreamSerializationAllowed = 1;
-        const bool pdl = use_pdl && !pdl_next_plain && !profile_events;
+        // pdl_mode 1: every iteration kernel; 2: only the small grids of the coarse multigrid levels (a persistent full-GPU
+        // kernel whose CTAs trickle in while its predecessor drains ends up unevenly spread over the SMs)
+        const bool pdl = pdl_mode > 0 && (pdl_mode == 1 || grid <= (unsigned)(2 * sm_count)) && !pdl_next_plain && !profile_events;
         cfg.attrs = pdl ? &attr : nullptr;
         cfg.numAttrs = pdl ? 1 : 0;
         pdl_next_plain = false;
         cudaLaunchKernelEx(&cfg, kernel, std::forward<Act>(args)...);
     }
-    bool use_pdl = !(getenv("ARAP_PDL") && atoi(getenv("ARAP_PDL")) == 0);
+    // Measured at 1M vertices (profiles/r02_experiments.txt): 2.08 ms per ARAP iteration without, 2.14 ms with the attribute on
+    // every kernel -- off by default, ARAP_PDL=1|2 switches it on.
+    int pdl_mode = getenv("ARAP_PDL") ? atoi(getenv("ARAP_PDL")) : 0;
     bool pdl_next_plain = true;
 
     int n_vertices = 0, n_faces = 0;
@@ -347,6 +352,18 @@ public:
     cudaGraph_t cg_graph = nullptr;                // one CG iteration (preconditioner included), replayed per iteration
     cudaGraphExec_t cg_graph_exec = nullptr;
     bool have_warm_rotations = false;              // quat[] holds the previous iteration's R_i
+
+    bool comm_counting = false, comm_counted = false;   // cross-GPU operations of one CG iteration (arap_solver_stats)
+    int comm_exchanges = 0, comm_allreduces = 0;
+    long long comm_bytes = 0;
+    void comm_count_begin() { comm_counting = true; comm_exchanges = comm_allreduces = 0; comm_bytes = 0; }
+    void comm_count_end() {
+        comm_counting = false;
+        comm_counted = true;
+        stats.comm_exchanges_per_cg_iteration = comm_exchanges;
+        stats.comm_allreduces_per_cg_iteration = comm_allreduces;
+        stats.comm_halo_bytes_per_cg_iteration = comm_bytes;
+    }
 
     int nnz = 0;
     int n_free = 0;
@@ -558,6 +575,7 @@ public:
         const int V = n_vertices, F = n_faces;
         prepared = false;
         std::memset(&stats, 0, sizeof(stats));
+        comm_counted = false;
         // ---- initializeMeshGeometry (arap.h:162-168)
         ARAP_CUDA(rest_xyz.ensure(3 * (size_t)V));
         { int rc = upload_cast(rest_host, 3 * (size_t)V, scalar_bytes, rest_xyz.ptr); if (rc) return rc; }
@@ -895,6 +913,7 @@ public:
     int exchange_halo(void *array, size_t elem_bytes, int site) {
         if (!transport) return ARAP_OK;
         pdl_next_plain = true;
+        if (comm_counting) { comm_exchanges += 1; comm_bytes += (long long)plan.n_send() * (long long)elem_bytes; }
         begin_launch(ARAP_K_HALO_PACK);
         const int rc = transport->exchange(stream, site, plan, send_index_dev.ptr, (char *)halo_sendbuf.ptr, (char *)array, elem_bytes);
         end_launch();
@@ -934,6 +953,7 @@ public:
     int exchange_level(int level, int which, MgVec *array) {
         MgLevelDev &lv = *mg[(size_t)level];
         pdl_next_plain = true;
+        if (comm_counting) { comm_exchanges += 1; comm_bytes += (long long)lv.plan.n_send() * (long long)sizeof(MgVec); }
         begin_launch(ARAP_K_HALO_PACK);
         const int rc = transport->exchange(stream, SITE_LEVEL_BASE + 4 * level + which, lv.plan, lv.send_index.ptr, (char *)mg_sendbuf.ptr,
                                            (char *)array, sizeof(MgVec));
@@ -987,6 +1007,7 @@ public:
         if (!transport) return ARAP_OK;
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
         (void)n_values;             // always the whole red[8] block: one site layout for every stage
+        if (comm_counting) comm_allreduces += 1;
         if (transport->allreduce_sum(stream, SITE_RED_BASE + stage, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
         pdl_next_plain = true;
         begin_launch(ARAP_K_CG_FINALIZE);
@@ -1304,6 +1325,7 @@ public:
         }
         // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
         MgLevelDev &cl = *mg[L - 1];
+        if (comm_counting) comm_allreduces += 1;
         if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
         pdl_next_plain = true;
         launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
@@ -1528,7 +1550,9 @@ public:
         ARAP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         capturing = true;
         pdl_next_plain = true;
+        comm_count_begin();
         const int rc_body = use_mg ? cg_iteration_mg() : cg_iteration_jacobi();
+        comm_count_end();
         capturing = false;
         pdl_next_plain = true;
         cudaError_t e = cudaStreamEndCapture(stream, &cg_graph);
@@ -1637,11 +1661,46 @@ public:
         if (cg_graph_exec && !profile_events) {
             for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) profile.launches[k] += graph_counts_iter[k];
             ARAP_CUDA(cudaGraphLaunch(cg_graph_exec, stream));
-        } else if (use_mg) {
-            return cg_iteration_mg();
         } else {
-            return cg_iteration_jacobi();
+            const bool count = transport && !comm_counted;
+            if (count) comm_count_begin();
+            const int rc = use_mg ? cg_iteration_mg() : cg_iteration_jacobi();
+            if (count) comm_count_end();
+            return rc;
         }
+        return ARAP_OK;
+    }
+
+    int comm_benchmark(int rounds, double *us_exchange, double *us_allreduce) override {
+        if (!transport || !prepared) return fail(ARAP_ERR_INVALID, "comm_benchmark: needs a prepared partitioned handle");
+        if (rounds <= 0) rounds = 1;
+        double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
+        float ms = 0.f;
+        for (int pass = 0; pass < 2; ++pass) {                   // pass 0 warms up
+            ARAP_CUDA(cudaEventRecord(timer_start, stream));
+            for (int k = 0; k < rounds; ++k) {
+                int rc;
+                if (use_mg) rc = exchange_halo(mg[0]->x2.ptr, sizeof(MgVec), SITE_CG_D);
+                else rc = exchange_halo(cg_d.ptr, sizeof(Vec3d), SITE_CG_D);
+                if (rc) return rc;
+            }
+            ARAP_CUDA(cudaEventRecord(timer_stop, stream));
+            ARAP_CUDA(cudaEventSynchronize(timer_stop));
+            ARAP_CUDA(cudaEventElapsedTime(&ms, timer_start, timer_stop));
+        }
+        if (us_exchange) *us_exchange = 1e3 * (double)ms / rounds;
+        ARAP_CUDA(cudaMemsetAsync(red, 0, 8 * sizeof(double), stream));
+        for (int pass = 0; pass < 2; ++pass) {
+            ARAP_CUDA(cudaEventRecord(timer_start, stream));
+            for (int k = 0; k < rounds; ++k)
+                if (transport->allreduce_sum(stream, SITE_RED_BASE + CG_STAGE_MERGED, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
+            ARAP_CUDA(cudaEventRecord(timer_stop, stream));
+            ARAP_CUDA(cudaEventSynchronize(timer_stop));
+            ARAP_CUDA(cudaEventElapsedTime(&ms, timer_start, timer_stop));
+        }
+        if (us_allreduce) *us_allreduce = 1e3 * (double)ms / rounds;
+        pdl_next_plain = true;
+        if (transport->poll_error()) return fail(ARAP_ERR_CUDA, transport->error);
         return ARAP_OK;
     }
 
@@ -2179,6 +2238,11 @@ int arap_attach_partition(arap_handle *h, const arap_partition_plan *plan, int32
                           const void *id, int32_t id_bytes) {
     ARAP_ENGINE_OR_FAIL(h);
     return h->engine->attach_partition(plan, rank, world_size, transport, id, id_bytes);
+}
+
+int arap_partition_comm_benchmark(arap_handle *h, int32_t rounds, double *us_per_exchange, double *us_per_allreduce) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->comm_benchmark(rounds, us_per_exchange, us_per_allreduce);
 }
 
 int arap_partition_set_global_mesh(arap_handle *h, const arap_global_mesh *g) {

@@ -45,6 +45,38 @@ def strip_owner(positions, n_parts):
     return owner
 
 
+def block_grid(n_parts):
+    """(pa, pb) with pa * pb == n_parts and pa >= pb as square as possible: 2 -> (2,1), 4 -> (2,2), 8 -> (4,2)."""
+    pb = int(np.floor(np.sqrt(n_parts)))
+    while n_parts % pb:
+        pb -= 1
+    return n_parts // pb, pb
+
+
+def block_owner(positions, n_parts):
+    """Owner rank per vertex for a pa x pb arrangement of blocks: pa slabs of equal vertex count along the longest
+    bounding-box axis, each cut into pb pieces of equal count along the second-longest. Blocks have up to 8 neighbours
+    (strips: 2) but a quarter of the halo of strips on a square grid."""
+    positions = np.asarray(positions)
+    pa, pb = block_grid(n_parts)
+    ext = positions.max(0) - positions.min(0)
+    a0 = int(np.argmax(ext))
+    ext2 = ext.copy()
+    ext2[a0] = -1.0
+    a1 = int(np.argmax(ext2))
+    n = positions.shape[0]
+    owner = np.empty(n, np.int32)
+    order = np.lexsort((np.arange(n), positions[:, a0]))
+    bounds = np.linspace(0, n, pa + 1).astype(np.int64)
+    for p in range(pa):
+        slab = order[bounds[p]:bounds[p + 1]]
+        sub = slab[np.lexsort((slab, positions[slab, a1]))]
+        b2 = np.linspace(0, sub.size, pb + 1).astype(np.int64)
+        for q in range(pb):
+            owner[sub[b2[q]:b2[q + 1]]] = p * pb + q
+    return owner
+
+
 def build_local_part(faces, owner, rank, world):
     """The local mesh and halo plan of `rank` (see module docstring)."""
     faces = np.asarray(faces)
