@@ -339,6 +339,7 @@ public:
     } global_mesh;
     bool have_global = false;
     bool mg_global = false;                        // the current hierarchy is this rank's share of the global one
+    int mg_first_replicated = 0;                   // global hierarchy: levels >= this one are kept whole on every rank
     std::vector<unsigned char> mg_global_mask;     // global constrained mask the hierarchy was built for
     DeviceBuffer<unsigned char> mg_sendbuf;
     // the coarse tail of the V-cycle as one cluster kernel (mg_kernels.cuh, mg_tail_kernel): levels [tail_first, last]
@@ -974,13 +975,13 @@ public:
             ex(SITE_MG0_X_PRE, &plan, (int)sizeof(MgVec));
             ex(SITE_MG0_R, &plan, (int)sizeof(MgVec));
             ex(SITE_MG0_X_POST, &plan, (int)sizeof(MgVec));
-            for (size_t l = 1; l + 1 < mg.size(); ++l)
+            for (int l = 1; l < mg_first_replicated; ++l)
                 for (int w = 0; w < 4; ++w) {
-                    if (SITE_LEVEL_BASE + 4 * (int)l + w >= SITE_COUNT) return fail(ARAP_ERR_SOLVER, "too many multigrid levels for the transport's site table");
-                    ex(SITE_LEVEL_BASE + 4 * (int)l + w, &mg[l]->plan, (int)sizeof(MgVec));
+                    if (SITE_LEVEL_BASE + 4 * l + w >= SITE_COUNT) return fail(ARAP_ERR_SOLVER, "too many multigrid levels for the transport's site table");
+                    ex(SITE_LEVEL_BASE + 4 * l + w, &mg[(size_t)l]->plan, (int)sizeof(MgVec));
                 }
             sites[SITE_COARSE_B].kind = SiteSpec::REDUCE_F32;
-            sites[SITE_COARSE_B].n = 4 * mg.back()->n;
+            sites[SITE_COARSE_B].n = 4 * mg[(size_t)mg_first_replicated]->n;
         }
         if (transport->configure(stream, sites)) return fail(ARAP_ERR_CUDA, transport->error);
         return ARAP_OK;
@@ -994,8 +995,8 @@ public:
         if (transport->allreduce_sum(stream, SITE_RED_BASE, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
         if (use_mg && mg_global) {
             { int rc = exchange_halo(mg[0]->x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }
-            for (size_t l = 1; l + 1 < mg.size(); ++l) { int rc = exchange_level((int)l, 0, mg[l]->x.ptr); if (rc) return rc; }
-            MgLevelDev &cl = *mg.back();
+            for (int l = 1; l < mg_first_replicated; ++l) { int rc = exchange_level(l, 0, mg[(size_t)l]->x.ptr); if (rc) return rc; }
+            MgLevelDev &cl = *mg[(size_t)mg_first_replicated];
             if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
         }
         ARAP_CUDA(cudaStreamSynchronize(stream));
@@ -1238,7 +1239,10 @@ public:
         for (int i = 0; i < V; ++i) global_of_local[(size_t)i] = gm.local_to_global[(size_t)h_perm[(size_t)i]];
         MgLocalHierarchy LH;
         std::string err;
-        if (!mg_slice_hierarchy(H, my_rank, n_rows, V, global_of_local.data(), LH, err)) return fail(ARAP_ERR_SOLVER, err);
+        // levels of at most this many rows are replicated on every rank (mg_partition.h): 4 halo exchanges less per level
+        const int replicate_rows = getenv("ARAP_MG_REPLICATE_ROWS") ? atoi(getenv("ARAP_MG_REPLICATE_ROWS")) : 400000;
+        if (!mg_slice_hierarchy(H, my_rank, n_rows, V, global_of_local.data(), LH, err, replicate_rows)) return fail(ARAP_ERR_SOLVER, err);
+        mg_first_replicated = LH.first_replicated;
         { MgHierarchyHost().levels.swap(H.levels); }          // the global matrices are no longer needed
         mg.clear();
         std::vector<float> fscratch;
@@ -1305,49 +1309,56 @@ public:
     int vcycle_partitioned() {
         const int R = n_rows;
         const int L = (int)mg.size();
+        const int Lr = mg_first_replicated;                      // levels >= Lr are whole on every rank: no exchanges there
         MgLevelDev &m0 = *mg[0];
         MgVec *z = m0.x2.ptr;
         // down
         { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
         LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
-               free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
+                   free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
         { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec), SITE_MG0_R); if (rc) return rc; }
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             ARAP_DISPATCH_LANES(f.r_lanes, LAUNCH_PDL(ARAP_K_MG_RESTRICT, mg_restrict_presmooth_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
-                                                  f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
-                                                  c.x.ptr, cg.ptr));
+                                                      f.r_rowptr.ptr, f.r_colidx.ptr, f.r_val.ptr, f.r.ptr, c.inv_diag.ptr, (float)c.omega, c.b.ptr,
+                                                      c.x.ptr, cg.ptr));
+            if (l + 1 == Lr) {
+                // into the replicated part: every rank restricted the rows it owns (zeros elsewhere); sum them, then redo the
+                // pre-smoothing x = omega D^-1 b with the complete right-hand side
+                if (comm_counting) comm_allreduces += 1;
+                if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)c.b.ptr, 4 * c.n)) return fail(ARAP_ERR_CUDA, transport->error);
+                pdl_next_plain = true;
+                if (l + 1 < L - 1)
+                    LAUNCH_PDL(ARAP_K_MG_RESTRICT, mg_jacobi_kernel, grid_for((size_t)c.n), c.n, c.inv_diag.ptr, (float)c.omega, c.b.ptr, c.x.ptr);
+            }
             if (l + 1 == L - 1) break;
-            { int rc = exchange_level(l + 1, 0, c.x.ptr); if (rc) return rc; }
+            if (l + 1 < Lr) { int rc = exchange_level(l + 1, 0, c.x.ptr); if (rc) return rc; }
             ARAP_DISPATCH_LANES(c.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)c.n * LN), c.n,
-                                                  c.a_rowptr.ptr, c.a_colidx.ptr, c.a_val.ptr, c.b.ptr, c.x.ptr, c.r.ptr, cg.ptr));
-            { int rc = exchange_level(l + 1, 1, c.r.ptr); if (rc) return rc; }
+                                                      c.a_rowptr.ptr, c.a_colidx.ptr, c.a_val.ptr, c.b.ptr, c.x.ptr, c.r.ptr, cg.ptr));
+            if (l + 1 < Lr) { int rc = exchange_level(l + 1, 1, c.r.ptr); if (rc) return rc; }
         }
-        // coarsest: every rank restricted its own rows of b (zeros elsewhere); sum them and solve redundantly
+        // coarsest: solved redundantly on every rank
         MgLevelDev &cl = *mg[L - 1];
-        if (comm_counting) comm_allreduces += 1;
-        if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)cl.b.ptr, 4 * cl.n)) return fail(ARAP_ERR_CUDA, transport->error);
-        pdl_next_plain = true;
         launch_dense_solve(cl.n, cl.b.ptr, cl.x2.ptr);
         // up
         for (int l = L - 2; l >= 0; --l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             const int rows = (l == 0) ? R : f.n;
-            if (l + 1 < L - 1) { int rc = exchange_level(l + 1, 2, c.x2.ptr); if (rc) return rc; }
+            if (l + 1 < Lr) { int rc = exchange_level(l + 1, 2, c.x2.ptr); if (rc) return rc; }
             LAUNCH_PDL(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
-                   c.x2.ptr, f.x.ptr, cg.ptr);
+                       c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
                 { int rc = exchange_halo(f.x.ptr, sizeof(MgVec), SITE_MG0_X_POST); if (rc) return rc; }
                 LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
-                       hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                           hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
             } else {
-                { int rc = exchange_level(l, 3, f.x.ptr); if (rc) return rc; }
+                if (l < Lr) { int rc = exchange_level(l, 3, f.x.ptr); if (rc) return rc; }
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
-                                                      f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
-                                                      f.x.ptr, f.x2.ptr, cg.ptr));
+                                                          f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
+                                                          f.x.ptr, f.x2.ptr, cg.ptr));
             }
         }
-        return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg (one GPU) / cg->red (partitioned: CG_STAGE_MERGED)
+        return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg->red until CG_STAGE_MERGED
     }
 
     // Which levels the one-kernel tail covers: from the first level with at most ARAP_TAIL_ROWS rows down to the coarsest,

@@ -106,7 +106,7 @@ bool extract_rows(const HostCsr &M, const std::vector<int> &rows, const std::vec
 }  // namespace
 
 bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_local0, const int *global_of_local0,
-                        MgLocalHierarchy &out, std::string &error) {
+                        MgLocalHierarchy &out, std::string &error, int replicate_rows) {
     const int L = (int)H.levels.size();
     if (L < 2) { error = "global multigrid: the hierarchy has a single level"; return false; }
     if (H.coarse_inv.empty() && !H.coarse_dense_on_device) { error = "global multigrid: no dense coarsest level"; return false; }
@@ -119,6 +119,9 @@ bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_
     out.coarse_dense_on_device = H.coarse_dense_on_device;
     if (H.coarse_dense_on_device) out.coarse_A = H.levels.back().A;
     out.operator_complexity = H.operator_complexity;
+    int Lr = L - 1;                                         // first replicated level (>= 1)
+    while (Lr > 1 && H.levels[(size_t)Lr - 1].A.n_rows <= replicate_rows) --Lr;
+    out.first_replicated = Lr;
 
     std::vector<std::vector<int>> g2l((size_t)L), own((size_t)L);
     // ---- level 0: the engine's numbering
@@ -146,7 +149,7 @@ bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_
         const int n = hl.A.n_rows;
         const std::vector<int> &block = hl.block;
         ol.omega = hl.omega;
-        if (l == L - 1) {                                   // coarsest: replicated, global numbering
+        if (l >= Lr) {                                      // replicated: every row, global numbering
             g2l[(size_t)l].resize((size_t)n);
             for (int c = 0; c < n; ++c) g2l[(size_t)l][(size_t)c] = c;
             for (int c = 0; c < n; ++c) if (block[(size_t)c] == rank) own[(size_t)l].push_back(c);
@@ -154,6 +157,7 @@ bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_
             ol.n_halo = 0;
             ol.inv_diag = hl.inv_diag;
             ol.global_id = g2l[(size_t)l];
+            if (l < L - 1) ol.A = hl.A;
             continue;
         }
         for (int c = 0; c < n; ++c) if (block[(size_t)c] == rank) own[(size_t)l].push_back(c);
@@ -217,9 +221,14 @@ bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_
         const MgLevelHost &hl = H.levels[(size_t)l];
         MgLocalLevel &ol = out.levels[(size_t)l];
         MgLocalLevel &oc = out.levels[(size_t)l + 1];
+        if (l >= Lr) {                                      // between two replicated levels: the whole operators
+            ol.P = hl.P;
+            ol.R = hl.R;
+            continue;
+        }
         if (!extract_rows(hl.P, own[(size_t)l], g2l[(size_t)l + 1], oc.n_own + oc.n_halo, ol.P)) { error = "global multigrid: prolongation column outside the coarse halo"; return false; }
         std::vector<int> rrows;
-        if (l + 1 == L - 1) {                               // replicated coarsest level: all rows, only mine filled
+        if (l + 1 == Lr) {                                  // into the replicated part: all rows, only mine filled (summed over the ranks)
             rrows.assign((size_t)oc.n_own, -1);
             for (int c : own[(size_t)l + 1]) rrows[(size_t)c] = c;
         } else {

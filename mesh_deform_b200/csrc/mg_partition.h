@@ -40,7 +40,8 @@ struct MgLocalLevel {
 };
 
 struct MgLocalHierarchy {
-    std::vector<MgLocalLevel> levels;   // the last one is the coarsest: replicated on every rank, global numbering
+    std::vector<MgLocalLevel> levels;   // levels >= first_replicated (at least the coarsest) are replicated on every rank, global numbering
+    int first_replicated = 0;
     int n_coarse = 0;
     std::vector<double> coarse_inv;     // dense inverse of the coarsest operator, or empty when ...
     bool coarse_dense_on_device = false;   // ... the engine is to invert coarse_A on the device (see MgHierarchyHost)
@@ -51,7 +52,11 @@ struct MgLocalHierarchy {
 // Cut rank `rank`'s share out of a hierarchy built with blocks. global_of_local0: for every LOCAL fine index of the
 // engine (owned first, then the one-ring halo) its global vertex id. Returns false (with a message) when the hierarchy
 // cannot be used in partitioned form (no dense coarsest level, or a column outside the halo).
+// replicate_rows: levels (other than the finest) with at most this many rows are kept WHOLE on every rank, in global
+// numbering, like the coarsest level always is: the V-cycle then exchanges halos only on the large levels above them and
+// sums one right-hand side (every rank fills the rows it owns) where it enters the replicated part. A partitioned level
+// costs four halo exchanges per V-cycle -- pure latency on levels this small -- and replicated work is cheap there.
 bool mg_slice_hierarchy(const MgHierarchyHost &H, int rank, int n_owned0, int n_local0, const int *global_of_local0,
-                        MgLocalHierarchy &out, std::string &error);
+                        MgLocalHierarchy &out, std::string &error, int replicate_rows = 0);
 
 }  // namespace arap

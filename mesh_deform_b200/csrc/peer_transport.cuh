@@ -55,6 +55,7 @@ struct PeerReduceDev {
     const void *local_slots;                            // `world` slots of n values in my arena
     const unsigned long long *local_flag[kPeerMaxRanks];
     unsigned long long send_epoch;
+    unsigned int done;                                  // CTAs of the put kernel that have finished their stores
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -129,19 +130,26 @@ __global__ void __launch_bounds__(256) peer_wait_unpack_kernel(const PeerExchang
     }
 }
 
+// Both reduce kernels are grid-stride over the values: the CG's 8 scalars take one CTA, the right-hand side of a replicated
+// multigrid level (up to a few hundred thousand rows) a few dozen.
 template <typename T>
 __global__ void __launch_bounds__(256) peer_reduce_put_kernel(PeerReduceDev *site, const T *__restrict__ values) {
     const int n = site->n, world = site->world;
-    for (int t = threadIdx.x; t < n * world; t += blockDim.x) {
-        const int k = t / n, c = t - k * n;
+    const long long total = (long long)n * world;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / n), c = (int)(t - (long long)k * n);
         ((T *)site->remote_slot[k])[c] = values[c];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long epoch = ++site->send_epoch;
-        __threadfence_system();
-        for (int k = 0; k < world; ++k) st_release_sys(site->remote_flag[k], epoch);
+        const unsigned int prev = atomicAdd(&site->done, 1u);
+        if (prev == gridDim.x - 1) {
+            site->done = 0;
+            const unsigned long long epoch = ++site->send_epoch;
+            __threadfence_system();
+            for (int k = 0; k < world; ++k) st_release_sys(site->remote_flag[k], epoch);
+        }
     }
 }
 
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(256) peer_reduce_wait_kernel(PeerReduceDev *si
     __syncthreads();
     if (ok) {
         const volatile T *slots = (const volatile T *)site->local_slots;
-        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
             T sum = slots[c];
             for (int k = 1; k < world; ++k) sum += slots[(size_t)k * n + c];
             values[c] = sum;
@@ -353,9 +361,11 @@ private:
     template <typename T>
     int reduce(cudaStream_t stream, int site, T *dev, int n, int kind) {
         if (site < 0 || site >= (int)kinds.size() || kinds[(size_t)site] != kind) { error = "peer transport: reduce site was not configured"; return -1; }
-        (void)n;
-        peer_reduce_put_kernel<T><<<1, 256, 0, stream>>>(rd_dev + site, dev);
-        peer_reduce_wait_kernel<T><<<1, 256, 0, stream>>>(rd_dev + site, dev, error_flag);
+        int pgrid = (int)(((long long)n * world + 4095) / 4096), wgrid = (n + 4095) / 4096;
+        pgrid = pgrid < 1 ? 1 : (pgrid > 128 ? 128 : pgrid);
+        wgrid = wgrid < 1 ? 1 : (wgrid > 64 ? 64 : wgrid);
+        peer_reduce_put_kernel<T><<<pgrid, 256, 0, stream>>>(rd_dev + site, dev);
+        peer_reduce_wait_kernel<T><<<wgrid, 256, 0, stream>>>(rd_dev + site, dev, error_flag);
         return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
     }
     void close_peers() {

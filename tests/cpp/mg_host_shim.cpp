@@ -54,6 +54,10 @@ void mgshim_block(int l, int *out) { for (size_t i = 0; i < g_h.levels[l].block.
 int mgshim_slice(int rank, int n_owned0, int n_local0, const int *global_of_local0) {
     return arap::mg_slice_hierarchy(g_h, rank, n_owned0, n_local0, global_of_local0, g_local, g_error) ? 1 : 0;
 }
+int mgshim_slice_replicated(int rank, int n_owned0, int n_local0, const int *global_of_local0, int replicate_rows) {
+    return arap::mg_slice_hierarchy(g_h, rank, n_owned0, n_local0, global_of_local0, g_local, g_error, replicate_rows) ? 1 : 0;
+}
+int mgshim_first_replicated() { return g_local.first_replicated; }
 const char *mgshim_error() { return g_error.c_str(); }
 static const arap::HostCsr &pick_local(int l, int which) { return which == 0 ? g_local.levels[l].A : which == 1 ? g_local.levels[l].P : g_local.levels[l].R; }
 void mgshim_local_dims(int l, int which, int *rows, int *cols, int *nnz) { const auto &m = pick_local(l, which); *rows = m.n_rows; *cols = m.n_cols; *nnz = m.nnz(); }

@@ -530,16 +530,23 @@ def _run_partitioned(P, F, idx, tgt, world, key, iters, transport=None, **kw):
     return pos, parts[0].solver_stats()
 
 
+@pytest.mark.parametrize("replicate_rows", ["0", "2000", None])
 @pytest.mark.parametrize("transport", ["host", "peer"])
-def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
+def test_partitioned_mesh_in_quadrants_matches_oracle(transport, replicate_rows, monkeypatch):
     """A 2 x 2 block partition instead of strips: two ranks have three neighbours (one of them only across the corner), the halo plans of
-    the multigrid levels differ from rank to rank. Same parity bar against the unpartitioned oracle."""
+    the multigrid levels differ from rank to rank. Same parity bar against the unpartitioned oracle.
+    replicate_rows (ARAP_MG_REPLICATE_ROWS): "0" keeps every level but the coarsest partitioned (four exchanges per level), "2000"
+    replicates the small ones, None is the default (everything below the fine level is replicated at this size)."""
+    if replicate_rows is None:
+        monkeypatch.delenv("ARAP_MG_REPLICATE_ROWS", raising=False)
+    else:
+        monkeypatch.setenv("ARAP_MG_REPLICATE_ROWS", replicate_rows)
     nx, nz, iters = 200, 160, 4            # 32k vertices: three multigrid levels, so a partitioned intermediate level
     P, F = G.grid_plane(nx, nz)
     idx, tgt = G.grid_constraints(nx, nz, P)
     owner = ((P[:, 0] > np.median(P[:, 0])).astype(np.int32) + 2 * (P[:, 2] > np.median(P[:, 2])).astype(np.int32)).astype(np.int32)
     kind = capi.TRANSPORT_PEER_IN_PROCESS if transport == "peer" else capi.TRANSPORT_IN_PROCESS
-    key = 3001 if transport == "peer" else 3002
+    key = (3001 if transport == "peer" else 3002) + 10 * (["0", "2000", None].index(replicate_rows))
     # (position_tolerance 1e-8: with the default 3e-8 this gently bent, fine grid lands at 7.8e-7 relative energy -- inside the
     #  1e-6 bar, but this test is about the partition plumbing, not about the margin of the stopping rule)
     parts = [capi.PartitionedDeformation(P, F, owner, r, 4, kind, key, np.float64, position_tolerance=1e-8) for r in range(4)]
@@ -563,7 +570,10 @@ def test_partitioned_mesh_in_quadrants_matches_oracle(transport):
     err = np.abs(pos - omesh).max() / bbox_diag(P)
     de = abs(sum(p.local_energy() for p in parts) - o.energy()) / o.energy()
     st = parts[0].solver_stats()
-    print("quadrants", transport, "err/diag", err, "rel dE", de, "levels", st["mg_levels"], "global", st["mg_global"])
+    print("quadrants", transport, replicate_rows, "err/diag", err, "rel dE", de, "levels", st["mg_levels"], "global", st["mg_global"],
+          "exchanges / all-reduces per CG iteration", st["comm_exchanges_per_cg_iteration"], st["comm_allreduces_per_cg_iteration"])
+    assert st["comm_allreduces_per_cg_iteration"] == 2                      # the replicated levels' right-hand side + the CG scalars
+    assert st["comm_exchanges_per_cg_iteration"] == (4 + 4 * (st["mg_levels"] - 2) if replicate_rows == "0" else 4 if replicate_rows is None else st["comm_exchanges_per_cg_iteration"])
     assert err <= POS_TOL and de <= E_TOL and st["mg_global"] == 1 and st["mg_levels"] >= 3
 
 

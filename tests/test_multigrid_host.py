@@ -128,9 +128,12 @@ def quadrant_owner(P):
     return ((P[:, 0] > cx).astype(np.int32) + 2 * (P[:, 2] > cz).astype(np.int32)).astype(np.int32)
 
 
+@pytest.mark.parametrize("replicate_rows", [0, 60, 100000])
 @pytest.mark.parametrize("world,kind", [(1, "strips"), (2, "strips"), (3, "strips"), (4, "quadrants")])
-def test_partitioned_vcycle_equals_global_vcycle(shim, world, kind):
-    """Every rank's slice + the exchange sequence of Engine::vcycle_partitioned == the V-cycle of the whole hierarchy."""
+def test_partitioned_vcycle_equals_global_vcycle(shim, world, kind, replicate_rows):
+    """Every rank's slice + the exchange sequence of Engine::vcycle_partitioned == the V-cycle of the whole hierarchy.
+    replicate_rows: levels with at most that many rows are kept whole on every rank (0: only the coarsest; 100000: all but
+    the finest)."""
     nx, nz = 40, 36
     P, F = G.grid_plane(nx, nz)
     idx, _ = G.grid_constraints(nx, nz, P)
@@ -150,8 +153,14 @@ def test_partitioned_vcycle_equals_global_vcycle(shim, world, kind):
     for r in range(world):
         part = PT.build_local_part(F, owner, r, world)
         l2g = np.ascontiguousarray(part.local_to_global, np.int32)
-        ok = shim.mgshim_slice(r, part.n_owned, part.n_local, _p(l2g))
+        ok = shim.mgshim_slice_replicated(r, part.n_owned, part.n_local, _p(l2g), replicate_rows)
         assert ok, shim.mgshim_error().decode()
+        Lr = shim.mgshim_first_replicated()
+        assert 1 <= Lr <= nl - 1
+        if replicate_rows == 0:
+            assert Lr == nl - 1
+        if replicate_rows >= 100000:
+            assert Lr == 1
         lv = []
         for l in range(nl):
             n_own, n_halo, n_nbr, n_send, omega = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_double()
@@ -227,21 +236,27 @@ def test_partitioned_vcycle_equals_global_vcycle(shim, world, kind):
             f, cl = ranks[r][l], ranks[r][c]
             rows = f["R"].shape[0]
             bb[c][r][:rows] = f["R"] @ res[l][r]
+        if c == Lr:                                             # entering the replicated part: every rank filled its rows; the all-reduce
+            total = sum(bb[c][r] for r in range(world))
+            for r in range(world):
+                bb[c][r] = total.copy()
+        for r in range(world):
+            cl = ranks[r][c]
+            rows = ranks[r][l]["R"].shape[0]
             x[c][r][:rows] = (cl["omega"] * cl["invd"])[:rows, None] * bb[c][r][:rows]
         if c == nl - 1:
             break
-        exchange(c, x[c])
+        exchange(c, x[c])                                       # no-op on replicated levels (no neighbours)
         for r in range(world):
             cl = ranks[r][c]
             n = cl["n_own"]
             res[c][r][:n] = bb[c][r][:n] - cl["A"] @ x[c][r]
         exchange(c, res[c])
-    total = sum(bb[nl - 1][r] for r in range(world))            # the all-reduce
     for r in range(world):
-        x2[nl - 1][r] = inv @ total
+        x2[nl - 1][r] = inv @ bb[nl - 1][r]
     for l in range(nl - 2, -1, -1):
         c = l + 1
-        if c < nl - 1:
+        if c < Lr:
             exchange(c, x2[c])
         for r in range(world):
             f = ranks[r][l]
