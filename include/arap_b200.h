@@ -142,6 +142,9 @@ typedef struct arap_solver_stats {
     int32_t comm_exchanges_per_cg_iteration;    /* halo exchanges (one per gathered vector and partitioned multigrid level) */
     int32_t comm_allreduces_per_cg_iteration;   /* all-reduces / all-gathers (CG scalars, replicated coarse levels) */
     int64_t comm_halo_bytes_per_cg_iteration;   /* bytes this rank sends in those exchanges */
+    int32_t tile_max_halo;         /* > 0: the one-ring kernels stage their neighbourhood through shared memory in tiles of 256 rows;
+                                    * this is the largest tile halo (distinct neighbours outside the tile). 0: untiled kernels */
+    int32_t reserved0;
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 

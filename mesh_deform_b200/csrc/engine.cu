@@ -8,6 +8,7 @@
 #include "../../include/arap_b200.h"
 #include "kernels.cuh"
 #include "mg_kernels.cuh"
+#include "tile_kernels.cuh"
 #include "mg_setup.h"
 #include "mg_partition.h"
 #include "partition.cuh"
@@ -221,6 +222,13 @@ public:
         end_launch();                                                                \
     } while (0)
 
+#define LAUNCH_PDL_SMEM(id, kernel, grid, smem, ...)                                  \
+    do {                                                                             \
+        begin_launch(id);                                                            \
+        launch_pdl(kernel, (unsigned)(grid), (unsigned)kBlock, (size_t)(smem), __VA_ARGS__); \
+        end_launch();                                                                \
+    } while (0)
+
 // Communication call sites of the partitioned solver (partition.cuh, SiteSpec): the same numbers on every rank.
 enum {
     SITE_CUR4 = 0, SITE_QUAT, SITE_CG_D, SITE_MG0_X_PRE, SITE_MG0_R, SITE_MG0_X_POST, SITE_COARSE_B,
@@ -296,6 +304,13 @@ public:
     DeviceBuffer<float> hot_weight_f32;            // fp32 copy for the multigrid preconditioner
     DeviceBuffer<unsigned char> free_mask;         // 1 = free row (internal order)
     bool have_perm = false;
+    // tiles of kTile consecutive rows with their halo lists and tile-local column indices (tile_kernels.cuh)
+    DeviceBuffer<int> tile_halo, tile_halo_count, tile_scalars;      // tile_scalars: [0] largest halo, [1] a tile did not fit
+    DeviceBuffer<unsigned short> tile_colidx;
+    bool tiles_built = false, use_tiles = false;
+    int n_tiles = 0, tile_max_halo = 0;
+    TileView tile_view() const { return TileView{tile_halo.ptr, tile_halo_count.ptr, tile_colidx.ptr, n_tiles}; }
+    size_t tile_smem(size_t record_bytes, int arrays) const { return (size_t)(kTile + tile_max_halo) * record_bytes * (size_t)arrays; }
     std::vector<int> faces_host;                   // kept until the vertex order has been decided
     std::vector<int> mg_visit_order;               // Morton sequence of internal indices: aggregation order of the fine level
     DeviceBuffer<Vec4T<S>> rest4, cur4, quat;      // _p, _pprime, _rotations
@@ -633,6 +648,8 @@ public:
         if (V > 0)
             LAUNCH(ARAP_K_MISC, perm_csr_fill_kernel<S>, grid_for((size_t)V), V, perm.ptr, iperm.ptr, rowptr.ptr, colidx.ptr, weight.ptr,
                    hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, hot_weight_f32.ptr);
+        // ---- tiles of the hot CSR (topology and order are fixed per handle: built once)
+        if (!tiles_built) { int rc = build_tiles(); if (rc) return rc; }
         // ---- initializeMeshGeometry / Rotations / Constraints into the solver layout (arap.h:162-168,246-249,277-281)
         ARAP_CUDA(rest4.ensure((size_t)V));
         ARAP_CUDA(cur4.ensure((size_t)V));
@@ -731,12 +748,117 @@ public:
         // iterating while another one is still allocating: cudaFree waits for ALL device work, spinning kernels included.
         if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
         stats.cg_graph = step_graph_exec ? 2 : (cg_graph_exec ? 1 : 0);
+        stats.tile_max_halo = use_tiles ? tile_max_halo : 0;
         pdl_next_plain = true;
         stats.mg_global = (use_mg && mg_global) ? 1 : 0;
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
         dirty = false;                                                   // arap.h:119
         prepared = true;
         return ARAP_OK;
+    }
+
+    // Tile structure for the staged one-ring kernels (tile_kernels.cuh); falls back to the untiled kernels (use_tiles = false)
+    // when a tile's halo does not fit, for tiny meshes, for batches (their members are far smaller than the halo capacity
+    // would allow... a member's rows all see each other) and with ARAP_TILES=0.
+    int build_tiles() {
+        tiles_built = true;
+        use_tiles = false;
+        const int R = n_rows;
+        if (getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) == 0) return ARAP_OK;
+        if (R < 2 * kTile || nnz <= 0) return ARAP_OK;
+        n_tiles = (R + kTile - 1) / kTile;
+        ARAP_CUDA(tile_halo.ensure((size_t)n_tiles * kTileHaloCap));
+        ARAP_CUDA(tile_halo_count.ensure((size_t)n_tiles));
+        ARAP_CUDA(tile_colidx.ensure((size_t)nnz));
+        ARAP_CUDA(tile_scalars.ensure(2));
+        ARAP_CUDA(cudaMemsetAsync(tile_scalars.ptr, 0, 2 * sizeof(int), stream));
+        LAUNCH(ARAP_K_MISC, build_tiles_kernel, n_tiles, R, hot_rowptr.ptr, hot_colidx.ptr, tile_halo.ptr, tile_halo_count.ptr, tile_colidx.ptr,
+               tile_scalars.ptr, tile_scalars.ptr + 1);
+        int h[2] = {0, 0};
+        ARAP_CUDA(cudaMemcpyAsync(h, tile_scalars.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        if (h[1] != 0) return ARAP_OK;                                  // a tile did not fit: untiled kernels
+        tile_max_halo = (h[0] + 31) & ~31;
+        // dynamic shared memory of the staged kernels: (kTile + largest halo) records per staged array
+        const size_t s_local = tile_smem(sizeof(Vec4T<S>), 2), s_rhs = tile_smem(sizeof(Vec4T<S>), 3), s_vec = tile_smem(sizeof(MgVec), 1);
+        if (s_rhs > 200 * 1024) return ARAP_OK;
+        ARAP_CUDA(cudaFuncSetAttribute(local_step_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_local));
+        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_rhs));
+        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_rhs));
+        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_residual_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
+        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_postsmooth_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
+        ARAP_CUDA(cudaFuncSetAttribute(cg_spmv_z_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
+        use_tiles = true;
+        return ARAP_OK;
+    }
+
+    // ---- launches of the one-ring kernels: staged through shared memory when the tile structure exists ------------------
+    void launch_local_step() {
+        const int R = n_rows;
+        if (use_tiles) {
+            const size_t sm = tile_smem(sizeof(Vec4T<S>), 2);
+            LAUNCH_PDL_SMEM(ARAP_K_LOCAL_STEP, local_step_tiled_kernel<S>, std::min(n_tiles, reduce_grid(local_step_tiled_kernel<S>, (size_t)R, sm)), sm, R, tile_view(),
+                            (const int *)hot_rowptr.ptr, (const S *)hot_weight.ptr, (const Vec4T<S> *)rest4.ptr, (const Vec4T<S> *)cur4.ptr, quat.ptr,
+                            redo_list.ptr, redo_count.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_LOCAL_STEP, local_step_kernel<S>, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
+                       redo_list.ptr, redo_count.ptr);
+        }
+        LAUNCH_PDL(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
+                   quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
+    }
+    template <bool MG>
+    void launch_rhs_residual(double omega0, float4 *x0) {
+        const int R = n_rows;
+        if (use_tiles) {
+            const size_t sm = tile_smem(sizeof(Vec4T<S>), 3);
+            LAUNCH_PDL_SMEM(ARAP_K_RHS_RESIDUAL, (rhs_residual_tiled_kernel<S, MG>), std::min(n_tiles, reduce_grid(rhs_residual_tiled_kernel<S, MG>, (size_t)R, sm)), sm, R,
+                            tile_view(), (const int *)hot_rowptr.ptr, (const S *)hot_weight.ptr, (const Vec4T<S> *)rest4.ptr, (const Vec4T<S> *)cur4.ptr,
+                            (const Vec4T<S> *)quat.ptr, (const double *)inv_diag.ptr, omega0, cg_r.ptr, cg_d.ptr, cg_x.ptr, x0, partials.ptr, counter.ptr, cg.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, MG>), reduce_grid(rhs_residual_kernel<S, MG>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
+                       hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, omega0, cg_r.ptr, cg_d.ptr, cg_x.ptr, x0, partials.ptr, counter.ptr, cg.ptr);
+        }
+    }
+    void launch_fine_residual() {
+        const int R = n_rows;
+        MgLevelDev &m0 = *mg[0];
+        if (use_tiles) {
+            const size_t sm = tile_smem(sizeof(MgVec), 1);
+            LAUNCH_PDL_SMEM(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_tiled_kernel, std::min(n_tiles, reduce_grid(mg_fine_residual_tiled_kernel, (size_t)R, sm)), sm, R,
+                            tile_view(), (const int *)hot_rowptr.ptr, (const float *)hot_weight_f32.ptr, (const unsigned char *)free_mask.ptr,
+                            (const Vec3d *)cg_r.ptr, (const MgVec *)m0.x.ptr, m0.r.ptr, (const CgScalars *)cg.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
+                       free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
+        }
+    }
+    void launch_fine_postsmooth() {
+        const int R = n_rows;
+        MgLevelDev &m0 = *mg[0];
+        if (use_tiles) {
+            const size_t sm = tile_smem(sizeof(MgVec), 1);
+            LAUNCH_PDL_SMEM(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_tiled_kernel, std::min(n_tiles, reduce_grid(mg_fine_postsmooth_tiled_kernel, (size_t)R, sm)), sm,
+                            R, tile_view(), (const int *)hot_rowptr.ptr, (const float *)hot_weight_f32.ptr, (const unsigned char *)free_mask.ptr,
+                            (const double *)inv_diag.ptr, m0.omega, (const Vec3d *)cg_r.ptr, (const MgVec *)m0.x.ptr, m0.x2.ptr, partials.ptr, counter.ptr, cg.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
+                       hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, m0.x.ptr, m0.x2.ptr, partials.ptr, counter.ptr, cg.ptr);
+        }
+    }
+    void launch_spmv_z() {
+        const int R = n_rows;
+        MgLevelDev &m0 = *mg[0];
+        if (use_tiles) {
+            const size_t sm = tile_smem(sizeof(MgVec), 1);
+            LAUNCH_PDL_SMEM(ARAP_K_CG_SPMV, cg_spmv_z_tiled_kernel<S>, std::min(n_tiles, reduce_grid(cg_spmv_z_tiled_kernel<S>, (size_t)R, sm)), sm, R, tile_view(),
+                            (const int *)hot_rowptr.ptr, (const S *)hot_weight.ptr, (const unsigned char *)free_mask.ptr, (const float4 *)m0.x2.ptr, cg_w.ptr,
+                            partials.ptr, counter.ptr, cg.ptr);
+        } else {
+            LAUNCH_PDL(ARAP_K_CG_SPMV, cg_spmv_z_kernel<S>, reduce_grid(cg_spmv_z_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
+                       free_mask.ptr, (const float4 *)m0.x2.ptr, cg_w.ptr, partials.ptr, counter.ptr, cg.ptr);
+        }
     }
 
     // bounding-box diagonal of the rest pose: the length scale of the position-error stopping rule. Partitioned mode with
@@ -821,8 +943,19 @@ public:
                     if (std::abs(a - b) <= window) ++near_user;
                     if (std::abs(rank_of[(size_t)a] - rank_of[(size_t)b]) <= window) ++near_morton;
                 }
+            // With the tiled kernels (tile_kernels.cuh) what matters is how many mesh edges leave their tile of kTile consecutive
+            // rows: every such edge puts a vertex on the tile's halo list. Count them in both orders.
+            long long cut_user = 0, cut_morton = 0;
+            for (size_t f = 0; f + 2 < faces_host.size(); f += 3)
+                for (int e = 0; e < 3; ++e) {
+                    const int a = faces_host[f + e], b = faces_host[f + (e + 1) % 3];
+                    if (a >= owned || b >= owned) continue;
+                    if (a / kTile != b / kTile) ++cut_user;
+                    if (rank_of[(size_t)a] / kTile != rank_of[(size_t)b] / kTile) ++cut_morton;
+                }
             const bool force = env && atoi(env) == 2;
-            const bool renumber = force || (double)near_morton > 1.15 * (double)near_user;
+            const bool tiling = !(getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) == 0) && owned >= 2 * kTile;
+            const bool renumber = force || (tiling ? (double)cut_morton < 0.8 * (double)cut_user : (double)near_morton > 1.15 * (double)near_user);
             mg_visit_order.resize((size_t)V);
             for (int i = 0; i < V; ++i) mg_visit_order[(size_t)i] = i;
             if (renumber) {
@@ -1314,8 +1447,7 @@ public:
         MgVec *z = m0.x2.ptr;
         // down
         { int rc = exchange_halo(m0.x.ptr, sizeof(MgVec), SITE_MG0_X_PRE); if (rc) return rc; }      // x0 = omega D^-1 r was made on owned rows
-        LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
-                   free_mask.ptr, cg_r.ptr, m0.x.ptr, m0.r.ptr, cg.ptr);
+        launch_fine_residual();
         { int rc = exchange_halo(m0.r.ptr, sizeof(MgVec), SITE_MG0_R); if (rc) return rc; }
         for (int l = 0; l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
@@ -1349,8 +1481,7 @@ public:
                        c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
                 { int rc = exchange_halo(f.x.ptr, sizeof(MgVec), SITE_MG0_X_POST); if (rc) return rc; }
-                LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
-                           hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                launch_fine_postsmooth();
             } else {
                 if (l < Lr) { int rc = exchange_level(l, 3, f.x.ptr); if (rc) return rc; }
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
@@ -1466,8 +1597,7 @@ public:
         for (int l = 0; l <= top && l + 1 < L; ++l) {
             MgLevelDev &f = *mg[l], &c = *mg[l + 1];
             if (l == 0) {
-                LAUNCH_PDL(ARAP_K_MG_FINE_RESIDUAL, mg_fine_residual_kernel, grid_for((size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight_f32.ptr,
-                       free_mask.ptr, cg_r.ptr, f.x.ptr, f.r.ptr, cg.ptr);
+                launch_fine_residual();
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_RESIDUAL, mg_csr_residual_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.b.ptr, f.x.ptr, f.r.ptr, cg.ptr));
@@ -1497,8 +1627,7 @@ public:
                 LAUNCH_PDL(ARAP_K_MG_PROLONG, mg_prolong_add_kernel, grid_for((size_t)rows), rows, f.p_rowptr.ptr, f.p_colidx.ptr, f.p_val.ptr,
                        c.x2.ptr, f.x.ptr, cg.ptr);
             if (l == 0) {
-                LAUNCH_PDL(ARAP_K_MG_FINE_POSTSMOOTH, mg_fine_postsmooth_kernel, reduce_grid(mg_fine_postsmooth_kernel, (size_t)R), R, hot_rowptr.ptr,
-                       hot_colidx.ptr, hot_weight_f32.ptr, free_mask.ptr, inv_diag.ptr, f.omega, cg_r.ptr, f.x.ptr, z, partials.ptr, counter.ptr, cg.ptr);
+                launch_fine_postsmooth();
             } else {
                 ARAP_DISPATCH_LANES(f.a_lanes, LAUNCH_PDL(ARAP_K_MG_CSR_POSTSMOOTH, mg_csr_postsmooth_kernel<LN>, grid_for((size_t)f.n * LN), f.n,
                                                       f.a_rowptr.ptr, f.a_colidx.ptr, f.a_val.ptr, f.inv_diag.ptr, (float)f.omega, f.b.ptr,
@@ -1545,8 +1674,7 @@ public:
         MgLevelDev &m0 = *mg[0];
         { int rc = vcycle(); if (rc) return rc; }
         { int rc = exchange_halo(m0.x2.ptr, sizeof(MgVec), SITE_CG_D); if (rc) return rc; }
-        LAUNCH_PDL(ARAP_K_CG_SPMV, cg_spmv_z_kernel<S>, reduce_grid(cg_spmv_z_kernel<S>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr,
-                   free_mask.ptr, (const float4 *)m0.x2.ptr, cg_w.ptr, partials.ptr, counter.ptr, cg.ptr);
+        launch_spmv_z();
         { int rc = reduce_stage(CG_STAGE_MERGED, 8); if (rc) return rc; }
         LAUNCH_PDL(ARAP_K_CG_UPDATE_MG, cg_fused_update_kernel, reduce_grid(cg_fused_update_kernel, ((size_t)n3 + 1) / 2), n3, inv_diag.ptr, m0.omega,
                    (const float *)m0.x2.ptr, (const double *)cg_w.ptr, (double *)cg_d.ptr, (double *)cg_ad.ptr, (double *)cg_x.ptr, (double *)cg_r.ptr,
@@ -1594,12 +1722,9 @@ public:
         MgLevelDev &m0 = *mg[0];
         // quat[] starts as identity (initializeRotations), which is already a usable Newton seed: the hot kernel
         // certifies convergence to the SVD's rotation per vertex and lists the vertices that need the Jacobi SVD.
-        LAUNCH_PDL(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
-                   redo_list.ptr, redo_count.ptr);
-        LAUNCH_PDL(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                   quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
-        LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
-                   hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+        launch_local_step();
+        
+        launch_rhs_residual<true>(mg[0]->omega, mg[0]->x.ptr);
     }
 
     int build_step_graph() {
@@ -1720,12 +1845,10 @@ public:
         const int R = n_rows, G = grid_for((size_t)R);
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                       quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+            launch_rhs_residual<true>(mg[0]->omega, mg[0]->x.ptr);
             { int rc = reduce_stage(CG_STAGE_START_MG, 5); if (rc) return rc; }
         } else {
-            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                       quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+            launch_rhs_residual<false>(1.0, (float4 *)nullptr);
             { int rc = reduce_stage(CG_STAGE_START_JACOBI, 5); if (rc) return rc; }
         }
         const int max_it = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : 20000;
@@ -1812,10 +1935,8 @@ public:
             return finish_iterate();
         }
         for (int it = 0; it < n; ++it) {
-            LAUNCH_PDL(ARAP_K_LOCAL_STEP, local_step_kernel<S>, G, R, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr,
-                       redo_list.ptr, redo_count.ptr);
-            LAUNCH_PDL(ARAP_K_LOCAL_STEP_REDO, local_step_redo_kernel<S>, sm_count * 2, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, rest4.ptr, cur4.ptr,
-                       quat.ptr, redo_list.ptr, redo_count.ptr, redo_done.ptr);
+            launch_local_step();
+            
             { int rc = exchange_halo(quat.ptr, sizeof(Vec4T<S>), SITE_QUAT); if (rc) return rc; }
             int rc = global_step();
             if (rc) return rc;
@@ -1887,11 +2008,9 @@ public:
         pdl_next_plain = true;
         if (use_mg) {
             MgLevelDev &m0 = *mg[0];
-            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, true>), reduce_grid(rhs_residual_kernel<S, true>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
-                       hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, m0.omega, cg_r.ptr, cg_d.ptr, cg_x.ptr, m0.x.ptr, partials.ptr, counter.ptr, cg.ptr);
+            launch_rhs_residual<true>(mg[0]->omega, mg[0]->x.ptr);
         } else {
-            LAUNCH_PDL(ARAP_K_RHS_RESIDUAL, (rhs_residual_kernel<S, false>), reduce_grid(rhs_residual_kernel<S, false>, (size_t)R), R, hot_rowptr.ptr, hot_colidx.ptr,
-                       hot_weight.ptr, rest4.ptr, cur4.ptr, quat.ptr, inv_diag.ptr, 1.0, cg_r.ptr, cg_d.ptr, cg_x.ptr, (float4 *)nullptr, partials.ptr, counter.ptr, cg.ptr);
+            launch_rhs_residual<false>(1.0, (float4 *)nullptr);
         }
         pdl_next_plain = true;
         ARAP_CUDA(staging.ensure(sizeof(double) * 3 * (size_t)(n_free > 0 ? n_free : 1)));
