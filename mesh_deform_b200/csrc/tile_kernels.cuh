@@ -24,7 +24,7 @@
 namespace arap {
 
 constexpr int kTile = kBlock;            // rows per tile = threads per CTA
-constexpr int kTileHaloCap = 768;        // capacity of a tile's halo list (entries of the global table per tile)
+constexpr int kTileHaloCap = 512;        // capacity of a tile's halo list: (256 + 512) staged records keep 3-4 CTAs of the fp64 kernels on an SM
 constexpr int kTileEdgeCap = 4096;       // candidate slots while building a tile (entries with a column outside the tile)
 constexpr int kTileChunk = 2;            // fp64 kernels: row entries whose index / weight loads are batched
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) build_tiles_kernel(int n_rows, const i
     {   // the compacted heads arrived in atomic order: sort them (<= kTileHaloCap entries)
         int pow2 = 1;
         while (pow2 < nu) pow2 <<= 1;
-        // uniq has kTileHaloCap (= 768) slots, pow2 may reach 1024: sort in ext[] (free again) instead
+        // sorted in ext[] (free again)
         for (int i = threadIdx.x; i < pow2; i += blockDim.x) ext[i] = i < nu ? uniq[i] : 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= pow2; k <<= 1)

@@ -50,6 +50,26 @@ def test_headers_compile_standalone(cpp_build, tmp_path):
                                os.path.join(ROOT, "include"), str(src)])
 
 
+def test_openmesh_adapter_header_compiles_against_the_openmesh_test_double(cpp_build, tmp_path):
+    """deform/openmesh_adapter.h (reference inc/deform/openmesh_adapter.h:24-118) is a real translation unit in this suite:
+    OpenMesh is not installed, so it is compiled against tests/cpp/mock_openmesh, a test double of the OpenMesh calls the
+    adapter and the demos make. Without that include path the header must refuse with a readable message."""
+    src = tmp_path / "t.cpp"
+    src.write_text("#include <deform/openmesh_adapter.h>\n#include <deform/arap.h>\n"
+                   "int main() { OpenMesh::TriMesh_ArrayKernelT<> m; deform::OpenMeshAdapter<> a(m); return a.numberOfVertices(); }\n")
+    base = ["g++", "-std=c++11", "-fsyntax-only", "-I", os.path.join(ROOT, "inc"), "-I", os.path.join(ROOT, "include")]
+    subprocess.check_call(base + ["-I", os.path.join(cpp_build, "mock_openmesh"), str(src)])
+    bad = subprocess.run(base + [str(src)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "needs OpenMesh" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_openmesh_adapter_cpp(cpp_build):
+    """reference tests/test_cotan.cpp:20-54 with its OpenMesh calls verbatim + a deformation through OpenMeshAdapter."""
+    out = subprocess.run([os.path.join(cpp_build, "test_openmesh_adapter")], capture_output=True, text=True)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.gpu
 def test_cotan_cpp_reference_test(cpp_build):
     out = subprocess.run([os.path.join(cpp_build, "test_cotan")], capture_output=True, text=True)
