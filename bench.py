@@ -691,6 +691,7 @@ def main():
     prepare_ms = 1e3 * (time.perf_counter() - t0)
     assert rc == capi.ARAP_OK
     prepare_host_setup_ms = arap.solver_stats()["setup_host_ms"]
+    prepare_device_setup_ms = arap.solver_stats()["setup_device_ms"]
     rp, ci, _ = arap.cotanWeights()
     nnz = int(ci.size)
     _, n_free = arap.freeIdxMap()
@@ -879,7 +880,7 @@ def main():
                "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
         "cold_start": {"what": "ARAP iterations 1..%d right after the handle move (the warm-up), one arap_iterate(1) each" % args.warmup,
                        "cg_iterations": cold["cg_iterations"], "ms": cold["ms"]},
-        "prepare_ms": prepare_ms, "prepare_host_setup_ms": prepare_host_setup_ms,
+        "prepare_ms": prepare_ms, "prepare_host_setup_ms": prepare_host_setup_ms, "prepare_device_setup_ms": prepare_device_setup_ms,
         "frame": {"protocol": "setConstraint(handles) + deform(5) incl. the dirty rebuild: H2D rest pose, weights/CSR, 5 iterations, D2H (reference demo loop)",
                   "ms": frame_ms, "h2d_bytes": int(V * 3 * s + 10 * (4 + 3 * 8)), "d2h_bytes": int(V * 3 * s),
                   "iterations_per_s": 5.0 / (frame_ms * 1e-3)},

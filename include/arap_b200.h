@@ -133,7 +133,7 @@ typedef struct arap_solver_stats {
     int32_t last_converged;
     int32_t mg_levels;             /* 0 when the Jacobi preconditioner is in use */
     double mg_operator_complexity;
-    double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare */
+    double setup_host_ms;          /* host time spent building the multigrid hierarchy in the last arap_prepare (0: built on the device) */
     int32_t cg_graph;              /* 1: a CG iteration (with its exchanges, if partitioned) is replayed from a CUDA graph;
                                     * 2: the whole ARAP iteration is one graph whose CG loop runs on the device (WHILE node) */
     int32_t mg_global;             /* 1: partitioned mode with the global hierarchy (arap_partition_set_global_mesh) */
@@ -145,6 +145,7 @@ typedef struct arap_solver_stats {
     int32_t tile_max_halo;         /* > 0: the one-ring kernels stage their neighbourhood through shared memory in tiles of 256 rows;
                                     * this is the largest tile halo (distinct neighbours outside the tile). 0: untiled kernels */
     int32_t reserved0;
+    double setup_device_ms;        /* wall time of the multigrid setup when it ran on the device (setup_host_ms is then 0) */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 

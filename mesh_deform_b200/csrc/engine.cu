@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "mg_kernels.cuh"
 #include "tile_kernels.cuh"
+#include "mg_setup_device.cuh"
 #include "mg_setup.h"
 #include "mg_partition.h"
 #include "partition.cuh"
@@ -1216,7 +1217,230 @@ public:
         return ARAP_OK;
     }
 
+
+    // ---- multigrid setup ON THE DEVICE (mg_setup_device.cuh): the same smoothed-aggregation hierarchy as mg_setup.cpp ----
+    struct DevCsr {
+        DeviceBuffer<int> rowptr, colidx;
+        DeviceBuffer<double> val;
+        int n_rows = 0, n_cols = 0, nnz = 0;
+    };
+    // row lengths in `len` (n entries) -> out.rowptr (n + 1), allocates colidx / val; one host round trip for nnz
+    int csr_allocate(DevCsr &out, int n_rows_, int n_cols_, const int *len) {
+        out.n_rows = n_rows_;
+        out.n_cols = n_cols_;
+        ARAP_CUDA(out.rowptr.ensure((size_t)n_rows_ + 1));
+        { int rc = exclusive_scan(len, n_rows_, out.rowptr.ptr); if (rc) return rc; }
+        ARAP_CUDA(cudaMemcpyAsync(&out.nnz, out.rowptr.ptr + n_rows_, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(out.colidx.ensure((size_t)out.nnz));
+        ARAP_CUDA(out.val.ensure((size_t)out.nnz));
+        return ARAP_OK;
+    }
+    int upload_level_matrix(const DevCsr &m, DeviceBuffer<int> &rp, DeviceBuffer<int> &ci, DeviceBuffer<float> &v) {
+        ARAP_CUDA(rp.ensure((size_t)m.n_rows + 1));
+        ARAP_CUDA(ci.ensure((size_t)m.nnz));
+        ARAP_CUDA(v.ensure((size_t)m.nnz));
+        ARAP_CUDA(cudaMemcpyAsync(rp.ptr, m.rowptr.ptr, sizeof(int) * ((size_t)m.n_rows + 1), cudaMemcpyDeviceToDevice, stream));
+        if (m.nnz > 0) {
+            ARAP_CUDA(cudaMemcpyAsync(ci.ptr, m.colidx.ptr, sizeof(int) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, stream));
+            mgdev::to_float_kernel<<<grid_for((size_t)m.nnz), kBlock, 0, stream>>>((size_t)m.nnz, m.val.ptr, v.ptr);
+        }
+        return ARAP_OK;
+    }
+
+    // Builds `mg` for the single-GPU solver. *built = false (and ARAP_OK) when the device path declines (an accumulator row
+    // overflowed, switched off with ARAP_MG_DEVICE_SETUP=0): the caller then runs the host setup.
+    int setup_multigrid_device(bool *built) {
+        using namespace mgdev;
+        *built = false;
+        if (getenv("ARAP_MG_DEVICE_SETUP") && atoi(getenv("ARAP_MG_DEVICE_SETUP")) == 0) return ARAP_OK;
+        if (transport || batch_members > 1) return ARAP_OK;
+        const auto t0 = std::chrono::steady_clock::now();
+        const int V = n_vertices;
+        const MgSetupOptions mo = engine_mg_options();
+        const double theta2 = mo.theta * mo.theta;
+        const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
+        DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
+        DeviceBuffer<unsigned long long> m1, gersh;
+        DeviceBuffer<double> inv_diag_d, vx, vy, sums;
+        ARAP_CUDA(scalars.ensure(4));        // [0] active rows, [1] newly elected roots, [2] still undecided, [3] accumulator overflow
+        ARAP_CUDA(sums.ensure(4));
+        ARAP_CUDA(gersh.ensure(1));
+        ARAP_CUDA(cudaMemsetAsync(scalars.ptr, 0, 4 * sizeof(int), stream));
+        // ---- level 0 as an explicit CSR
+        std::unique_ptr<DevCsr> A(new DevCsr());
+        ARAP_CUDA(len.ensure((size_t)V + 1));
+        level0_rows_kernel<S><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, 0, len.ptr,
+                                                                           nullptr, nullptr, nullptr);
+        { int rc = csr_allocate(*A, V, V, len.ptr); if (rc) return rc; }
+        level0_rows_kernel<S><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, 1, nullptr,
+                                                                           A->rowptr.ptr, A->colidx.ptr, A->val.ptr);
+        const double fine_nnz = std::max(1, A->nnz);
+        double total_nnz = 0;
+        std::vector<std::unique_ptr<MgLevelDev>> levels;
+        int h_scalars[4] = {0, 0, 0, 0};
+        for (;;) {
+            const int n = A->n_rows;
+            const int l = (int)levels.size();
+            std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+            d->n = n;
+            // ---- 1 / diagonal, number of active rows
+            ARAP_CUDA(inv_diag_d.ensure((size_t)n));
+            ARAP_CUDA(cudaMemsetAsync(scalars.ptr, 0, sizeof(int), stream));
+            inv_diag_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, scalars.ptr);
+            // ---- omega = 4 / (3 rho(D^-1 A)): 12 power iterations + Gershgorin bound
+            ARAP_CUDA(vx.ensure((size_t)n));
+            ARAP_CUDA(vy.ensure((size_t)n));
+            ARAP_CUDA(cudaMemsetAsync(gersh.ptr, 0, sizeof(unsigned long long), stream));
+            rho_init_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, inv_diag_d.ptr, vx.ptr);
+            const int rgrid = std::min(grid_for((size_t)n), sm_count * 4);
+            for (int it = 0; it < 12; ++it) {
+                rho_step_kernel<<<rgrid, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, vx.ptr, vy.ptr, partials.ptr, counter.ptr,
+                                                              sums.ptr, it == 0 ? gersh.ptr : nullptr);
+                rho_scale_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, vy.ptr, sums.ptr, vx.ptr);
+            }
+            double h_sums[4] = {0, 0, 0, 0};
+            unsigned long long h_gersh = 0;
+            ARAP_CUDA(cudaMemcpyAsync(h_sums, sums.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(&h_gersh, gersh.ptr, sizeof(h_gersh), cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h_scalars, scalars.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaStreamSynchronize(stream));
+            double rho = h_sums[1] > 0 ? h_sums[0] / h_sums[1] : 1.0;
+            double gbound;
+            std::memcpy(&gbound, &h_gersh, sizeof(double));
+            rho *= 1.1;
+            if (gbound > 0) rho = std::min(rho, gbound);
+            rho = std::max(rho, 1.0);
+            d->omega = 4.0 / (3.0 * rho);
+            const int active = h_scalars[0];
+            total_nnz += A->nnz;
+            // ---- this level's arrays for the V-cycle (fp32)
+            if (l > 0) {
+                { int rc = upload_level_matrix(*A, d->a_rowptr, d->a_colidx, d->a_val); if (rc) return rc; }
+                ARAP_CUDA(d->b.ensure((size_t)n));
+                d->a_lanes = pick_lanes((size_t)A->nnz, (size_t)n);
+            }
+            ARAP_CUDA(d->inv_diag.ensure((size_t)n));
+            to_float_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>((size_t)n, inv_diag_d.ptr, d->inv_diag.ptr);
+            ARAP_CUDA(d->x.ensure((size_t)n));
+            ARAP_CUDA(d->x2.ensure((size_t)n));
+            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
+            bool coarsened = false;
+            const bool last = active <= mo.coarse_size || l + 1 >= mo.max_levels;
+            if (!last) {
+                // ---- aggregation: roots = maximal independent set of the squared strength graph
+                ARAP_CUDA(agg.ensure((size_t)n));
+                ARAP_CUDA(status.ensure((size_t)n));
+                ARAP_CUDA(m1.ensure((size_t)n));
+                ARAP_CUDA(flag.ensure((size_t)n + 1));
+                ARAP_CUDA(root_id.ensure((size_t)n + 1));
+                ARAP_CUDA(joined.ensure((size_t)n));
+                const int G = grid_for((size_t)n);
+                agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, agg.ptr, status.ptr);
+                for (int round = 0; round < 64; ++round) {
+                    ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
+                    agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, m1.ptr);
+                    agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, m1.ptr, status.ptr, scalars.ptr + 1);
+                    agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr);
+                    agg_cover2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, scalars.ptr + 2);
+                    ARAP_CUDA(cudaMemcpyAsync(h_scalars + 1, scalars.ptr + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    if (h_scalars[2] == 0) break;
+                }
+                agg_root_flag_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, flag.ptr);
+                { int rc = exclusive_scan(flag.ptr, n, root_id.ptr); if (rc) return rc; }
+                int n_agg = 0;
+                ARAP_CUDA(cudaMemcpyAsync(&n_agg, root_id.ptr + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                agg_assign1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, root_id.ptr, agg.ptr);
+                agg_assign2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, agg.ptr, joined.ptr);
+                ARAP_CUDA(cudaStreamSynchronize(stream));
+                if (n_agg > 0 && n_agg < 0.8 * active) {
+                    // ---- P = (I - omega D^-1 A) T
+                    DevCsr P, R, AP;
+                    std::unique_ptr<DevCsr> Ac(new DevCsr());
+                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, joined.ptr, d->omega, 0, len.ptr,
+                                                                 nullptr, nullptr, nullptr, scalars.ptr + 3);
+                    { int rc = csr_allocate(P, n, n_agg, len.ptr); if (rc) return rc; }
+                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, joined.ptr, d->omega, 1, nullptr,
+                                                                 P.rowptr.ptr, P.colidx.ptr, P.val.ptr, scalars.ptr + 3);
+                    // ---- R = P^T, rows sorted
+                    ARAP_CUDA(cursor.ensure((size_t)n_agg + 1));
+                    ARAP_CUDA(len.ensure((size_t)std::max(n, n_agg) + 1));
+                    ARAP_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(int) * ((size_t)n_agg + 1), stream));
+                    if (P.nnz > 0) col_count_kernel<<<grid_for((size_t)P.nnz), kBlock, 0, stream>>>(P.nnz, P.colidx.ptr, cursor.ptr);
+                    { int rc = csr_allocate(R, n_agg, n, cursor.ptr); if (rc) return rc; }
+                    ARAP_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(int) * ((size_t)n_agg + 1), stream));
+                    transpose_fill_kernel<<<G, kBlock, 0, stream>>>(n, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, R.rowptr.ptr, cursor.ptr, R.colidx.ptr, R.val.ptr);
+                    sort_rows_kernel<<<grid_for((size_t)n_agg), kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr);
+                    // ---- AP = A P ; A_c = R (A P)
+                    spgemm_rows_kernel<128><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, 0, len.ptr,
+                                                                      nullptr, nullptr, nullptr, scalars.ptr + 3);
+                    { int rc = csr_allocate(AP, n, n_agg, len.ptr); if (rc) return rc; }
+                    spgemm_rows_kernel<128><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, 1, nullptr,
+                                                                      AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, scalars.ptr + 3);
+                    const int Gc = grid_for((size_t)n_agg);
+                    spgemm_rows_kernel<128><<<Gc, kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr, AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, 0, len.ptr,
+                                                                       nullptr, nullptr, nullptr, scalars.ptr + 3);
+                    { int rc = csr_allocate(*Ac, n_agg, n_agg, len.ptr); if (rc) return rc; }
+                    spgemm_rows_kernel<128><<<Gc, kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr, AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, 1, nullptr,
+                                                                       Ac->rowptr.ptr, Ac->colidx.ptr, Ac->val.ptr, scalars.ptr + 3);
+                    ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    ARAP_CUDA(cudaGetLastError());
+                    if (h_scalars[3] != 0) return ARAP_OK;             // a row outgrew its accumulator: the host setup handles it
+                    { int rc = upload_level_matrix(P, d->p_rowptr, d->p_colidx, d->p_val); if (rc) return rc; }
+                    { int rc = upload_level_matrix(R, d->r_rowptr, d->r_colidx, d->r_val); if (rc) return rc; }
+                    ARAP_CUDA(d->r.ensure((size_t)n));
+                    d->r_lanes = pick_lanes((size_t)R.nnz, (size_t)n_agg);
+                    ARAP_CUDA(cudaStreamSynchronize(stream));       // P, R, AP die at scope exit
+                    if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz) -> %d aggregates, omega %.4f\n", l, n, active, A->nnz, n_agg, d->omega);
+                    levels.push_back(std::move(d));
+                    A = std::move(Ac);
+                    coarsened = true;
+                }
+            }
+            if (coarsened) continue;
+            // ---- coarsest level: dense inverse (host up to host_dense_max rows, device above) or one more smoothing level
+            mg_dense = false;
+            if (n <= mo.max_dense) {
+                HostCsr hA;
+                hA.n_rows = hA.n_cols = n;
+                hA.rowptr.resize((size_t)n + 1);
+                hA.colidx.resize((size_t)A->nnz);
+                hA.val.resize((size_t)A->nnz);
+                ARAP_CUDA(cudaMemcpyAsync(hA.rowptr.data(), A->rowptr.ptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, stream));
+                if (A->nnz > 0) {
+                    ARAP_CUDA(cudaMemcpyAsync(hA.colidx.data(), A->colidx.ptr, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaMemcpyAsync(hA.val.data(), A->val.ptr, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, stream));
+                }
+                ARAP_CUDA(cudaStreamSynchronize(stream));
+                int rc = invert_coarsest_on_device(hA);
+                if (rc) return rc;
+            }
+            if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz), coarsest, dense inverse %s\n", l, n, active, A->nnz, mg_dense ? "yes" : "no");
+            levels.push_back(std::move(d));
+            break;
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        mg.swap(levels);
+        { int rc = plan_tail(); if (rc) return rc; }
+        stats.mg_levels = (int)mg.size();
+        stats.mg_operator_complexity = total_nnz / fine_nnz;
+        stats.setup_host_ms = 0.0;
+        stats.setup_device_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *built = true;
+        return ARAP_OK;
+    }
+
     int setup_multigrid() {
+        {   // the device path first; the host path below remains for batches, partitions and as the fallback
+            bool built = false;
+            int rc = setup_multigrid_device(&built);
+            if (rc) return rc;
+            if (built) return ARAP_OK;
+        }
         const int V = n_vertices;
         auto t0 = std::chrono::steady_clock::now();
         std::vector<int> h_rowptr((size_t)V + 1), h_colidx((size_t)nnz);

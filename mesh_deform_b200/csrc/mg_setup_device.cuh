@@ -1,0 +1,330 @@
+// mg_setup_device.cuh -- the smoothed-aggregation setup of mg_setup.cpp as CUDA kernels (the role of the reference's
+// setupLinearSystem + SimplicialLDLT::compute, arap.h:292-340: a one-off analysis of L per change of the constrained set).
+//
+// Same algorithm as the host version (Vanek, Mandel, Brezina): strength graph |a_ij| >= theta sqrt(a_ii a_jj), aggregates =
+// root + strong neighbours, P = (I - omega D^-1 A) T, R = P^T, A_c = R A P, all in fp64. What differs is how the aggregates
+// are found: the host walks the vertices one after the other (greedy, in Morton order); here the roots are a maximal
+// independent set of the SQUARE of the strength graph (no two roots within distance 2 -- exactly the property the greedy
+// walk guarantees), found in a handful of parallel rounds: an undecided vertex becomes a root when its hashed key is the
+// largest among the undecided vertices within distance 2. Every sparse product is built row by row, one thread per row,
+// into a small sorted accumulator in the thread's local memory: rows come out sorted by column and every sum runs in a
+// fixed order, so the hierarchy is bit-reproducible from run to run and from rank to rank.
+#pragma once
+
+#include "device_utils.cuh"
+
+namespace arap {
+namespace mgdev {
+
+constexpr int kAggUnset = -2;
+
+__device__ __forceinline__ unsigned hash_u32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// key of a vertex in the root election: hash in the high bits (random-looking priorities give well spread roots), index in
+// the low bits (unique, so ties cannot happen). 0 = "not a candidate".
+__device__ __forceinline__ unsigned long long root_key(int i) { return ((unsigned long long)(hash_u32((unsigned)i) | 1u) << 32) | (unsigned)i; }
+
+// ---- level 0: L = D - W on the free rows as an explicit CSR (full vertex index space, constrained rows empty) ---------
+// pass 1 (fill == 0): row lengths; pass 2: entries sorted by column with the diagonal in place.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) level0_rows_kernel(int n, int n_cols_valid, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                             const S *__restrict__ w, const unsigned char *__restrict__ is_free, int fill,
+                                                             int *__restrict__ out_len, const int *__restrict__ a_rowptr,
+                                                             int *__restrict__ a_col, double *__restrict__ a_val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!is_free[i]) { if (!fill) out_len[i] = 0; return; }
+    int cnt = 1;
+    double diag = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        diag += (double)w[k];
+        if (j != i && j < n_cols_valid && is_free[j]) ++cnt;
+    }
+    if (!fill) { out_len[i] = cnt; return; }
+    const int base = a_rowptr[i];
+    int q = 0;
+    a_col[base] = i; a_val[base] = diag; q = 1;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        if (j == i || j >= n_cols_valid || !is_free[j]) continue;
+        // insertion into the sorted prefix (rows have ~7 entries); a repeated column (cannot happen in a merged CSR) would add up
+        int p = q;
+        while (p > 0 && a_col[base + p - 1] > j) { a_col[base + p] = a_col[base + p - 1]; a_val[base + p] = a_val[base + p - 1]; --p; }
+        a_col[base + p] = j; a_val[base + p] = -(double)w[k];
+        ++q;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) inv_diag_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                          const double *__restrict__ val, double *__restrict__ inv_diag, int *__restrict__ active) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double d = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) if (colidx[k] == i && val[k] > 0.0) d = 1.0 / val[k];
+    inv_diag[i] = d;
+    if (d > 0.0) atomicAdd(active, 1);
+}
+
+// ---- largest eigenvalue of D^-1 A: power iteration (Rayleigh quotient x'Ax / x'Dx) + Gershgorin bound -----------------
+__global__ void __launch_bounds__(kBlock) rho_init_kernel(int n, const double *__restrict__ inv_diag, double *__restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = inv_diag[i] > 0 ? 1.0 + 0.37 * (double)(((unsigned)i * 2654435761u) % 97u) / 97.0 * ((i & 1) ? 1.0 : -1.0) : 0.0;
+}
+// y = D^-1 A x ; sums[0..2] = x'Ax, x'Dx, |y|^2 ; sums[3] = max_i sum_j |a_ij| / a_ii (as a sum-free max via atomics on bits)
+__global__ void __launch_bounds__(kBlock) rho_step_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                          const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                          const double *__restrict__ x, double *__restrict__ y,
+                                                          double *__restrict__ partials, unsigned *__restrict__ counter,
+                                                          double *__restrict__ sums, unsigned long long *__restrict__ gersh_bits) {
+    double red[3] = {0, 0, 0};
+    double g = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double s = 0.0, a = 0.0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { s += val[k] * x[colidx[k]]; a += fabs(val[k]); }
+        const double d = inv_diag[i], xi = x[i];
+        red[0] += xi * s;
+        if (d > 0) red[1] += xi * xi / d;
+        const double yi = s * d;
+        y[i] = yi;
+        red[2] += yi * yi;
+        g = fmax(g, a * d);
+    }
+    if (gersh_bits) atomicMax(gersh_bits, (unsigned long long)__double_as_longlong(g));      // g >= 0: bit order == value order
+    double total[3];
+    if (grid_sum_last_block<3>(red, partials, counter, total)) { sums[0] = total[0]; sums[1] = total[1]; sums[2] = total[2]; }
+}
+__global__ void __launch_bounds__(kBlock) rho_scale_kernel(int n, const double *__restrict__ y, const double *__restrict__ sums, double *__restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double nrm = sqrt(sums[2]);
+    if (nrm > 0) x[i] = y[i] / nrm;
+}
+
+// ---- aggregation ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_strong(int i, int j, double a, const double *__restrict__ inv_diag, const int *__restrict__ block, double theta2) {
+    if (j == i) return false;
+    const double dj = inv_diag[j];
+    if (!(dj > 0)) return false;
+    if (block && block[i] != block[j]) return false;                        // aggregates stay inside one partition block
+    return a * a * inv_diag[i] * dj >= theta2;
+}
+// agg = -1 where the row takes no part in the coarse level (empty row or no strong neighbour), UNSET elsewhere
+__global__ void __launch_bounds__(kBlock) agg_init_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                          const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                          const int *__restrict__ block, double theta2, int *__restrict__ agg,
+                                                          int *__restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool has = false;
+    if (inv_diag[i] > 0)
+        for (int k = rowptr[i]; k < rowptr[i + 1] && !has; ++k) has = is_strong(i, colidx[k], val[k], inv_diag, block, theta2);
+    agg[i] = has ? kAggUnset : -1;
+    status[i] = has ? 0 : 2;              // 0 undecided, 1 root, 2 out of the election
+}
+// m1[i] = largest key among the undecided vertices of the closed strong neighbourhood of i (0 if none)
+__global__ void __launch_bounds__(kBlock) agg_max1_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                          const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                          const int *__restrict__ block, double theta2, const int *__restrict__ status,
+                                                          unsigned long long *__restrict__ m1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long m = status[i] == 0 ? root_key(i) : 0ULL;
+    if (inv_diag[i] > 0)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] == 0) { const unsigned long long kj = root_key(j); if (kj > m) m = kj; }
+        }
+    m1[i] = m;
+}
+// an undecided vertex whose key is the largest within distance 2 becomes a root
+__global__ void __launch_bounds__(kBlock) agg_elect_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                           const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                           const int *__restrict__ block, double theta2, const unsigned long long *__restrict__ m1,
+                                                           int *__restrict__ status, int *__restrict__ n_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] != 0) return;
+    unsigned long long m = m1[i];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        if (is_strong(i, j, val[k], inv_diag, block, theta2) && m1[j] > m) m = m1[j];
+    }
+    if (m == root_key(i)) { status[i] = 1; atomicAdd(n_new, 1); }
+}
+// after an election: neighbours of roots leave the election (status 3 = adjacent to a root), then their neighbours do (2)
+__global__ void __launch_bounds__(kBlock) agg_cover1_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                            const int *__restrict__ block, double theta2, int *__restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] != 0) return;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] == 1) { status[i] = 3; return; }
+    }
+}
+__global__ void __launch_bounds__(kBlock) agg_cover2_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                            const int *__restrict__ block, double theta2, int *__restrict__ status,
+                                                            int *__restrict__ n_undecided) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] != 0) return;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] == 3) { status[i] = 2; return; }
+    }
+    atomicAdd(n_undecided, 1);
+}
+__global__ void __launch_bounds__(kBlock) agg_root_flag_kernel(int n, const int *__restrict__ status, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = status[i] == 1 ? 1 : 0;
+}
+// roots get their id (prefix of the root flags: coarse numbering follows the fine numbering); a vertex next to a root joins the
+// root it is most strongly connected to (ties: the smaller root id)
+__global__ void __launch_bounds__(kBlock) agg_assign1_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                             const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                             const int *__restrict__ block, double theta2, const int *__restrict__ status,
+                                                             const int *__restrict__ root_id, int *__restrict__ agg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || agg[i] == -1) return;
+    if (status[i] == 1) { agg[i] = root_id[i]; return; }
+    double best = -1.0;
+    int pick = kAggUnset;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] == 1) {
+            const double a = fabs(val[k]);
+            const int id = root_id[j];
+            if (a > best || (a == best && id < pick)) { best = a; pick = id; }
+        }
+    }
+    agg[i] = pick;
+}
+// leftovers (distance 2 from the nearest root) join the aggregate of pass 1 they are most strongly connected to
+__global__ void __launch_bounds__(kBlock) agg_assign2_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                             const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                             const int *__restrict__ block, double theta2, const int *__restrict__ agg,
+                                                             int *__restrict__ joined) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int pick = agg[i];
+    if (pick == kAggUnset) {
+        double best = -1.0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            if (is_strong(i, j, val[k], inv_diag, block, theta2) && agg[j] >= 0) {
+                const double a = fabs(val[k]);
+                if (a > best || (a == best && agg[j] < pick)) { best = a; pick = agg[j]; }
+            }
+        }
+    }
+    joined[i] = pick;
+}
+// coarse block (owner) = block of the aggregate's root
+__global__ void __launch_bounds__(kBlock) agg_block_kernel(int n, const int *__restrict__ status, const int *__restrict__ root_id,
+                                                           const int *__restrict__ block, int *__restrict__ block_c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && status[i] == 1) block_c[root_id[i]] = block[i];
+}
+
+// ---- sorted accumulator in local memory ------------------------------------------------------------------------------
+template <int CAP>
+struct RowAcc {
+    int col[CAP];
+    double val[CAP];
+    int n = 0;
+    bool overflow = false;
+    __device__ __forceinline__ void add(int c, double v) {
+        int lo = 0, hi = n;                      // first position with col >= c
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < c) lo = mid + 1; else hi = mid; }
+        if (lo < n && col[lo] == c) { val[lo] += v; return; }
+        if (n == CAP) { overflow = true; return; }
+        for (int p = n; p > lo; --p) { col[p] = col[p - 1]; val[p] = val[p - 1]; }
+        col[lo] = c; val[lo] = v; ++n;
+    }
+};
+
+// P = (I - omega D^-1 A) T, T piecewise constant over the aggregates. fill == 0: row lengths.
+constexpr int kCapP = 24;
+__global__ void __launch_bounds__(kBlock) prolongator_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                             const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                             const int *__restrict__ agg, double omega, int fill, int *__restrict__ out_len,
+                                                             const int *__restrict__ p_rowptr, int *__restrict__ p_col, double *__restrict__ p_val,
+                                                             int *__restrict__ error) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RowAcc<kCapP> acc;
+    const double d = inv_diag[i];
+    if (d > 0) {
+        if (agg[i] >= 0) acc.add(agg[i], 1.0);
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int J = agg[colidx[k]];
+            if (J >= 0) acc.add(J, -omega * d * val[k]);
+        }
+    }
+    if (acc.overflow) *error = 1;
+    if (!fill) { out_len[i] = acc.n; return; }
+    const int base = p_rowptr[i];
+    for (int q = 0; q < acc.n; ++q) { p_col[base + q] = acc.col[q]; p_val[base + q] = acc.val[q]; }
+}
+
+// transpose: column counts, then a scatter with per-column cursors, then every row of the result sorted by column
+__global__ void __launch_bounds__(kBlock) col_count_kernel(int nnz, const int *__restrict__ colidx, int *__restrict__ count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) atomicAdd(&count[colidx[k]], 1);
+}
+__global__ void __launch_bounds__(kBlock) transpose_fill_kernel(int n_rows, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                                const double *__restrict__ val, const int *__restrict__ t_rowptr,
+                                                                int *__restrict__ cursor, int *__restrict__ t_col, double *__restrict__ t_val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int c = colidx[k];
+        const int q = t_rowptr[c] + atomicAdd(&cursor[c], 1);
+        t_col[q] = i; t_val[q] = val[k];
+    }
+}
+__global__ void __launch_bounds__(kBlock) sort_rows_kernel(int n_rows, const int *__restrict__ rowptr, int *__restrict__ colidx, double *__restrict__ val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int lo = rowptr[i], hi = rowptr[i + 1];
+    for (int a = lo + 1; a < hi; ++a) {
+        const int cj = colidx[a];
+        const double cv = val[a];
+        int q = a - 1;
+        while (q >= lo && colidx[q] > cj) { colidx[q + 1] = colidx[q]; val[q + 1] = val[q]; --q; }
+        colidx[q + 1] = cj; val[q + 1] = cv;
+    }
+}
+
+// C = A * B, one thread per row of A (rows of a few dozen products). fill == 0: row lengths.
+template <int CAP>
+__global__ void __launch_bounds__(kBlock) spgemm_rows_kernel(int n, const int *__restrict__ a_rowptr, const int *__restrict__ a_col,
+                                                             const double *__restrict__ a_val, const int *__restrict__ b_rowptr,
+                                                             const int *__restrict__ b_col, const double *__restrict__ b_val, int fill,
+                                                             int *__restrict__ out_len, const int *__restrict__ c_rowptr, int *__restrict__ c_col,
+                                                             double *__restrict__ c_val, int *__restrict__ error) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RowAcc<CAP> acc;
+    for (int k = a_rowptr[i]; k < a_rowptr[i + 1]; ++k) {
+        const int j = a_col[k];
+        const double a = a_val[k];
+        for (int q = b_rowptr[j]; q < b_rowptr[j + 1]; ++q) acc.add(b_col[q], a * b_val[q]);
+    }
+    if (acc.overflow) *error = 1;
+    if (!fill) { out_len[i] = acc.n; return; }
+    const int base = c_rowptr[i];
+    for (int q = 0; q < acc.n; ++q) { c_col[base + q] = acc.col[q]; c_val[base + q] = acc.val[q]; }
+}
+
+// fp64 setup arrays -> the fp32 arrays the V-cycle reads
+__global__ void __launch_bounds__(kBlock) to_float_kernel(size_t n, const double *__restrict__ in, float *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+}  // namespace mgdev
+}  // namespace arap

@@ -194,3 +194,48 @@ def test_parity_deep_into_a_run(prec):
         gpu_err = np.abs(mesh.astype(np.float64) - m64).max() / diag
         print("float: oracle32 vs oracle64", ref_err, "engine32 vs oracle64", gpu_err)
         assert gpu_err <= max(2 * ref_err, 2e-5)
+
+
+@pytest.mark.parametrize("mesh", ["ico", "grid", "delaunay"])
+def test_device_built_hierarchy_matches_host_built(mesh, monkeypatch):
+    """The multigrid hierarchy built by the CUDA setup kernels (parallel MIS-2 aggregation, row-wise sparse products) against
+    the one built on the host (greedy aggregation in Morton order): both are only preconditioners of the same exact system, so
+    the results agree to the solver tolerance and the CG iteration counts stay close; both match the oracle."""
+    if mesh == "ico":
+        P, F = G.icosphere(64)
+        idx, tgt = G.cap_constraints(P)
+    elif mesh == "grid":
+        P, F = G.grid_plane(220, 180)
+        idx, tgt = G.grid_constraints(220, 180, P)
+    else:
+        rng = np.random.default_rng(5)
+        from scipy.spatial import Delaunay
+        pts = rng.random((20000, 2))
+        F = Delaunay(pts).simplices.astype(np.int32)
+        P = np.stack([pts[:, 0], 0.05 * np.sin(6 * pts[:, 0]) * np.cos(5 * pts[:, 1]), pts[:, 1]], 1)
+        order = np.argsort(pts[:, 0])
+        idx = np.concatenate([order[:200], order[-100:]]).astype(np.int32)
+        tgt = P[idx].copy()
+        tgt[200:] += [0.0, 0.15, 0.0]
+    its = 4
+    results = {}
+    for side in ("device", "host"):
+        monkeypatch.setenv("ARAP_MG_DEVICE_SETUP", "1" if side == "device" else "0")
+        m = P.copy()
+        a = ARAP(m, F, np.float64)
+        a.setConstraints(idx, tgt)
+        assert a.deform(its)
+        st = a.solver_stats()
+        assert (st["setup_device_ms"] > 0) == (side == "device") and (st["setup_host_ms"] > 0) == (side == "host"), st
+        results[side] = (m, a.energy(), st)
+    o, omesh = oracle_for(P, F, idx, tgt)
+    assert o.deform(its)
+    diag = bbox_diag(P)
+    for side, (m, e, st) in results.items():
+        dp, de = np.abs(m - omesh).max() / diag, abs(e - o.energy()) / o.energy()
+        print(mesh, side, "levels", st["mg_levels"], "complexity %.3f" % st["mg_operator_complexity"], "CG iterations", st["cg_iterations_total"],
+              "setup ms", st["setup_device_ms"] + st["setup_host_ms"], "dp/diag", dp, "rel dE", de)
+        assert dp <= POS_TOL and de <= E_TOL
+    dev, host = results["device"][2], results["host"][2]
+    assert dev["cg_iterations_total"] <= 1.6 * host["cg_iterations_total"] + 4      # a different aggregation, not a worse preconditioner
+    assert dev["mg_operator_complexity"] <= 1.6
