@@ -1248,21 +1248,31 @@ public:
         return ARAP_OK;
     }
 
-    // Builds `mg` for the single-GPU solver. *built = false (and ARAP_OK) when the device path declines (an accumulator row
-    // overflowed, switched off with ARAP_MG_DEVICE_SETUP=0): the caller then runs the host setup.
-    int setup_multigrid_device(bool *built) {
+    // One level of a hierarchy as the device setup leaves it (fp64): A, 1/diag, omega, and -- unless it is the coarsest -- P, R.
+    struct DevLevel {
+        std::unique_ptr<DevCsr> A, P, R;
+        DeviceBuffer<double> inv_diag;
+        DeviceBuffer<int> block;               // owner rank per row (partitioned hierarchies), else empty
+        DeviceBuffer<int> block_next;          // ... of the next level's rows, until that level has copied it
+        double omega = 2.0 / 3.0;
+        int n = 0, active = 0;
+    };
+
+    // The hierarchy of L = D - W restricted to the rows with is_free != 0 (one-ring CSR rowptr / colidx / weight over V vertices),
+    // built on the device. block0 (optional, device, V entries): aggregates never mix two blocks (partitioned mode).
+    // *built = false (and ARAP_OK) when a row outgrew its accumulator: the caller falls back to the host setup.
+    template <typename W>
+    int build_hierarchy_device(int V, const int *d_rowptr, const int *d_colidx, const W *d_weight, const unsigned char *d_is_free,
+                               const int *block0, const MgSetupOptions &mo, std::vector<std::unique_ptr<DevLevel>> &levels,
+                               double *operator_complexity, bool *built) {
         using namespace mgdev;
         *built = false;
-        if (getenv("ARAP_MG_DEVICE_SETUP") && atoi(getenv("ARAP_MG_DEVICE_SETUP")) == 0) return ARAP_OK;
-        if (transport || batch_members > 1) return ARAP_OK;
-        const auto t0 = std::chrono::steady_clock::now();
-        const int V = n_vertices;
-        const MgSetupOptions mo = engine_mg_options();
+        levels.clear();
         const double theta2 = mo.theta * mo.theta;
         const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
         DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
         DeviceBuffer<unsigned long long> m1, gersh;
-        DeviceBuffer<double> inv_diag_d, vx, vy, sums;
+        DeviceBuffer<double> vx, vy, sums;
         ARAP_CUDA(scalars.ensure(4));        // [0] active rows, [1] newly elected roots, [2] still undecided, [3] accumulator overflow
         ARAP_CUDA(sums.ensure(4));
         ARAP_CUDA(gersh.ensure(1));
@@ -1270,32 +1280,36 @@ public:
         // ---- level 0 as an explicit CSR
         std::unique_ptr<DevCsr> A(new DevCsr());
         ARAP_CUDA(len.ensure((size_t)V + 1));
-        level0_rows_kernel<S><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, 0, len.ptr,
-                                                                           nullptr, nullptr, nullptr);
+        level0_rows_kernel<W><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, d_rowptr, d_colidx, d_weight, d_is_free, 0, len.ptr, nullptr, nullptr, nullptr);
         { int rc = csr_allocate(*A, V, V, len.ptr); if (rc) return rc; }
-        level0_rows_kernel<S><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, 1, nullptr,
-                                                                           A->rowptr.ptr, A->colidx.ptr, A->val.ptr);
+        level0_rows_kernel<W><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, V, d_rowptr, d_colidx, d_weight, d_is_free, 1, nullptr, A->rowptr.ptr, A->colidx.ptr,
+                                                                           A->val.ptr);
         const double fine_nnz = std::max(1, A->nnz);
         double total_nnz = 0;
-        std::vector<std::unique_ptr<MgLevelDev>> levels;
+        const int *block = block0;
         int h_scalars[4] = {0, 0, 0, 0};
         for (;;) {
             const int n = A->n_rows;
             const int l = (int)levels.size();
-            std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+            std::unique_ptr<DevLevel> d(new DevLevel());
             d->n = n;
+            if (block) {
+                ARAP_CUDA(d->block.ensure((size_t)n));
+                ARAP_CUDA(cudaMemcpyAsync(d->block.ptr, block, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+                block = d->block.ptr;
+            }
             // ---- 1 / diagonal, number of active rows
-            ARAP_CUDA(inv_diag_d.ensure((size_t)n));
+            ARAP_CUDA(d->inv_diag.ensure((size_t)n));
             ARAP_CUDA(cudaMemsetAsync(scalars.ptr, 0, sizeof(int), stream));
-            inv_diag_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, scalars.ptr);
+            inv_diag_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, d->inv_diag.ptr, scalars.ptr);
             // ---- omega = 4 / (3 rho(D^-1 A)): 12 power iterations + Gershgorin bound
             ARAP_CUDA(vx.ensure((size_t)n));
             ARAP_CUDA(vy.ensure((size_t)n));
             ARAP_CUDA(cudaMemsetAsync(gersh.ptr, 0, sizeof(unsigned long long), stream));
-            rho_init_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, inv_diag_d.ptr, vx.ptr);
+            rho_init_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, d->inv_diag.ptr, vx.ptr);
             const int rgrid = std::min(grid_for((size_t)n), sm_count * 4);
             for (int it = 0; it < 12; ++it) {
-                rho_step_kernel<<<rgrid, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, vx.ptr, vy.ptr, partials.ptr, counter.ptr,
+                rho_step_kernel<<<rgrid, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, d->inv_diag.ptr, vx.ptr, vy.ptr, partials.ptr, counter.ptr,
                                                               sums.ptr, it == 0 ? gersh.ptr : nullptr);
                 rho_scale_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>(n, vy.ptr, sums.ptr, vx.ptr);
             }
@@ -1313,19 +1327,8 @@ public:
             rho = std::max(rho, 1.0);
             d->omega = 4.0 / (3.0 * rho);
             const int active = h_scalars[0];
+            d->active = active;
             total_nnz += A->nnz;
-            // ---- this level's arrays for the V-cycle (fp32)
-            if (l > 0) {
-                { int rc = upload_level_matrix(*A, d->a_rowptr, d->a_colidx, d->a_val); if (rc) return rc; }
-                ARAP_CUDA(d->b.ensure((size_t)n));
-                d->a_lanes = pick_lanes((size_t)A->nnz, (size_t)n);
-            }
-            ARAP_CUDA(d->inv_diag.ensure((size_t)n));
-            to_float_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>((size_t)n, inv_diag_d.ptr, d->inv_diag.ptr);
-            ARAP_CUDA(d->x.ensure((size_t)n));
-            ARAP_CUDA(d->x2.ensure((size_t)n));
-            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
-            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
             bool coarsened = false;
             const bool last = active <= mo.coarse_size || l + 1 >= mo.max_levels;
             if (!last) {
@@ -1337,13 +1340,14 @@ public:
                 ARAP_CUDA(root_id.ensure((size_t)n + 1));
                 ARAP_CUDA(joined.ensure((size_t)n));
                 const int G = grid_for((size_t)n);
-                agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, agg.ptr, status.ptr);
+                const double *idg = d->inv_diag.ptr;
+                agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, agg.ptr, status.ptr);
                 for (int round = 0; round < 64; ++round) {
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
-                    agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, m1.ptr);
-                    agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, m1.ptr, status.ptr, scalars.ptr + 1);
-                    agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr);
-                    agg_cover2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, scalars.ptr + 2);
+                    agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, m1.ptr);
+                    agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, m1.ptr, status.ptr, scalars.ptr + 1);
+                    agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                    agg_cover2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, scalars.ptr + 2);
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 1, scalars.ptr + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
                     ARAP_CUDA(cudaStreamSynchronize(stream));
                     if (h_scalars[2] == 0) break;
@@ -1352,21 +1356,23 @@ public:
                 { int rc = exclusive_scan(flag.ptr, n, root_id.ptr); if (rc) return rc; }
                 int n_agg = 0;
                 ARAP_CUDA(cudaMemcpyAsync(&n_agg, root_id.ptr + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                agg_assign1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, status.ptr, root_id.ptr, agg.ptr);
-                agg_assign2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, nullptr, theta2, agg.ptr, joined.ptr);
+                agg_assign1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, root_id.ptr, agg.ptr);
+                agg_assign2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, agg.ptr, joined.ptr);
                 ARAP_CUDA(cudaStreamSynchronize(stream));
                 if (n_agg > 0 && n_agg < 0.8 * active) {
                     // ---- P = (I - omega D^-1 A) T
-                    DevCsr P, R, AP;
+                    d->P.reset(new DevCsr());
+                    d->R.reset(new DevCsr());
+                    DevCsr &P = *d->P, &R = *d->R;
+                    DevCsr AP;
                     std::unique_ptr<DevCsr> Ac(new DevCsr());
-                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, joined.ptr, d->omega, 0, len.ptr,
+                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 0, len.ptr,
                                                                  nullptr, nullptr, nullptr, scalars.ptr + 3);
                     { int rc = csr_allocate(P, n, n_agg, len.ptr); if (rc) return rc; }
-                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, inv_diag_d.ptr, joined.ptr, d->omega, 1, nullptr,
+                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 1, nullptr,
                                                                  P.rowptr.ptr, P.colidx.ptr, P.val.ptr, scalars.ptr + 3);
                     // ---- R = P^T, rows sorted
                     ARAP_CUDA(cursor.ensure((size_t)n_agg + 1));
-                    ARAP_CUDA(len.ensure((size_t)std::max(n, n_agg) + 1));
                     ARAP_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(int) * ((size_t)n_agg + 1), stream));
                     if (P.nnz > 0) col_count_kernel<<<grid_for((size_t)P.nnz), kBlock, 0, stream>>>(P.nnz, P.colidx.ptr, cursor.ptr);
                     { int rc = csr_allocate(R, n_agg, n, cursor.ptr); if (rc) return rc; }
@@ -1385,49 +1391,111 @@ public:
                     { int rc = csr_allocate(*Ac, n_agg, n_agg, len.ptr); if (rc) return rc; }
                     spgemm_rows_kernel<128><<<Gc, kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr, AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, 1, nullptr,
                                                                        Ac->rowptr.ptr, Ac->colidx.ptr, Ac->val.ptr, scalars.ptr + 3);
+                    DeviceBuffer<int> block_c;
+                    if (block) {
+                        ARAP_CUDA(block_c.ensure((size_t)n_agg));
+                        agg_block_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, root_id.ptr, block, block_c.ptr);
+                    }
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));       // AP dies at scope exit
                     ARAP_CUDA(cudaGetLastError());
                     if (h_scalars[3] != 0) return ARAP_OK;             // a row outgrew its accumulator: the host setup handles it
-                    { int rc = upload_level_matrix(P, d->p_rowptr, d->p_colidx, d->p_val); if (rc) return rc; }
-                    { int rc = upload_level_matrix(R, d->r_rowptr, d->r_colidx, d->r_val); if (rc) return rc; }
-                    ARAP_CUDA(d->r.ensure((size_t)n));
-                    d->r_lanes = pick_lanes((size_t)R.nnz, (size_t)n_agg);
-                    ARAP_CUDA(cudaStreamSynchronize(stream));       // P, R, AP die at scope exit
                     if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz) -> %d aggregates, omega %.4f\n", l, n, active, A->nnz, n_agg, d->omega);
+                    d->A = std::move(A);
                     levels.push_back(std::move(d));
                     A = std::move(Ac);
+                    if (block) {
+                        // the next level copies its block array out of this temporary at the top of the loop; keep it alive there
+                        levels.back()->block_next.ptr = block_c.ptr; levels.back()->block_next.count = block_c.count;
+                        block_c.ptr = nullptr; block_c.count = 0;
+                        block = levels.back()->block_next.ptr;
+                    }
                     coarsened = true;
                 }
             }
             if (coarsened) continue;
-            // ---- coarsest level: dense inverse (host up to host_dense_max rows, device above) or one more smoothing level
-            mg_dense = false;
-            if (n <= mo.max_dense) {
-                HostCsr hA;
-                hA.n_rows = hA.n_cols = n;
-                hA.rowptr.resize((size_t)n + 1);
-                hA.colidx.resize((size_t)A->nnz);
-                hA.val.resize((size_t)A->nnz);
-                ARAP_CUDA(cudaMemcpyAsync(hA.rowptr.data(), A->rowptr.ptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, stream));
-                if (A->nnz > 0) {
-                    ARAP_CUDA(cudaMemcpyAsync(hA.colidx.data(), A->colidx.ptr, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, stream));
-                    ARAP_CUDA(cudaMemcpyAsync(hA.val.data(), A->val.ptr, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, stream));
-                }
-                ARAP_CUDA(cudaStreamSynchronize(stream));
-                int rc = invert_coarsest_on_device(hA);
-                if (rc) return rc;
-            }
-            if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz), coarsest, dense inverse %s\n", l, n, active, A->nnz, mg_dense ? "yes" : "no");
+            if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz), coarsest\n", l, n, active, A->nnz);
+            d->A = std::move(A);
             levels.push_back(std::move(d));
             break;
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        if (operator_complexity) *operator_complexity = total_nnz / fine_nnz;
+        *built = true;
+        return ARAP_OK;
+    }
+
+    int download_csr(const DevCsr &m, HostCsr &h) {
+        h.n_rows = m.n_rows;
+        h.n_cols = m.n_cols;
+        h.rowptr.resize((size_t)m.n_rows + 1);
+        h.colidx.resize((size_t)m.nnz);
+        h.val.resize((size_t)m.nnz);
+        ARAP_CUDA(cudaMemcpyAsync(h.rowptr.data(), m.rowptr.ptr, sizeof(int) * ((size_t)m.n_rows + 1), cudaMemcpyDeviceToHost, stream));
+        if (m.nnz > 0) {
+            ARAP_CUDA(cudaMemcpyAsync(h.colidx.data(), m.colidx.ptr, sizeof(int) * (size_t)m.nnz, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(h.val.data(), m.val.ptr, sizeof(double) * (size_t)m.nnz, cudaMemcpyDeviceToHost, stream));
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        return ARAP_OK;
+    }
+
+    // Builds `mg` for the single-GPU solver on the device. *built = false (and ARAP_OK) when the device path declines (an
+    // accumulator row overflowed, switched off with ARAP_MG_DEVICE_SETUP=0): the caller then runs the host setup.
+    int setup_multigrid_device(bool *built) {
+        using namespace mgdev;
+        *built = false;
+        if (getenv("ARAP_MG_DEVICE_SETUP") && atoi(getenv("ARAP_MG_DEVICE_SETUP")) == 0) return ARAP_OK;
+        if (transport || batch_members > 1) return ARAP_OK;
+        const auto t0 = std::chrono::steady_clock::now();
+        const MgSetupOptions mo = engine_mg_options();
+        std::vector<std::unique_ptr<DevLevel>> dl;
+        double complexity = 0;
+        bool ok = false;
+        { int rc = build_hierarchy_device<S>(n_vertices, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, nullptr, mo, dl, &complexity, &ok); if (rc) return rc; }
+        if (!ok) return ARAP_OK;
+        std::vector<std::unique_ptr<MgLevelDev>> levels;
+        const size_t L = dl.size();
+        for (size_t l = 0; l < L; ++l) {
+            DevLevel &src = *dl[l];
+            const int n = src.n;
+            std::unique_ptr<MgLevelDev> d(new MgLevelDev());
+            d->n = n;
+            d->omega = src.omega;
+            if (l > 0) {
+                { int rc = upload_level_matrix(*src.A, d->a_rowptr, d->a_colidx, d->a_val); if (rc) return rc; }
+                ARAP_CUDA(d->b.ensure((size_t)n));
+                d->a_lanes = pick_lanes((size_t)src.A->nnz, (size_t)n);
+            }
+            ARAP_CUDA(d->inv_diag.ensure((size_t)n));
+            to_float_kernel<<<grid_for((size_t)n), kBlock, 0, stream>>>((size_t)n, src.inv_diag.ptr, d->inv_diag.ptr);
+            if (l + 1 < L) {
+                { int rc = upload_level_matrix(*src.P, d->p_rowptr, d->p_colidx, d->p_val); if (rc) return rc; }
+                { int rc = upload_level_matrix(*src.R, d->r_rowptr, d->r_colidx, d->r_val); if (rc) return rc; }
+                ARAP_CUDA(d->r.ensure((size_t)n));
+                d->r_lanes = pick_lanes((size_t)src.R->nnz, (size_t)src.R->n_rows);
+            }
+            ARAP_CUDA(d->x.ensure((size_t)n));
+            ARAP_CUDA(d->x2.ensure((size_t)n));
+            ARAP_CUDA(cudaMemsetAsync(d->x.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
+            ARAP_CUDA(cudaMemsetAsync(d->x2.ptr, 0, sizeof(MgVec) * (size_t)(n > 0 ? n : 1), stream));
+            levels.push_back(std::move(d));
+        }
+        // ---- coarsest level: dense inverse on the device, or one more smoothing level when it is too large
+        mg_dense = false;
+        if (dl.back()->n <= mo.max_dense) {
+            HostCsr hA;
+            { int rc = download_csr(*dl.back()->A, hA); if (rc) return rc; }
+            int rc = invert_coarsest_on_device(hA);
+            if (rc) return rc;
         }
         ARAP_CUDA(cudaStreamSynchronize(stream));
         ARAP_CUDA(cudaGetLastError());
         mg.swap(levels);
         { int rc = plan_tail(); if (rc) return rc; }
         stats.mg_levels = (int)mg.size();
-        stats.mg_operator_complexity = total_nnz / fine_nnz;
+        stats.mg_operator_complexity = complexity;
         stats.setup_host_ms = 0.0;
         stats.setup_device_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         *built = true;
@@ -1574,12 +1642,98 @@ public:
     // ---- partitioned mode: this rank's share of the GLOBAL hierarchy (mg_partition.h) -----------------------------
     // Returns ARAP_OK with mg_global == false when the global hierarchy is unusable for a reason every rank sees alike
     // (single level / no dense coarsest level); the caller then falls back to the per-rank hierarchy.
+    // ---- partitioned mode: the GLOBAL hierarchy built on this rank's GPU (every rank builds the same one: the kernels are
+    // deterministic), then downloaded for the host-side slicing (mg_partition.cpp). Replaces ~16 s of host work per rank at 16M
+    // vertices by the cotan CSR + setup kernels on the whole mesh and a download. *built = false: use the host path.
+    int build_global_hierarchy_device(MgHierarchyHost &H, bool *built) {
+        *built = false;
+        if (getenv("ARAP_MG_DEVICE_SETUP") && atoi(getenv("ARAP_MG_DEVICE_SETUP")) == 0) return ARAP_OK;
+        const GlobalMesh &gm = global_mesh;
+        const int Vg = gm.n_vertices, Fg = gm.n_faces;
+        if (Vg <= 0 || Fg <= 0) return ARAP_OK;
+        const auto t0 = std::chrono::steady_clock::now();
+        DeviceBuffer<int> d_faces, d_count, d_rawptr, d_cursor, d_rawcol, d_unique, d_rowptr, d_colidx, d_owner;
+        DeviceBuffer<double> d_rest, d_rawval, d_weight;
+        DeviceBuffer<unsigned> d_tag;
+        DeviceBuffer<unsigned char> d_free;
+        ARAP_CUDA(upload_vector(d_faces, gm.faces, stream));
+        ARAP_CUDA(upload_vector(d_rest, gm.rest, stream));
+        ARAP_CUDA(upload_vector(d_owner, gm.owner, stream));
+        {
+            std::vector<unsigned char> is_free((size_t)Vg);
+            for (int v = 0; v < Vg; ++v) is_free[(size_t)v] = gm.constrained[(size_t)v] ? 0 : 1;
+            ARAP_CUDA(upload_vector(d_free, is_free, stream));
+            ARAP_CUDA(cudaStreamSynchronize(stream));
+        }
+        // cotan weights + CSR of the global mesh: the same kernels as arap_prepare's computeCotanWeights (arap.h:182-239)
+        ARAP_CUDA(d_count.ensure((size_t)Vg + 1));
+        ARAP_CUDA(d_rawptr.ensure((size_t)Vg + 1));
+        ARAP_CUDA(d_cursor.ensure((size_t)Vg + 1));
+        ARAP_CUDA(d_unique.ensure((size_t)Vg + 1));
+        ARAP_CUDA(d_rowptr.ensure((size_t)Vg + 1));
+        ARAP_CUDA(d_rawcol.ensure(6 * (size_t)Fg));
+        ARAP_CUDA(d_rawval.ensure(6 * (size_t)Fg));
+        ARAP_CUDA(d_tag.ensure(6 * (size_t)Fg));
+        ARAP_CUDA(cudaMemsetAsync(d_count.ptr, 0, sizeof(int) * ((size_t)Vg + 1), stream));
+        ARAP_CUDA(cudaMemsetAsync(d_cursor.ptr, 0, sizeof(int) * ((size_t)Vg + 1), stream));
+        weights_count_kernel<<<grid_for((size_t)Fg), kBlock, 0, stream>>>(d_faces.ptr, Fg, d_count.ptr);
+        { int rc = exclusive_scan(d_count.ptr, Vg, d_rawptr.ptr); if (rc) return rc; }
+        weights_fill_kernel<double><<<grid_for((size_t)Fg), kBlock, 0, stream>>>(d_faces.ptr, Fg, d_rest.ptr, d_rawptr.ptr, d_cursor.ptr, d_rawcol.ptr, d_rawval.ptr, d_tag.ptr);
+        ARAP_CUDA(cudaMemsetAsync(d_cursor.ptr + Vg, 0, sizeof(int), stream));
+        row_sort_merge_kernel<double><<<grid_for((size_t)Vg), kBlock, 0, stream>>>(Vg, d_rawptr.ptr, d_rawcol.ptr, d_rawval.ptr, d_tag.ptr, d_unique.ptr, d_cursor.ptr,
+                                                                                   d_cursor.ptr + Vg);
+        row_sort_long_kernel<double><<<sm_count, kBlock, 0, stream>>>(d_cursor.ptr, d_cursor.ptr + Vg, d_rawptr.ptr, d_rawcol.ptr, d_rawval.ptr, d_tag.ptr, d_unique.ptr);
+        { int rc = exclusive_scan(d_unique.ptr, Vg, d_rowptr.ptr); if (rc) return rc; }
+        int g_nnz = 0;
+        ARAP_CUDA(cudaMemcpyAsync(&g_nnz, d_rowptr.ptr + Vg, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(d_colidx.ensure((size_t)g_nnz));
+        ARAP_CUDA(d_weight.ensure((size_t)g_nnz));
+        csr_compact_kernel<double><<<grid_for((size_t)Vg), kBlock, 0, stream>>>(Vg, d_rawptr.ptr, d_rawcol.ptr, d_rawval.ptr, d_rowptr.ptr, d_colidx.ptr, d_weight.ptr);
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        d_rawcol.release(); d_rawval.release(); d_tag.release(); d_faces.release();
+        // the hierarchy, aggregates confined to one owner each
+        const MgSetupOptions mo = engine_mg_options();
+        std::vector<std::unique_ptr<DevLevel>> dl;
+        double complexity = 0;
+        bool ok = false;
+        { int rc = build_hierarchy_device<double>(Vg, d_rowptr.ptr, d_colidx.ptr, d_weight.ptr, d_free.ptr, d_owner.ptr, mo, dl, &complexity, &ok); if (rc) return rc; }
+        if (!ok) return ARAP_OK;
+        // download: mg_slice_hierarchy works on host matrices
+        H.levels.clear();
+        H.levels.resize(dl.size());
+        for (size_t l = 0; l < dl.size(); ++l) {
+            DevLevel &src = *dl[l];
+            MgLevelHost &hl = H.levels[l];
+            { int rc = download_csr(*src.A, hl.A); if (rc) return rc; }
+            if (src.P) { int rc = download_csr(*src.P, hl.P); if (rc) return rc; }
+            if (src.R) { int rc = download_csr(*src.R, hl.R); if (rc) return rc; }
+            hl.inv_diag.resize((size_t)src.n);
+            hl.block.resize((size_t)src.n);
+            ARAP_CUDA(cudaMemcpyAsync(hl.inv_diag.data(), src.inv_diag.ptr, sizeof(double) * (size_t)src.n, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaMemcpyAsync(hl.block.data(), src.block.ptr, sizeof(int) * (size_t)src.n, cudaMemcpyDeviceToHost, stream));
+            ARAP_CUDA(cudaStreamSynchronize(stream));
+            hl.omega = src.omega;
+            dl[l].reset();                                      // free this level's device copy as soon as it is on the host
+        }
+        H.n_coarse = H.levels.back().A.n_rows;
+        H.coarse_inv.clear();
+        H.coarse_dense_on_device = H.n_coarse <= mo.max_dense;
+        H.operator_complexity = complexity;
+        stats.setup_device_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *built = true;
+        return ARAP_OK;
+    }
+
     int setup_multigrid_global() {
         auto t0 = std::chrono::steady_clock::now();
         mg_global = false;
         const GlobalMesh &gm = global_mesh;
         MgHierarchyHost H;
-        {
+        bool on_device = false;
+        { int rc = build_global_hierarchy_device(H, &on_device); if (rc) return rc; }
+        if (!on_device) {
             std::vector<int> g_rowptr, g_colidx, visit;
             std::vector<double> g_w;
             build_global_csr(gm.n_vertices, gm.n_faces, gm.faces.data(), gm.rest.data(), g_rowptr, g_colidx, g_w);

@@ -46,6 +46,8 @@ struct PeerExchangeDev {
     int n_recv_words;
     unsigned long long send_epoch;
     unsigned int done;
+    unsigned int left;                                  // one-kernel exchange: CTAs that have read send_epoch_base
+    unsigned long long send_epoch_base;                 // one-kernel exchange: epoch of the previous exchange at this site
 };
 
 struct PeerReduceDev {
@@ -130,6 +132,64 @@ __global__ void __launch_bounds__(256) peer_wait_unpack_kernel(const PeerExchang
     }
 }
 
+// put + wait + unpack in ONE kernel (the default): every CTA first stores its share of the outgoing entries, the last CTA to
+// finish publishes the epoch, then every CTA waits for the neighbours' flags itself and copies its share of the mailbox.
+// Nothing in the second half depends on the other CTAs of this kernel, so no grid-wide barrier is needed; and every rank
+// puts before it waits, so the ranks cannot wait for each other in a cycle. Half the launches of the two-kernel form.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerExchangeDev *site, const int *__restrict__ send_index,
+                                                            const unsigned long long *__restrict__ array, unsigned long long *__restrict__ halo,
+                                                            int *error) {
+    __shared__ unsigned long long s_epoch;
+    __shared__ int ok;
+    const int words = site->words, n_nbr = site->n_nbr;
+    const int total = site->send_offset[n_nbr] * words;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int e = t / words, w = t - e * words;
+        int k = 0;
+        while (e >= site->send_offset[k + 1]) ++k;
+        site->remote_payload[k][(size_t)(e - site->send_offset[k]) * words + w] = array[(size_t)send_index[e] * words + w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ok = 1;
+        // the epoch of THIS exchange: the kernels of one stream run one after the other, so send_epoch + 1 is the same for
+        // every CTA of this launch until the last one to finish its stores increments it (and only then can the neighbours'
+        // matching puts be told apart from the previous exchange's)
+        const unsigned long long epoch = *(volatile unsigned long long *)&site->send_epoch_base + 1ULL;
+        s_epoch = epoch;
+        const unsigned int prev = atomicAdd(&site->done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence_system();
+            for (int k = 0; k < n_nbr; ++k) st_release_sys(site->remote_flag[k], epoch);
+        }
+        const unsigned int left = atomicAdd(&site->left, 1u);
+        if (left == gridDim.x - 1) {            // the last CTA to have READ the base advances it for the next launch
+            site->left = 0;
+            site->done = 0;
+            site->send_epoch = epoch;
+            __threadfence();
+            *(volatile unsigned long long *)&site->send_epoch_base = epoch;
+        }
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    if ((int)threadIdx.x < n_nbr && !peer_spin_until(site->local_flag[threadIdx.x], epoch, error)) ok = 0;
+    __syncthreads();
+    if (!ok) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const int nw = site->n_recv_words;
+    if (WIDE) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(site->local_payload);
+        uint4 *dst = reinterpret_cast<uint4 *>(halo);
+        for (int t = tid; t < nw / 2; t += stride) dst[t] = __ldcv(src + t);
+        if ((nw & 1) && tid == 0) halo[nw - 1] = __ldcv(site->local_payload + nw - 1);
+    } else {
+        for (int t = tid; t < nw; t += stride) halo[t] = __ldcv(site->local_payload + t);
+    }
+}
+
 // Both reduce kernels are grid-stride over the values: the CG's 8 scalars take one CTA, the right-hand side of a replicated
 // multigrid level (up to a few hundred thousand rows) a few dozen.
 template <typename T>
@@ -166,6 +226,38 @@ __global__ void __launch_bounds__(256) peer_reduce_wait_kernel(PeerReduceDev *si
     if (ok) {
         const volatile T *slots = (const volatile T *)site->local_slots;
         for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+            T sum = slots[c];
+            for (int k = 1; k < world; ++k) sum += slots[(size_t)k * n + c];
+            values[c] = sum;
+        }
+    }
+}
+
+// small all-reduce (the CG's scalars) in ONE single-CTA kernel: put to every rank, publish, wait for every rank, add up
+template <typename T>
+__global__ void __launch_bounds__(256) peer_reduce_small_kernel(PeerReduceDev *site, T *__restrict__ values, int *error) {
+    __shared__ int ok;
+    __shared__ unsigned long long s_epoch;
+    const int n = site->n, world = site->world;
+    for (int t = threadIdx.x; t < n * world; t += blockDim.x) {
+        const int k = t / n, c = t - k * n;
+        ((T *)site->remote_slot[k])[c] = values[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ok = 1;
+        const unsigned long long epoch = ++site->send_epoch;
+        s_epoch = epoch;
+        __threadfence_system();
+        for (int k = 0; k < world; ++k) st_release_sys(site->remote_flag[k], epoch);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world && !peer_spin_until(site->local_flag[threadIdx.x], s_epoch, error)) ok = 0;
+    __syncthreads();
+    if (ok) {
+        const volatile T *slots = (const volatile T *)site->local_slots;
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
             T sum = slots[c];
             for (int k = 1; k < world; ++k) sum += slots[(size_t)k * n + c];
             values[c] = sum;
@@ -335,11 +427,19 @@ public:
         const int total = plan.n_send() * (int)(elem_bytes / 8);
         int grid = (total + 255) / 256;
         grid = grid < 1 ? 1 : (grid > 128 ? 128 : grid);
+        unsigned long long *halo = (unsigned long long *)(array + (size_t)plan.n_owned * elem_bytes);
+        static const bool two_kernels = getenv("ARAP_PEER_TWO_KERNELS") != nullptr && atoi(getenv("ARAP_PEER_TWO_KERNELS")) != 0;
+        if (!two_kernels) {
+            // grid <= 64 CTAs: all of them are resident at once on any GPU this runs on, which the in-kernel wait relies on
+            if (grid > 64) grid = 64;
+            if (((uintptr_t)halo & 15) == 0) peer_exchange_kernel<true><<<grid, 256, 0, stream>>>(ex_dev + site, send_index_dev, (const unsigned long long *)array, halo, error_flag);
+            else peer_exchange_kernel<false><<<grid, 256, 0, stream>>>(ex_dev + site, send_index_dev, (const unsigned long long *)array, halo, error_flag);
+            return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
+        }
         peer_put_kernel<<<grid, 256, 0, stream>>>(ex_dev + site, send_index_dev, (const unsigned long long *)array);
         const size_t recv_bytes = (size_t)plan.n_halo() * elem_bytes;
         int wgrid = (int)((recv_bytes + 16383) / 16384);
         wgrid = wgrid < 1 ? 1 : (wgrid > 16 ? 16 : wgrid);
-        unsigned long long *halo = (unsigned long long *)(array + (size_t)plan.n_owned * elem_bytes);
         if (((uintptr_t)halo & 15) == 0) peer_wait_unpack_kernel<true><<<wgrid, 256, 0, stream>>>(ex_dev + site, halo, error_flag);
         else peer_wait_unpack_kernel<false><<<wgrid, 256, 0, stream>>>(ex_dev + site, halo, error_flag);
         return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
@@ -361,6 +461,10 @@ private:
     template <typename T>
     int reduce(cudaStream_t stream, int site, T *dev, int n, int kind) {
         if (site < 0 || site >= (int)kinds.size() || kinds[(size_t)site] != kind) { error = "peer transport: reduce site was not configured"; return -1; }
+        if ((long long)n * world <= 2048) {
+            peer_reduce_small_kernel<T><<<1, 256, 0, stream>>>(rd_dev + site, dev, error_flag);
+            return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
+        }
         int pgrid = (int)(((long long)n * world + 4095) / 4096), wgrid = (n + 4095) / 4096;
         pgrid = pgrid < 1 ? 1 : (pgrid > 128 ? 128 : pgrid);
         wgrid = wgrid < 1 ? 1 : (wgrid > 64 ? 64 : wgrid);
