@@ -862,6 +862,9 @@ def main():
                               % (stats["mg_levels"], stats["mg_operator_complexity"],
                                  "on the device (one CUDA graph per ARAP iteration)" if stats["cg_graph"] == 2 else "driven by the host (one CUDA graph per CG iteration)"))
                    if stats["mg_levels"] else "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "stopping_rule": stopping_rule(args),
+                   "one_ring_kernels": ("neighbourhood staged through shared memory in tiles of 256 rows (largest tile halo %d)" % stats["tile_max_halo"])
+                   if stats["tile_max_halo"] > 0 else "gathers straight from global memory",
+                   "vertex_order": "renumbered internally in Morton patches" if stats["renumbered"] else "the caller's order",
                    "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
                 "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",

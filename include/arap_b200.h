@@ -144,7 +144,7 @@ typedef struct arap_solver_stats {
     int64_t comm_halo_bytes_per_cg_iteration;   /* bytes this rank sends in those exchanges */
     int32_t tile_max_halo;         /* > 0: the one-ring kernels stage their neighbourhood through shared memory in tiles of 256 rows;
                                     * this is the largest tile halo (distinct neighbours outside the tile). 0: untiled kernels */
-    int32_t reserved0;
+    int32_t renumbered;            /* 1: the engine renumbered the vertices internally (Morton patches) for this handle */
     double setup_device_ms;        /* wall time of the multigrid setup when it ran on the device (setup_host_ms is then 0) */
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);

@@ -308,7 +308,7 @@ public:
     // tiles of kTile consecutive rows with their halo lists and tile-local column indices (tile_kernels.cuh)
     DeviceBuffer<int> tile_halo, tile_halo_count, tile_scalars;      // tile_scalars: [0] largest halo, [1] a tile did not fit
     DeviceBuffer<unsigned short> tile_colidx;
-    bool tiles_built = false, use_tiles = false;
+    bool tiles_built = false, use_tiles = false, renumbered = false;
     int n_tiles = 0, tile_max_halo = 0;
     TileView tile_view() const { return TileView{tile_halo.ptr, tile_halo_count.ptr, tile_colidx.ptr, n_tiles}; }
     size_t tile_smem(size_t record_bytes, int arrays) const { return (size_t)(kTile + tile_max_halo) * record_bytes * (size_t)arrays; }
@@ -750,6 +750,7 @@ public:
         if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
         stats.cg_graph = step_graph_exec ? 2 : (cg_graph_exec ? 1 : 0);
         stats.tile_max_halo = use_tiles ? tile_max_halo : 0;
+        stats.renumbered = renumbered ? 1 : 0;
         pdl_next_plain = true;
         stats.mg_global = (use_mg && mg_global) ? 1 : 0;
         have_warm_rotations = false;                                     // initializeRotations (arap.h:246-249)
@@ -781,15 +782,16 @@ public:
         ARAP_CUDA(cudaGetLastError());
         if (h[1] != 0) return ARAP_OK;                                  // a tile did not fit: untiled kernels
         tile_max_halo = (h[0] + 31) & ~31;
-        // dynamic shared memory of the staged kernels: (kTile + largest halo) records per staged array
-        const size_t s_local = tile_smem(sizeof(Vec4T<S>), 2), s_rhs = tile_smem(sizeof(Vec4T<S>), 3), s_vec = tile_smem(sizeof(MgVec), 1);
-        if (s_rhs > 200 * 1024) return ARAP_OK;
-        ARAP_CUDA(cudaFuncSetAttribute(local_step_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_local));
-        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_rhs));
-        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_rhs));
-        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_residual_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
-        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_postsmooth_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
-        ARAP_CUDA(cudaFuncSetAttribute(cg_spmv_z_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_vec));
+        // Dynamic shared memory of the staged kernels: (kTile + largest halo of THIS handle) records per staged array. The opt-in
+        // limit is a property of the kernel function, shared by every handle of the process (several partitions of one mesh
+        // may live in one process): always raise it to what the largest admissible halo needs, never to this handle's own size.
+        const size_t cap_records = (size_t)kTile + kTileHaloCap;
+        ARAP_CUDA(cudaFuncSetAttribute(local_step_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(Vec4T<S>) * 2)));
+        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(Vec4T<S>) * 3)));
+        ARAP_CUDA(cudaFuncSetAttribute(rhs_residual_tiled_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(Vec4T<S>) * 3)));
+        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_residual_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(MgVec))));
+        ARAP_CUDA(cudaFuncSetAttribute(mg_fine_postsmooth_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(MgVec))));
+        ARAP_CUDA(cudaFuncSetAttribute(cg_spmv_z_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap_records * sizeof(MgVec))));
         use_tiles = true;
         return ARAP_OK;
     }
@@ -959,6 +961,7 @@ public:
             const bool renumber = force || (tiling ? (double)cut_morton < 0.8 * (double)cut_user : (double)near_morton > 1.15 * (double)near_user);
             mg_visit_order.resize((size_t)V);
             for (int i = 0; i < V; ++i) mg_visit_order[(size_t)i] = i;
+            renumbered = renumber;
             if (renumber) {
                 for (int i = 0; i < owned; ++i) h_perm[(size_t)i] = keyed[(size_t)i].second;       // internal order IS the Morton order
             } else {
@@ -1041,6 +1044,8 @@ public:
         dirty = true;
         prepared = false;
         have_perm = false;
+        tiles_built = false;              // the owned block is renumbered on the next prepare: the tile structure follows
+        use_tiles = false;
         return ARAP_OK;
     }
 

@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
 #ifndef ARAP_LOCAL_MIN_BLOCKS
 #define ARAP_LOCAL_MIN_BLOCKS 4
 #endif
+#ifndef ARAP_RHS_MIN_BLOCKS
+#define ARAP_RHS_MIN_BLOCKS 3
+#endif
 template <typename S> struct GatherChunk;
 template <> struct GatherChunk<float> { static constexpr int value = 6; };
 template <> struct GatherChunk<double> { static constexpr int value = ARAP_LOCAL_CHUNK_F64; };
@@ -583,7 +586,7 @@ __global__ void cg_finalize_kernel(CgScalars *cg, int stage) {
 // MG = true : multigrid start (rho = 0 so the first beta is 0, x0 = omega0 D^-1 r feeds the first V-cycle).
 // (A variant with 8 lanes per vertex and a shuffle reduction of the nine partial sums measured 4x slower: 383 us.)
 template <typename S, bool MG>
-__global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+__global__ void __launch_bounds__(kBlock, ARAP_RHS_MIN_BLOCKS) rhs_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                               const S *__restrict__ weight, const Vec4T<S> *__restrict__ rest4,
                                                               const Vec4T<S> *__restrict__ cur4, const Vec4T<S> *__restrict__ quat,
                                                               const double *__restrict__ inv_diag, double omega0,
@@ -627,22 +630,18 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_kernel(int n, const in
                 for (int u = 0; u < CH; ++u) {
                     const S hw = S(0.5) * w[u];
                     const S ex = hw * (pi.x - pj[u].x), ey = hw * (pi.y - pj[u].y), ez = hw * (pi.z - pj[u].z);
-                    S rj[9];
-                    quat_to_matrix<S>(qj[u].x, qj[u].y, qj[u].z, qj[u].w, rj);     // quat stored as (w,x,y,z) in (.x,.y,.z,.w)
-                    rot_j[0] += (double)(rj[0] * ex + rj[1] * ey + rj[2] * ez);
-                    rot_j[1] += (double)(rj[3] * ex + rj[4] * ey + rj[5] * ez);
-                    rot_j[2] += (double)(rj[6] * ex + rj[7] * ey + rj[8] * ez);
+                    S rx, ry, rz;                                                  // R_j e_ij, quat stored as (w,x,y,z) in (.x,.y,.z,.w)
+                    quat_rotate<S>(qj[u].x, qj[u].y, qj[u].z, qj[u].w, ex, ey, ez, rx, ry, rz);
+                    rot_j[0] += (double)rx; rot_j[1] += (double)ry; rot_j[2] += (double)rz;
                     se[0] += (double)ex; se[1] += (double)ey; se[2] += (double)ez;
                     lap[0] += (double)w[u] * ((double)ci.x - (double)cj[u].x);
                     lap[1] += (double)w[u] * ((double)ci.y - (double)cj[u].y);
                     lap[2] += (double)w[u] * ((double)ci.z - (double)cj[u].z);
                 }
             }
-            double ri[9];
-            quat_to_matrix<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, ri);
-            const double rhs0 = rot_j[0] + ri[0] * se[0] + ri[1] * se[1] + ri[2] * se[2];
-            const double rhs1 = rot_j[1] + ri[3] * se[0] + ri[4] * se[1] + ri[5] * se[2];
-            const double rhs2 = rot_j[2] + ri[6] * se[0] + ri[7] * se[1] + ri[8] * se[2];
+            double ox, oy, oz;                                                     // R_i sum_j (w/2) e_ij
+            quat_rotate<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, se[0], se[1], se[2], ox, oy, oz);
+            const double rhs0 = rot_j[0] + ox, rhs1 = rot_j[1] + oy, rhs2 = rot_j[2] + oz;
             r.x = rhs0 - lap[0]; r.y = rhs1 - lap[1]; r.z = rhs2 - lap[2];
             const double idg = inv_diag[i];
             z.x = r.x * idg; z.y = r.y * idg; z.z = r.z * idg;

@@ -272,22 +272,18 @@ __global__ void __launch_bounds__(kBlock, 3) rhs_residual_tiled_kernel(int n, Ti
                         const Vec4T<S> pj = StageRec<S>::get(s_rest, lj[u]), cj = StageRec<S>::get(s_cur, lj[u]), qj = StageRec<S>::get(s_quat, lj[u]);
                         const S hw = S(0.5) * w[u];
                         const S ex = hw * (pi.x - pj.x), ey = hw * (pi.y - pj.y), ez = hw * (pi.z - pj.z);
-                        S rj[9];
-                        quat_to_matrix<S>(qj.x, qj.y, qj.z, qj.w, rj);     // quat stored as (w,x,y,z) in (.x,.y,.z,.w)
-                        rot_j[0] += (double)(rj[0] * ex + rj[1] * ey + rj[2] * ez);
-                        rot_j[1] += (double)(rj[3] * ex + rj[4] * ey + rj[5] * ez);
-                        rot_j[2] += (double)(rj[6] * ex + rj[7] * ey + rj[8] * ez);
+                        S rx, ry, rz;                                      // R_j e_ij, quat stored as (w,x,y,z) in (.x,.y,.z,.w)
+                        quat_rotate<S>(qj.x, qj.y, qj.z, qj.w, ex, ey, ez, rx, ry, rz);
+                        rot_j[0] += (double)rx; rot_j[1] += (double)ry; rot_j[2] += (double)rz;
                         se[0] += (double)ex; se[1] += (double)ey; se[2] += (double)ez;
                         lap[0] += (double)w[u] * ((double)ci.x - (double)cj.x);
                         lap[1] += (double)w[u] * ((double)ci.y - (double)cj.y);
                         lap[2] += (double)w[u] * ((double)ci.z - (double)cj.z);
                     }
                 }
-                double ri[9];
-                quat_to_matrix<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, ri);
-                const double rhs0 = rot_j[0] + ri[0] * se[0] + ri[1] * se[1] + ri[2] * se[2];
-                const double rhs1 = rot_j[1] + ri[3] * se[0] + ri[4] * se[1] + ri[5] * se[2];
-                const double rhs2 = rot_j[2] + ri[6] * se[0] + ri[7] * se[1] + ri[8] * se[2];
+                double ox, oy, oz;                                                 // R_i sum_j (w/2) e_ij
+                quat_rotate<double>((double)qi.x, (double)qi.y, (double)qi.z, (double)qi.w, se[0], se[1], se[2], ox, oy, oz);
+                const double rhs0 = rot_j[0] + ox, rhs1 = rot_j[1] + oy, rhs2 = rot_j[2] + oz;
                 r.x = rhs0 - lap[0]; r.y = rhs1 - lap[1]; r.z = rhs2 - lap[2];
                 z.x = r.x * idg; z.y = r.y * idg; z.z = r.z * idg;
                 red[0] += r.x * z.x; red[1] += r.y * z.y; red[2] += r.z * z.z;
