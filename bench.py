@@ -879,7 +879,7 @@ def main():
         "kernels": kernels,
         "kernels_note": "avg_us from a second pass of the same K steps with every launch bracketed by CUDA events (graphs off): ~1.5x slower than "
                         "the timed pass overall and ~5 us too long per small kernel; shares agree with the ncu launch list in profiles/",
-        "cg": {"iterations_per_arap_iteration": window_cg,
+        "cg": {"iterations_per_arap_iteration": window_cg, "kernel_launches_per_cg_iteration": stats["launches_per_cg_iteration"],
                "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
         "cold_start": {"what": "ARAP iterations 1..%d right after the handle move (the warm-up), one arap_iterate(1) each" % args.warmup,
                        "cg_iterations": cold["cg_iterations"], "ms": cold["ms"]},

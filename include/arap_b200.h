@@ -146,6 +146,8 @@ typedef struct arap_solver_stats {
                                     * this is the largest tile halo (distinct neighbours outside the tile). 0: untiled kernels */
     int32_t renumbered;            /* 1: the engine renumbered the vertices internally (Morton patches) for this handle */
     double setup_device_ms;        /* wall time of the multigrid setup when it ran on the device (setup_host_ms is then 0) */
+    int32_t launches_per_cg_iteration;   /* kernels in the captured CG iteration (0 when no graph was built) */
+    int32_t reserved1;
 } arap_solver_stats;
 int arap_get_solver_stats(arap_handle *h, arap_solver_stats *out);
 

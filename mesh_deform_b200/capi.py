@@ -52,7 +52,7 @@ class SolverStats(C.Structure):
                 ("mg_operator_complexity", C.c_double), ("setup_host_ms", C.c_double), ("cg_graph", C.c_int32), ("mg_global", C.c_int32), ("last_position_error", C.c_double),
                 ("comm_exchanges_per_cg_iteration", C.c_int32), ("comm_allreduces_per_cg_iteration", C.c_int32),
                 ("comm_halo_bytes_per_cg_iteration", C.c_int64), ("tile_max_halo", C.c_int32), ("renumbered", C.c_int32),
-                ("setup_device_ms", C.c_double)]
+                ("setup_device_ms", C.c_double), ("launches_per_cg_iteration", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class GlobalMesh(C.Structure):

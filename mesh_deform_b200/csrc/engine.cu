@@ -732,8 +732,15 @@ public:
         if (transport) { int rc = configure_transport(); if (rc) return rc; }
         destroy_step_graph();
         if (!transport) {
-            { int rc = build_cg_graph(); if (rc) return rc; }
-            { int rc = build_step_graph(); if (rc) return rc; }
+            int rc = build_cg_graph();
+            if (rc && tail_first > 0) {           // a cooperative / cluster launch that cannot be captured here: one launch per phase instead
+                cudaGetLastError();
+                tail_first = 0;
+                tail_grid = false;
+                rc = build_cg_graph();
+            }
+            if (rc) return rc;
+            { int rc2 = build_step_graph(); if (rc2) return rc2; }
         }
         else if (transport->capturable()) {
             // NCCL calls and the peer transport's kernels are stream operations and can sit inside the graph, which removes
@@ -750,6 +757,8 @@ public:
         if (transport && transport->barrier(stream)) return fail(ARAP_ERR_CUDA, transport->error);
         stats.cg_graph = step_graph_exec ? 2 : (cg_graph_exec ? 1 : 0);
         stats.tile_max_halo = use_tiles ? tile_max_halo : 0;
+        stats.launches_per_cg_iteration = 0;
+        for (int k = 0; k < ARAP_K_COUNT_MAX; ++k) stats.launches_per_cg_iteration += (int)(step_graph_exec ? body_counts[k] : graph_counts_iter[k]);
         stats.renumbered = renumbered ? 1 : 0;
         pdl_next_plain = true;
         stats.mg_global = (use_mg && mg_global) ? 1 : 0;
@@ -1875,22 +1884,33 @@ public:
         return ARAP_OK;      // gamma = r.z and the position-error norm sit in cg->red until CG_STAGE_MERGED
     }
 
-    // Which levels the one-kernel tail covers: from the first level with at most ARAP_TAIL_ROWS rows down to the coarsest,
-    // provided its parent is small enough for the two transfer phases to run inside one cluster.
-    // OFF by default (ARAP_TAIL_ROWS unset = 0). Measured at 1M vertices (profiles/r01_d_variants.txt, "one-kernel tail"): the
-    // 7 launches it replaces cost ~25 us per CG iteration when replayed from the CUDA graph (3.6 us each), the cluster kernel
-    // 34-42 us: with only 8-16 CTAs every phase is a chain of dependent L2 round trips that the full-GPU launches overlap.
+    // The coarse part of the V-cycle as one kernel. Two forms (ARAP_TAIL): "grid" (default) -- every level below the fine one,
+    // with the restriction out of and the prolongation into the fine level, in one COOPERATIVE kernel that fills the GPU and
+    // separates its phases with a grid barrier (mg_tail_grid_kernel); "cluster" -- the round-1 experiment (levels of at most
+    // ARAP_TAIL_ROWS rows in one thread-block cluster; measured slower than separate launches); "0" -- one launch per phase.
+    DeviceBuffer<GridBarrier> tail_barrier;
+    bool tail_grid = false;
+    int tail_grid_ctas = 0;
+    size_t tail_grid_smem = 0;
     int plan_tail() {
         tail_first = 0;
+        tail_grid = false;
         const int L = (int)mg.size();
-        const char *env_rows = getenv("ARAP_TAIL_ROWS"), *env_parent = getenv("ARAP_TAIL_PARENT_ROWS"), *env_cluster = getenv("ARAP_TAIL_CLUSTER");
-        const int max_rows = env_rows ? atoi(env_rows) : 0, max_parent = env_parent ? atoi(env_parent) : 65536;
-        tail_cluster = env_cluster ? atoi(env_cluster) : 8;
-        if (L < 2 || max_rows <= 0 || mg_global) return ARAP_OK;
+        const char *env_mode = getenv("ARAP_TAIL");
+        const std::string mode = env_mode ? env_mode : "grid";
+        if (L < 2 || mg_global || transport || mode == "0") return ARAP_OK;
         int t = 0;
-        for (int l = 1; l < L; ++l) if (mg[(size_t)l]->n <= max_rows) { t = l; break; }
-        if (t == 0 || mg[(size_t)t - 1]->n > max_parent || L - t + 1 > kTailMaxLevels) return ARAP_OK;
-        if (t - 1 == 0 && transport) return ARAP_OK;           // partitioned: level 0 rows are the owned rows only; keep the plain path
+        if (mode == "grid") {
+            if (L > kTailMaxLevels) return ARAP_OK;
+            t = 1;
+        } else {
+            const char *env_rows = getenv("ARAP_TAIL_ROWS"), *env_parent = getenv("ARAP_TAIL_PARENT_ROWS"), *env_cluster = getenv("ARAP_TAIL_CLUSTER");
+            const int max_rows = env_rows ? atoi(env_rows) : 0, max_parent = env_parent ? atoi(env_parent) : 65536;
+            tail_cluster = env_cluster ? atoi(env_cluster) : 8;
+            if (max_rows <= 0) return ARAP_OK;
+            for (int l = 1; l < L; ++l) if (mg[(size_t)l]->n <= max_rows) { t = l; break; }
+            if (t == 0 || mg[(size_t)t - 1]->n > max_parent || L - t + 1 > kTailMaxLevels) return ARAP_OK;
+        }
         std::memset(&tail_args, 0, sizeof(tail_args));
         tail_args.n_levels = L - t + 1;
         tail_args.dense = mg_dense ? 1 : 0;
@@ -1899,18 +1919,48 @@ public:
         for (int l = t - 1; l < L; ++l) {
             MgLevelDev &d = *mg[(size_t)l];
             MgTailLevel &a = tail_args.lv[l - (t - 1)];
-            a.n = d.n; a.a_lanes = d.a_lanes; a.r_lanes = d.r_lanes; a.omega = (float)d.omega;
+            a.n = (l == 0) ? n_rows : d.n;
+            a.a_lanes = d.a_lanes; a.r_lanes = d.r_lanes; a.omega = (float)d.omega;
             a.a_rowptr = d.a_rowptr.ptr; a.a_colidx = d.a_colidx.ptr; a.a_val = d.a_val.ptr; a.inv_diag = d.inv_diag.ptr;
             a.p_rowptr = d.p_rowptr.ptr; a.p_colidx = d.p_colidx.ptr; a.p_val = d.p_val.ptr;
             a.r_rowptr = d.r_rowptr.ptr; a.r_colidx = d.r_colidx.ptr; a.r_val = d.r_val.ptr;
             a.b = d.b.ptr; a.x = d.x.ptr; a.x2 = d.x2.ptr; a.r = d.r.ptr;
         }
-        if (tail_cluster > 8) ARAP_CUDA(cudaFuncSetAttribute(mg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (mode == "grid") {
+            int coop = 0;
+            ARAP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            if (!coop) return ARAP_OK;
+            tail_grid_smem = mg_dense ? sizeof(MgVec) * (size_t)mg_coarse_ld : 0;
+            if (tail_grid_smem > 48 * 1024) ARAP_CUDA(cudaFuncSetAttribute(mg_tail_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mg_tail_grid_kernel, kBlock, tail_grid_smem) != cudaSuccess || occ <= 0) { cudaGetLastError(); return ARAP_OK; }
+            const char *env_occ = getenv("ARAP_TAIL_CTAS_PER_SM");
+            if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
+            tail_grid_ctas = sm_count * occ;
+            ARAP_CUDA(tail_barrier.ensure(1));
+            ARAP_CUDA(cudaMemsetAsync(tail_barrier.ptr, 0, sizeof(GridBarrier), stream));
+            tail_grid = true;
+        } else if (tail_cluster > 8) {
+            ARAP_CUDA(cudaFuncSetAttribute(mg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
         tail_first = t;
         return ARAP_OK;
     }
 
     int launch_tail() {
+        if (tail_grid) {
+            const CgScalars *cgp = cg.ptr;
+            GridBarrier *bar = tail_barrier.ptr;
+            void *params[3] = {(void *)&tail_args, (void *)&cgp, (void *)&bar};
+            pdl_next_plain = true;
+            begin_launch(ARAP_K_MG_TAIL);
+            const cudaError_t e = cudaLaunchCooperativeKernel((const void *)mg_tail_grid_kernel, dim3((unsigned)tail_grid_ctas, 1, 1), dim3(kBlock, 1, 1), params,
+                                                              tail_grid_smem, stream);
+            end_launch();
+            pdl_next_plain = true;
+            if (e != cudaSuccess) return fail(ARAP_ERR_CUDA, std::string("mg_tail_grid_kernel launch: ") + cudaGetErrorString(e));
+            return ARAP_OK;
+        }
         cudaLaunchConfig_t cfg;
         cfg = cudaLaunchConfig_t();
         cfg.gridDim = dim3((unsigned)tail_cluster, 1, 1);

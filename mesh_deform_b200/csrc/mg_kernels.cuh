@@ -515,6 +515,149 @@ __global__ void __launch_bounds__(kTailThreads, 1) mg_tail_kernel(const MgTailAr
     prolong_add(args.lv[0], args.lv[1]);
 }
 
+// ---- the whole coarse part of the V-cycle in ONE cooperative kernel ---------------------------------------------------
+// Same phases as mg_tail_kernel, but run by a grid that fills the GPU (cudaLaunchCooperativeKernel: all CTAs co-resident)
+// and separated by a grid-wide barrier in global memory instead of a cluster barrier: with ~150k threads the 100k-row level 1
+// is processed as fast as by its own kernels, the small levels cost one barrier (~1.5 us) instead of a launch each, and the
+// restriction out of / prolongation into the fine level move in here too. One CG iteration at 1M vertices then is 5 launches
+// (fine residual, this kernel, fine post-smoothing, w = A z, the fused update) instead of 17.
+struct GridBarrier { unsigned count; unsigned generation; };
+
+__device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned n_blocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = *(volatile unsigned *)&b->generation;
+        __threadfence();                                          // this CTA's writes before the arrival
+        if (atomicAdd(&b->count, 1u) == n_blocks - 1) {
+            b->count = 0;
+            __threadfence();
+            atomicAdd(&b->generation, 1u);
+        } else {
+            while (*(volatile unsigned *)&b->generation == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock) mg_tail_grid_kernel(const MgTailArgs args, const CgScalars *__restrict__ cg, GridBarrier *bar) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    if (cg->converged) return;                                  // uniform over the grid: nobody reaches a barrier
+    const int nt = (int)gridDim.x * kBlock;
+    const int tid = (int)blockIdx.x * kBlock + (int)threadIdx.x;
+    const unsigned nb = gridDim.x;
+    const int L = args.n_levels;
+
+    auto restrict_presmooth = [&](const MgTailLevel &f, const MgTailLevel &c) {      // b_c = R r_f ; x_c = omega_c D_c^-1 b_c
+        const int lanes = f.r_lanes, per = nt / lanes;
+        for (int base = 0; base < c.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 bc = tail_apply_row(row, row < c.n, lanes, f.r_rowptr, f.r_colidx, f.r_val, f.r);
+            if (row < c.n && (threadIdx.x & (lanes - 1)) == 0) {
+                c.b[row] = MgVec{bc.x, bc.y, bc.z, 0.f};
+                const float s = c.omega * __ldg(&c.inv_diag[row]);
+                c.x[row] = MgVec{s * bc.x, s * bc.y, s * bc.z, 0.f};
+            }
+        }
+    };
+    auto residual = [&](const MgTailLevel &f) {                                       // r = b - A x
+        const int lanes = f.a_lanes, per = nt / lanes;
+        for (int base = 0; base < f.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 ax = tail_apply_row(row, row < f.n, lanes, f.a_rowptr, f.a_colidx, f.a_val, f.x);
+            if (row < f.n && (threadIdx.x & (lanes - 1)) == 0) {
+                const MgVec bi = tail_load(&f.b[row]);
+                f.r[row] = MgVec{bi.x - ax.x, bi.y - ax.y, bi.z - ax.z, 0.f};
+            }
+        }
+    };
+    auto postsmooth = [&](const MgTailLevel &f) {                                     // x2 = x + omega D^-1 (b - A x)
+        const int lanes = f.a_lanes, per = nt / lanes;
+        for (int base = 0; base < f.n; base += per) {
+            const int row = base + tid / lanes;
+            const float3 ax = tail_apply_row(row, row < f.n, lanes, f.a_rowptr, f.a_colidx, f.a_val, f.x);
+            if (row < f.n && (threadIdx.x & (lanes - 1)) == 0) {
+                const MgVec bi = tail_load(&f.b[row]), xi = tail_load(&f.x[row]);
+                const float s = f.omega * __ldg(&f.inv_diag[row]);
+                f.x2[row] = MgVec{xi.x + s * (bi.x - ax.x), xi.y + s * (bi.y - ax.y), xi.z + s * (bi.z - ax.z), 0.f};
+            }
+        }
+    };
+    auto prolong_add = [&](const MgTailLevel &f, const MgTailLevel &c) {              // x_f += P x2_c (P rows are short: one thread each)
+        for (int row = tid; row < f.n; row += nt) {
+            const int k0 = __ldg(&f.p_rowptr[row]), k1 = __ldg(&f.p_rowptr[row + 1]);
+            if (k0 == k1) continue;
+            MgVec xi = tail_load(&f.x[row]);
+            for (int k = k0; k < k1; ++k) {
+                const float a = __ldg(&f.p_val[k]);
+                const MgVec xc = tail_load(&c.x2[__ldg(&f.p_colidx[k])]);
+                xi.x += a * xc.x; xi.y += a * xc.y; xi.z += a * xc.z;
+            }
+            f.x[row] = xi;
+        }
+    };
+
+    // down
+    restrict_presmooth(args.lv[0], args.lv[1]);
+    grid_barrier(bar, nb);
+    for (int l = 1; l + 1 < L; ++l) {
+        residual(args.lv[l]);
+        grid_barrier(bar, nb);
+        restrict_presmooth(args.lv[l], args.lv[l + 1]);
+        grid_barrier(bar, nb);
+    }
+    // coarsest
+    {
+        const MgTailLevel &c = args.lv[L - 1];
+        if (args.dense) {                                         // x2 = A^-1 b: one warp per row, b staged in shared memory by the CTAs that have rows
+            const int n = c.n, ld = args.coarse_ld, n4 = ld >> 2;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if ((int)blockIdx.x * kWarpsPerBlock < n) {
+                MgVec *sb = reinterpret_cast<MgVec *>(tail_smem);
+                for (int k = threadIdx.x; k < ld; k += kBlock) sb[k] = k < n ? tail_load(&c.b[k]) : MgVec{0.f, 0.f, 0.f, 0.f};
+                __syncthreads();
+                for (int row = (int)blockIdx.x * kWarpsPerBlock + warp; row < n; row += (int)gridDim.x * kWarpsPerBlock) {
+                    const float4 *arow = reinterpret_cast<const float4 *>(args.coarse_inv + (size_t)row * ld);
+                    float s0 = 0, s1 = 0, s2 = 0;
+                    for (int base = 0; base < n4; base += 32 * 8) {
+                        float4 a[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int q = base + lane + 32 * u; a[u] = q < n4 ? __ldg(&arow[q]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int q = base + lane + 32 * u;
+                            if (q < n4) {
+                                const MgVec *bq = sb + 4 * q;
+                                s0 += a[u].x * bq[0].x + a[u].y * bq[1].x + a[u].z * bq[2].x + a[u].w * bq[3].x;
+                                s1 += a[u].x * bq[0].y + a[u].y * bq[1].y + a[u].z * bq[2].y + a[u].w * bq[3].y;
+                                s2 += a[u].x * bq[0].z + a[u].y * bq[1].z + a[u].z * bq[2].z + a[u].w * bq[3].z;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+                    }
+                    if (lane == 0) c.x2[row] = MgVec{s0, s1, s2, 0.f};
+                }
+            }
+        } else {
+            postsmooth(c);
+        }
+    }
+    grid_barrier(bar, nb);
+    // up
+    for (int l = L - 2; l >= 1; --l) {
+        prolong_add(args.lv[l], args.lv[l + 1]);
+        grid_barrier(bar, nb);
+        postsmooth(args.lv[l]);
+        grid_barrier(bar, nb);
+    }
+    prolong_add(args.lv[0], args.lv[1]);
+}
+
 // ---- dense inverse of the coarsest operator on the device (setup, once per hierarchy) ---------------------------------
 // The host inverts coarsest levels of up to a few hundred rows; with up to 2048 rows the hierarchy is one or two levels
 // shorter (4-8 launches less per V-cycle), but O(n^3) scalar host code would take seconds. In-place Gauss-Jordan without
