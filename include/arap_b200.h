@@ -121,6 +121,15 @@ int arap_get_rotations(arap_handle *h, void *rot9);
  * the vertex with free index f (arap_get_free_map). Runs the engine's right-hand-side kernel once; for tests / inspection. */
 int arap_get_rhs(arap_handle *h, double *rhs /* n_free x 3 */);
 
+/* Viewer interop (the per-frame work of the reference's viewer, examples/osg_viewer.cpp:45-72: update_normals(), then copy
+ * positions and normals into float vertex arrays and re-upload them): float positions (V x 3) and -- unless `normals` is NULL --
+ * per-vertex normals (V x 3; unit face normals of the current pose summed over the incident faces and normalised, what
+ * OpenMesh's update_normals() computes), both made on the device. location = ARAP_BUFFER_HOST: the pointers are host memory;
+ * ARAP_BUFFER_DEVICE: they are DEVICE memory of the caller on the handle's device, e.g. an OpenGL vertex buffer mapped with
+ * cudaGraphicsResourceGetMappedPointer -- the frame's geometry then never leaves the GPU. */
+enum { ARAP_BUFFER_HOST = 0, ARAP_BUFFER_DEVICE = 1 };
+int arap_get_render_buffers(arap_handle *h, float *positions, float *normals, int32_t location);
+
 /* ARAP energy sum_i sum_j w_ij |(p'_i-p'_j) - R_i (p_i-p_j)|^2 (Sorkine & Alexa eq. 3; the reference has none). */
 int arap_energy(arap_handle *h, double *energy);
 

@@ -29,7 +29,7 @@ K_COUNT_MAX = 32
 EXPORTED_SYMBOLS = (
     "arap_default_options", "arap_create", "arap_destroy", "arap_set_constraints", "arap_is_dirty",
     "arap_prepare", "arap_iterate", "arap_get_positions", "arap_deform", "arap_get_csr_nnz", "arap_get_csr",
-    "arap_get_free_map", "arap_get_rotations", "arap_get_rhs", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
+    "arap_get_free_map", "arap_get_rotations", "arap_get_rhs", "arap_get_render_buffers", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
     "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
     "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
@@ -107,6 +107,7 @@ def lib():
     L.arap_get_free_map.argtypes = [vp, vp, C.POINTER(i32)]
     L.arap_get_rotations.argtypes = [vp, vp]
     L.arap_get_rhs.argtypes = [vp, vp]
+    L.arap_get_render_buffers.argtypes = [vp, vp, vp, i32]
     L.arap_energy.argtypes = [vp, C.POINTER(C.c_double)]
     L.arap_get_solver_stats.argtypes = [vp, C.POINTER(SolverStats)]
     L.arap_profile_enable.argtypes = [vp, i32]
@@ -296,6 +297,17 @@ class AsRigidAsPossibleDeformation:
         out = np.zeros((n_free, 3), np.float64)
         self._check(lib().arap_get_rhs(self._h, _ptr(out)))
         return out
+
+    def render_buffers(self, normals=True, device_pointers=None):
+        """Viewer interop (reference examples/osg_viewer.cpp:45-72): float32 positions and vertex normals of the current pose.
+        device_pointers = (positions_ptr, normals_ptr or 0): write into device memory of the caller (a mapped VBO) instead."""
+        if device_pointers is not None:
+            self._check(lib().arap_get_render_buffers(self._h, C.c_void_p(device_pointers[0]), C.c_void_p(device_pointers[1] or None), 1))
+            return None
+        pos = np.zeros((self.nV, 3), np.float32)
+        nrm = np.zeros((self.nV, 3), np.float32) if normals else None
+        self._check(lib().arap_get_render_buffers(self._h, _ptr(pos), _ptr(nrm) if normals else None, 0))
+        return pos, nrm
 
     def energy(self):
         e = C.c_double()

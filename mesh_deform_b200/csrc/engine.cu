@@ -104,6 +104,7 @@ public:
     virtual int get_free_map(int *free_idx, int *n_free) = 0;
     virtual int get_rotations(void *rot9) = 0;
     virtual int get_rhs(double *out) = 0;
+    virtual int get_render_buffers(float *positions, float *normals, int location) = 0;
     virtual int energy(double *e) = 0;
     virtual int attach_partition(const arap_partition_plan *p, int rank, int world, int kind, const void *id, int id_bytes) = 0;
     virtual int set_global_mesh(const arap_global_mesh *g) = 0;
@@ -2454,6 +2455,46 @@ public:
         ARAP_CUDA(cudaGetLastError());
         return ARAP_OK;
     }
+    // Viewer interop (reference examples/osg_viewer.cpp:45-72): float positions + vertex normals of the current pose, into host
+    // memory or straight into a device buffer of the caller (location = ARAP_BUFFER_DEVICE: e.g. a mapped OpenGL VBO).
+    DeviceBuffer<int> vf_ptr, vf_face, vf_cursor;
+    DeviceBuffer<float4> face_normal;
+    DeviceBuffer<float> render_staging;
+    bool vf_built = false;
+    int get_render_buffers(float *positions, float *normals, int location) override {
+        if (!positions || (location != ARAP_BUFFER_HOST && location != ARAP_BUFFER_DEVICE)) return fail(ARAP_ERR_INVALID, "get_render_buffers: bad arguments");
+        if (!cur4.ptr || !have_perm) return fail(ARAP_ERR_INVALID, "get_render_buffers: no state (call arap_prepare first)");
+        if (transport) return fail(ARAP_ERR_INVALID, "get_render_buffers: not available on a partitioned handle");
+        const int V = n_vertices, F = n_faces;
+        if (normals && !vf_built) {
+            ARAP_CUDA(vf_ptr.ensure((size_t)V + 1));
+            ARAP_CUDA(vf_cursor.ensure((size_t)V + 1));
+            ARAP_CUDA(vf_face.ensure(3 * (size_t)F));
+            ARAP_CUDA(face_normal.ensure((size_t)F));
+            ARAP_CUDA(cudaMemsetAsync(vf_cursor.ptr, 0, sizeof(int) * ((size_t)V + 1), stream));
+            if (F > 0) LAUNCH(ARAP_K_MISC, vf_count_kernel, grid_for((size_t)F), F, faces.ptr, vf_cursor.ptr);
+            { int rc = exclusive_scan(vf_cursor.ptr, V, vf_ptr.ptr); if (rc) return rc; }
+            ARAP_CUDA(cudaMemsetAsync(vf_cursor.ptr, 0, sizeof(int) * ((size_t)V + 1), stream));
+            if (F > 0) LAUNCH(ARAP_K_MISC, vf_fill_kernel, grid_for((size_t)F), F, faces.ptr, vf_ptr.ptr, vf_cursor.ptr, vf_face.ptr);
+            if (V > 0) LAUNCH(ARAP_K_MISC, vf_sort_kernel, grid_for((size_t)V), V, vf_ptr.ptr, vf_face.ptr);
+            vf_built = true;
+        }
+        float *d_pos = positions, *d_nrm = normals;
+        if (location == ARAP_BUFFER_HOST) {
+            ARAP_CUDA(render_staging.ensure(6 * (size_t)(V > 0 ? V : 1)));
+            d_pos = render_staging.ptr;
+            d_nrm = normals ? render_staging.ptr + 3 * (size_t)V : nullptr;
+        }
+        if (normals && F > 0) LAUNCH(ARAP_K_MISC, face_normals_kernel<S>, grid_for((size_t)F), F, faces.ptr, iperm.ptr, cur4.ptr, face_normal.ptr);
+        if (V > 0) LAUNCH(ARAP_K_MISC, render_buffers_kernel<S>, grid_for((size_t)V), V, iperm.ptr, cur4.ptr, vf_ptr.ptr, vf_face.ptr, face_normal.ptr, d_pos, d_nrm);
+        if (location == ARAP_BUFFER_HOST) {
+            ARAP_CUDA(cudaMemcpyAsync(positions, d_pos, sizeof(float) * 3 * (size_t)V, cudaMemcpyDeviceToHost, stream));
+            if (normals) ARAP_CUDA(cudaMemcpyAsync(normals, d_nrm, sizeof(float) * 3 * (size_t)V, cudaMemcpyDeviceToHost, stream));
+        }
+        ARAP_CUDA(cudaStreamSynchronize(stream));
+        ARAP_CUDA(cudaGetLastError());
+        return ARAP_OK;
+    }
     int energy(double *e) override {
         if (!quat.ptr || !hot_rowptr.ptr) return fail(ARAP_ERR_INVALID, "energy: call arap_prepare first");
         const int V = prepared ? n_rows : n_vertices;      // partitioned mode: this rank's share (owned rows)
@@ -2610,6 +2651,10 @@ int arap_get_rhs(arap_handle *h, double *rhs) {
     ARAP_ENGINE_OR_FAIL(h);
     if (!rhs) return ARAP_ERR_INVALID;
     return h->engine->get_rhs(rhs);
+}
+int arap_get_render_buffers(arap_handle *h, float *positions, float *normals, int32_t location) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->get_render_buffers(positions, normals, location);
 }
 int arap_energy(arap_handle *h, double *energy) {
     ARAP_ENGINE_OR_FAIL(h);

@@ -1059,4 +1059,70 @@ __global__ void __launch_bounds__(kBlock) export_rotations_kernel(int n, const i
     for (int k = 0; k < 9; ++k) rot9[9 * u + k] = r[k];
 }
 
+// =================================================================================================
+// Viewer interop (reference examples/osg_viewer.cpp:45-72): what the viewer's update callback needs every frame --
+// float positions and per-vertex normals -- produced on the device, optionally straight into a caller-owned DEVICE buffer
+// (a mapped OpenGL vertex buffer), so a frame needs no host round trip of the geometry.
+// Normals as OpenMesh's update_normals() makes them: unit face normals, vertex normal = normalised sum of the incident ones.
+// =================================================================================================
+// vertex -> incident faces, built once per handle: counts, (scan), fill with cursors, rows sorted by face id
+__global__ void __launch_bounds__(kBlock) vf_count_kernel(int n_faces, const int *__restrict__ faces, int *__restrict__ count) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) atomicAdd(&count[faces[3 * (size_t)f + k]], 1);
+}
+__global__ void __launch_bounds__(kBlock) vf_fill_kernel(int n_faces, const int *__restrict__ faces, const int *__restrict__ vf_ptr,
+                                                         int *__restrict__ cursor, int *__restrict__ vf_face) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int v = faces[3 * (size_t)f + k];
+        vf_face[vf_ptr[v] + atomicAdd(&cursor[v], 1)] = f;
+    }
+}
+__global__ void __launch_bounds__(kBlock) vf_sort_kernel(int n_vertices, const int *__restrict__ vf_ptr, int *__restrict__ vf_face) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vertices) return;
+    const int lo = vf_ptr[v], hi = vf_ptr[v + 1];
+    for (int a = lo + 1; a < hi; ++a) {
+        const int f = vf_face[a];
+        int b = a - 1;
+        while (b >= lo && vf_face[b] > f) { vf_face[b + 1] = vf_face[b]; --b; }
+        vf_face[b + 1] = f;
+    }
+}
+// unit face normals of the current pose ((p1 - p0) x (p2 - p0), the mesh's own winding); degenerate faces get (0,0,0)
+template <typename S>
+__global__ void __launch_bounds__(kBlock) face_normals_kernel(int n_faces, const int *__restrict__ faces, const int *__restrict__ iperm,
+                                                              const Vec4T<S> *__restrict__ cur4, float4 *__restrict__ face_normal) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const Vec4T<S> a = cur4[iperm[faces[3 * (size_t)f]]], b = cur4[iperm[faces[3 * (size_t)f + 1]]], c = cur4[iperm[faces[3 * (size_t)f + 2]]];
+    const double ux = (double)b.x - (double)a.x, uy = (double)b.y - (double)a.y, uz = (double)b.z - (double)a.z;
+    const double vx = (double)c.x - (double)a.x, vy = (double)c.y - (double)a.y, vz = (double)c.z - (double)a.z;
+    const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    const double len = sqrt(nx * nx + ny * ny + nz * nz);
+    const double inv = len > 0.0 ? 1.0 / len : 0.0;
+    face_normal[f] = make_float4((float)(nx * inv), (float)(ny * inv), (float)(nz * inv), 0.f);
+}
+// float positions + vertex normals in the caller's vertex numbering (one thread per user vertex)
+template <typename S>
+__global__ void __launch_bounds__(kBlock) render_buffers_kernel(int n_vertices, const int *__restrict__ iperm, const Vec4T<S> *__restrict__ cur4,
+                                                                const int *__restrict__ vf_ptr, const int *__restrict__ vf_face,
+                                                                const float4 *__restrict__ face_normal, float *__restrict__ out_pos,
+                                                                float *__restrict__ out_nrm) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vertices) return;
+    const Vec4T<S> p = cur4[iperm[v]];
+    out_pos[3 * (size_t)v] = (float)p.x; out_pos[3 * (size_t)v + 1] = (float)p.y; out_pos[3 * (size_t)v + 2] = (float)p.z;
+    if (!out_nrm) return;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    for (int k = vf_ptr[v]; k < vf_ptr[v + 1]; ++k) { const float4 n = face_normal[vf_face[k]]; nx += n.x; ny += n.y; nz += n.z; }
+    const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+    const float inv = len > 0.f ? 1.f / len : 0.f;
+    out_nrm[3 * (size_t)v] = nx * inv; out_nrm[3 * (size_t)v + 1] = ny * inv; out_nrm[3 * (size_t)v + 2] = nz * inv;
+}
+
 }  // namespace arap

@@ -239,3 +239,35 @@ def test_device_built_hierarchy_matches_host_built(mesh, monkeypatch):
     dev, host = results["device"][2], results["host"][2]
     assert dev["cg_iterations_total"] <= 1.6 * host["cg_iterations_total"] + 4      # a different aggregation, not a worse preconditioner
     assert dev["mg_operator_complexity"] <= 1.6
+
+
+def test_viewer_interop_render_buffers(meshes):
+    """reference examples/osg_viewer.cpp:45-72: after deform() the viewer recomputes the normals (OpenMesh update_normals) and
+    refills its float vertex / normal arrays. arap_get_render_buffers produces both on the device, into host memory or straight
+    into a device buffer of the caller (what a mapped OpenGL VBO is)."""
+    import torch
+    P, F = meshes["sphere"]
+    mesh = P.astype(np.float32)
+    a = ARAP(mesh, F, np.float64)
+    a.setConstraint(37, P[37])
+    a.setConstraint(32, P[32] + [0, 0, 0.5])
+    assert a.deform(5)
+    pos, nrm = a.render_buffers()
+    assert np.array_equal(pos, mesh)                                    # the same float cast as the write-back (arap.h:133-135)
+    p = a.positions(np.float64)
+    fn = np.cross(p[F[:, 1]] - p[F[:, 0]], p[F[:, 2]] - p[F[:, 0]])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    vn = np.zeros_like(p)
+    for k in range(3):
+        np.add.at(vn, F[:, k], fn)
+    vn /= np.linalg.norm(vn, axis=1, keepdims=True)
+    assert np.abs(nrm - vn).max() < 2e-6
+    assert np.abs(np.linalg.norm(nrm, axis=1) - 1).max() < 1e-6
+    # the same into caller-owned device memory: no host round trip of the geometry
+    d_pos = torch.zeros((P.shape[0], 3), dtype=torch.float32, device="cuda")
+    d_nrm = torch.zeros((P.shape[0], 3), dtype=torch.float32, device="cuda")
+    a.render_buffers(device_pointers=(d_pos.data_ptr(), d_nrm.data_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_pos.cpu().numpy(), pos) and np.array_equal(d_nrm.cpu().numpy(), nrm)
+    pos_only, none = a.render_buffers(normals=False)
+    assert none is None and np.array_equal(pos_only, pos)
