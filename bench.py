@@ -436,14 +436,41 @@ def _strip(res):
     return {k: v for k, v in res.items() if k != "positions"}
 
 
-def multi_gpu_arms(args, rank, world, local_rank, dist):
+class Watchdog:
+    """Prints rank 0's JSON line and ends the process if the guarded section does not finish in `seconds` (a rank stuck in a
+    collective cannot be interrupted from Python; a timer thread can still print and leave)."""
+
+    def __init__(self, rank, line, seconds):
+        self.rank, self.line, self.seconds = rank, line, seconds
+        self.timer = None
+
+    def _fire(self):
+        if self.rank == 0 and self.line is not None:
+            try:
+                self.line.setdefault("multi_gpu", {})["watchdog"] = "multi-GPU arms did not finish within %d s; partial results" % self.seconds
+                print(json.dumps(self.line, default=str), flush=True)
+            except Exception:      # noqa: BLE001
+                pass
+        os._exit(0)
+
+    def start(self):
+        self.timer = threading.Timer(self.seconds, self._fire)
+        self.timer.daemon = True
+        self.timer.start()
+
+    def cancel(self):
+        if self.timer is not None:
+            self.timer.cancel()
+
+
+def multi_gpu_arms(args, rank, world, local_rank, dist, out):
     """Partitioned strong scaling (one grid over N strips and over N blocks), weak scaling (2M vertices per GPU), the sharded
     batch of sphere deformations, and a partitioned run checked against the CPU oracle. Sizes come from --part-nx,
     --weak-verts-per-gpu, --batch, --oracle-nx (defaults = BASELINE.json configs[3], configs[4])."""
     from mesh_deform_b200 import meshgen as G, partition as PT
     t_begin = time.perf_counter()
-    out = {"world": world, "note": "one process per GPU; partitioned arms exchange halos of p', R, the multigrid vectors and the CG's gathered "
-                                   "vector and all-reduce the CG scalars every CG iteration (transport: %s)" % args.transport}
+    out.update({"world": world, "note": "one process per GPU; partitioned arms exchange halos of p', R, the multigrid vectors and the CG's gathered "
+                                        "vector and all-reduce the CG scalars every CG iteration (transport: %s)" % args.transport})
     W, K = args.warmup, args.steps
 
     def over_budget():      # collective: every rank must take the same decision
@@ -775,126 +802,132 @@ def main():
                "positions": a32.positions(np.float64), "energy": a32.energy(), "iterations": parity_iters}
         a32.close()
 
-    multi = None
     if dist is not None and not args.no_multi:
         arap.close()
         del pinned, mesh
-        multi = multi_gpu_arms(args, rank, world, local_rank, dist)
+    line = None
+    if rank == 0:
+        value = world * args.steps / (ms * 1e-3)
+        e2e_value = world * args.steps / (e2e_ms * 1e-3)
+        ab = algorithmic_bytes(V, n_free, nnz, s)
+        total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {}
+        for name, v in prof.items():
+            if v["launches"] == 0:
+                continue
+            avg_ms = v["ms"] / v["launches"]
+            entry = {"launches_per_step": v["launches"] / args.steps, "avg_us": 1e3 * avg_ms, "share": v["ms"] / total_kernel_ms}
+            if name in ab and avg_ms > 0:
+                entry["algorithmic_bytes"] = ab[name]
+                entry["achieved_gbs"] = ab[name] / (avg_ms * 1e-3) / 1e9
+                entry["frac_of_peak"] = entry["achieved_gbs"] / peak_gbs
+            kernels[name] = entry
+        # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
+        ncu_file = next((f for f in ("r02_ncu_summary.json", "r01_h_ncu_summary.json") if os.path.exists(os.path.join(ROOT, "profiles", f))), None)
+        ncu = json.load(open(os.path.join(ROOT, "profiles", ncu_file))) if ncu_file and args.nu == 316 and args.precision == "f64" else {}
+        for name, entry in kernels.items():
+            if name in ncu and "traffic_bytes" in ncu[name]:
+                entry["ncu_dram_traffic_bytes"] = ncu[name]["traffic_bytes"]
+        # The roofline object is pinned to the kernel BASELINE.json's metric names (the local step); the whole step's aggregate and
+        # every other kernel sit beside it. (Round 1 picked "the kernel with the largest share", which flipped between three ~11 % kernels.)
+        pinned_kernel = "local_step" if "local_step" in kernels and "achieved_gbs" in kernels["local_step"] else \
+            max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["share"])
+        pk = kernels[pinned_kernel]
+        step_bytes = sum(kernels[k]["algorithmic_bytes"] * kernels[k]["launches_per_step"] for k in kernels if "algorithmic_bytes" in kernels[k])
+        roofline = {"kernel": pinned_kernel, "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak_gbs,
+                    "unit": "GB/s", "frac": pk["frac_of_peak"],
+                    "traffic": pk.get("ncu_dram_traffic_bytes"), "algorithmic_bytes": pk["algorithmic_bytes"],
+                    "traffic_source": ("profiles/%s (ncu --set full, dram__bytes_read+write per launch)" % ncu_file) if ncu else None,
+                    "peak_source": peak_src, "share_of_step": pk["share"], "avg_launch_us": pk["avg_us"],
+                    "step_aggregate": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                       "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak_gbs,
+                                       "note": "algorithmic bytes of every fine-level kernel of one ARAP iteration / un-profiled time per iteration "
+                                               "(the coarse multigrid levels count as time but not as bytes)"}}
+        local = kernels.get("local_step", {})
+
+        cpu_baseline = None
+        parity_out = None
+        if parity is not None:
+            o, omesh, t_prep = run_cpu_oracle(P, F, idx, tgt, 0, real)
+            o.reset_timers()
+            t0 = time.perf_counter()
+            o.deform(parity_iters)
+            dt = time.perf_counter() - t0
+            tm = o.timers()
+            diag = float(np.linalg.norm(P.max(0) - P.min(0)))
+            cpu_e = o.energy()
+            parity_out = {"iterations": parity_iters,
+                          "max_dp_over_bbox_diag": float(np.abs(parity["gpu_positions"] - omesh.astype(np.float64)).max() / diag),
+                          "rel_energy_diff": abs(parity["gpu_energy"] - cpu_e) / cpu_e, "tolerance": {"dp": 1e-5, "dE": 1e-6},
+                          "note": "engine vs the CPU oracle after the cold start + %d warm-up + %d timed iterations: the state at the end of the timed window" % (args.warmup, args.steps)}
+            if f32 is not None:
+                f32["max_dp_over_bbox_diag_vs_fp64_oracle"] = float(np.abs(f32.pop("positions") - omesh.astype(np.float64)).max() / diag)
+                f32["rel_energy_diff_vs_fp64_oracle"] = abs(f32.pop("energy") - cpu_e) / cpu_e
+            cpu_baseline = {"value": parity_iters / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"full workload (V={V}), {parity_iters} ARAP iterations after prepare; prepare {t_prep:.1f} s "
+                                      f"(LDL^T factor, {o.factor_nnz()} nnz) excluded; per-iteration s: local {tm['local'] / parity_iters:.3f} "
+                                      f"rhs {tm['rhs'] / parity_iters:.3f} solve {tm['solve'] / parity_iters:.3f}; host cores available: {os.cpu_count()}"}
+        if f32 is not None:
+            f32.pop("positions", None)
+            f32.pop("energy", None)
+
+        working_set_mb = (V * (3 * 4 * s + 8) + nnz * (4 + s) + V * 4 + V * 4 * 24) / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"icosphere nu={args.nu} V={V} 5% anchors + 1% handles (BASELINE.json configs[2])",
+                       "vertices": int(V), "faces": int(F.shape[0]), "nnz": nnz, "n_free": int(n_free),
+                       "sharding": "one independent deformation per GPU, no collective (the partitioned and batched workloads are in `multi_gpu`)" if world > 1 else "single GPU",
+                       "solver": ("warm-started single-reduction CG, smoothed-aggregation multigrid V(1,1) preconditioner, %d levels, operator complexity %.2f, CG loop %s"
+                                  % (stats["mg_levels"], stats["mg_operator_complexity"],
+                                     "on the device (one CUDA graph per ARAP iteration)" if stats["cg_graph"] == 2 else "driven by the host (one CUDA graph per CG iteration)"))
+                       if stats["mg_levels"] else "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "stopping_rule": stopping_rule(args),
+                       "one_ring_kernels": ("neighbourhood staged through shared memory in tiles of 256 rows (largest tile halo %d)" % stats["tile_max_halo"])
+                       if stats["tile_max_halo"] > 0 else "gathers straight from global memory",
+                       "vertex_order": "renumbered internally in Morton patches" if stats["renumbered"] else "the caller's order",
+                       "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
+                    "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",
+                    "h2d_note": "deform() reads the mesh only when a constraint changed (reference arap.h:102-107), so a steady-state step has no "
+                                "host input; the per-frame protocol WITH the upload is `frame`",
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "local_step": {"achieved_gbs": local.get("achieved_gbs"), "frac_of_measured_peak": local.get("frac_of_peak"),
+                           "frac_of_nominal_8TBs": (local.get("achieved_gbs") or 0) / 8000.0, "avg_us": local.get("avg_us")},
+            "kernels": kernels,
+            "kernels_note": "avg_us from a second pass of the same K steps with every launch bracketed by CUDA events (graphs off): ~1.5x slower than "
+                            "the timed pass overall and ~5 us too long per small kernel; shares agree with the ncu launch list in profiles/",
+            "cg": {"iterations_per_arap_iteration": window_cg, "kernel_launches_per_cg_iteration": stats["launches_per_cg_iteration"],
+                   "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
+            "cold_start": {"what": "ARAP iterations 1..%d right after the handle move (the warm-up), one arap_iterate(1) each" % args.warmup,
+                           "cg_iterations": cold["cg_iterations"], "ms": cold["ms"]},
+            "prepare_ms": prepare_ms, "prepare_host_setup_ms": prepare_host_setup_ms, "prepare_device_setup_ms": prepare_device_setup_ms,
+            "frame": {"protocol": "setConstraint(handles) + deform(5) incl. the dirty rebuild: H2D rest pose, weights/CSR, 5 iterations, D2H (reference demo loop)",
+                      "ms": frame_ms, "h2d_bytes": int(V * 3 * s + 10 * (4 + 3 * 8)), "d2h_bytes": int(V * 3 * s),
+                      "iterations_per_s": 5.0 / (frame_ms * 1e-3)},
+            "profiled_pass_ms_per_step": ms_profiled / args.steps,
+            "f32": f32,
+            "cpu_baseline": cpu_baseline,
+            "parity": parity_out,
+        }
+    if dist is not None and not args.no_multi:
+        # The multi-GPU workloads run AFTER the headline line is assembled, under a watchdog: should a rank ever hang in a
+        # collective, rank 0 still prints the line (with whatever arms finished) and every rank leaves before the driver's limit.
+        multi = {}
+        if line is not None:
+            line["multi_gpu"] = multi
+        watchdog = Watchdog(rank, line, args.multi_budget_s + 150)
+        watchdog.start()
+        multi_gpu_arms(args, rank, world, local_rank, dist, multi)
+        watchdog.cancel()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    if rank != 0:
-        return 0
-
-    value = world * args.steps / (ms * 1e-3)
-    e2e_value = world * args.steps / (e2e_ms * 1e-3)
-    ab = algorithmic_bytes(V, n_free, nnz, s)
-    total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    kernels = {}
-    for name, v in prof.items():
-        if v["launches"] == 0:
-            continue
-        avg_ms = v["ms"] / v["launches"]
-        entry = {"launches_per_step": v["launches"] / args.steps, "avg_us": 1e3 * avg_ms, "share": v["ms"] / total_kernel_ms}
-        if name in ab and avg_ms > 0:
-            entry["algorithmic_bytes"] = ab[name]
-            entry["achieved_gbs"] = ab[name] / (avg_ms * 1e-3) / 1e9
-            entry["frac_of_peak"] = entry["achieved_gbs"] / peak_gbs
-        kernels[name] = entry
-    # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
-    ncu_file = next((f for f in ("r02_ncu_summary.json", "r01_h_ncu_summary.json") if os.path.exists(os.path.join(ROOT, "profiles", f))), None)
-    ncu = json.load(open(os.path.join(ROOT, "profiles", ncu_file))) if ncu_file and args.nu == 316 and args.precision == "f64" else {}
-    for name, entry in kernels.items():
-        if name in ncu and "traffic_bytes" in ncu[name]:
-            entry["ncu_dram_traffic_bytes"] = ncu[name]["traffic_bytes"]
-    # The roofline object is pinned to the kernel BASELINE.json's metric names (the local step); the whole step's aggregate and
-    # every other kernel sit beside it. (Round 1 picked "the kernel with the largest share", which flipped between three ~11 % kernels.)
-    pinned_kernel = "local_step" if "local_step" in kernels and "achieved_gbs" in kernels["local_step"] else \
-        max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["share"])
-    pk = kernels[pinned_kernel]
-    step_bytes = sum(kernels[k]["algorithmic_bytes"] * kernels[k]["launches_per_step"] for k in kernels if "algorithmic_bytes" in kernels[k])
-    roofline = {"kernel": pinned_kernel, "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak_gbs,
-                "unit": "GB/s", "frac": pk["frac_of_peak"],
-                "traffic": pk.get("ncu_dram_traffic_bytes"), "algorithmic_bytes": pk["algorithmic_bytes"],
-                "traffic_source": ("profiles/%s (ncu --set full, dram__bytes_read+write per launch)" % ncu_file) if ncu else None,
-                "peak_source": peak_src, "share_of_step": pk["share"], "avg_launch_us": pk["avg_us"],
-                "step_aggregate": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
-                                   "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak_gbs,
-                                   "note": "algorithmic bytes of every fine-level kernel of one ARAP iteration / un-profiled time per iteration "
-                                           "(the coarse multigrid levels count as time but not as bytes)"}}
-    local = kernels.get("local_step", {})
-
-    cpu_baseline = None
-    parity_out = None
-    if parity is not None:
-        o, omesh, t_prep = run_cpu_oracle(P, F, idx, tgt, 0, real)
-        o.reset_timers()
-        t0 = time.perf_counter()
-        o.deform(parity_iters)
-        dt = time.perf_counter() - t0
-        tm = o.timers()
-        diag = float(np.linalg.norm(P.max(0) - P.min(0)))
-        cpu_e = o.energy()
-        parity_out = {"iterations": parity_iters,
-                      "max_dp_over_bbox_diag": float(np.abs(parity["gpu_positions"] - omesh.astype(np.float64)).max() / diag),
-                      "rel_energy_diff": abs(parity["gpu_energy"] - cpu_e) / cpu_e, "tolerance": {"dp": 1e-5, "dE": 1e-6},
-                      "note": "engine vs the CPU oracle after the cold start + %d warm-up + %d timed iterations: the state at the end of the timed window" % (args.warmup, args.steps)}
-        if f32 is not None:
-            f32["max_dp_over_bbox_diag_vs_fp64_oracle"] = float(np.abs(f32.pop("positions") - omesh.astype(np.float64)).max() / diag)
-            f32["rel_energy_diff_vs_fp64_oracle"] = abs(f32.pop("energy") - cpu_e) / cpu_e
-        cpu_baseline = {"value": parity_iters / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"full workload (V={V}), {parity_iters} ARAP iterations after prepare; prepare {t_prep:.1f} s "
-                                  f"(LDL^T factor, {o.factor_nnz()} nnz) excluded; per-iteration s: local {tm['local'] / parity_iters:.3f} "
-                                  f"rhs {tm['rhs'] / parity_iters:.3f} solve {tm['solve'] / parity_iters:.3f}; host cores available: {os.cpu_count()}"}
-    if f32 is not None:
-        f32.pop("positions", None)
-        f32.pop("energy", None)
-
-    working_set_mb = (V * (3 * 4 * s + 8) + nnz * (4 + s) + V * 4 + V * 4 * 24) / 1e6
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"icosphere nu={args.nu} V={V} 5% anchors + 1% handles (BASELINE.json configs[2])",
-                   "vertices": int(V), "faces": int(F.shape[0]), "nnz": nnz, "n_free": int(n_free),
-                   "sharding": "one independent deformation per GPU, no collective (the partitioned and batched workloads are in `multi_gpu`)" if world > 1 else "single GPU",
-                   "solver": ("warm-started single-reduction CG, smoothed-aggregation multigrid V(1,1) preconditioner, %d levels, operator complexity %.2f, CG loop %s"
-                              % (stats["mg_levels"], stats["mg_operator_complexity"],
-                                 "on the device (one CUDA graph per ARAP iteration)" if stats["cg_graph"] == 2 else "driven by the host (one CUDA graph per CG iteration)"))
-                   if stats["mg_levels"] else "warm-started Jacobi-PCG (matrix-free CSR SpMV, 3 RHS)", "stopping_rule": stopping_rule(args),
-                   "one_ring_kernels": ("neighbourhood staged through shared memory in tiles of 256 rows (largest tile halo %d)" % stats["tile_max_halo"])
-                   if stats["tile_max_halo"] > 0 else "gathers straight from global memory",
-                   "vertex_order": "renumbered internally in Morton patches" if stats["renumbered"] else "the caller's order",
-                   "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2, no explicit flush"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(V * 3 * s),
-                "call": "arap_deform(h, pinned_host_mesh, 1) on a prepared handle: 1 iteration + write-back of p' to the host mesh",
-                "h2d_note": "deform() reads the mesh only when a constraint changed (reference arap.h:102-107), so a steady-state step has no "
-                            "host input; the per-frame protocol WITH the upload is `frame`",
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "local_step": {"achieved_gbs": local.get("achieved_gbs"), "frac_of_measured_peak": local.get("frac_of_peak"),
-                       "frac_of_nominal_8TBs": (local.get("achieved_gbs") or 0) / 8000.0, "avg_us": local.get("avg_us")},
-        "kernels": kernels,
-        "kernels_note": "avg_us from a second pass of the same K steps with every launch bracketed by CUDA events (graphs off): ~1.5x slower than "
-                        "the timed pass overall and ~5 us too long per small kernel; shares agree with the ncu launch list in profiles/",
-        "cg": {"iterations_per_arap_iteration": window_cg, "kernel_launches_per_cg_iteration": stats["launches_per_cg_iteration"],
-               "last_relative_residual": stats["last_relative_residual"], "converged": bool(stats["last_converged"])},
-        "cold_start": {"what": "ARAP iterations 1..%d right after the handle move (the warm-up), one arap_iterate(1) each" % args.warmup,
-                       "cg_iterations": cold["cg_iterations"], "ms": cold["ms"]},
-        "prepare_ms": prepare_ms, "prepare_host_setup_ms": prepare_host_setup_ms, "prepare_device_setup_ms": prepare_device_setup_ms,
-        "frame": {"protocol": "setConstraint(handles) + deform(5) incl. the dirty rebuild: H2D rest pose, weights/CSR, 5 iterations, D2H (reference demo loop)",
-                  "ms": frame_ms, "h2d_bytes": int(V * 3 * s + 10 * (4 + 3 * 8)), "d2h_bytes": int(V * 3 * s),
-                  "iterations_per_s": 5.0 / (frame_ms * 1e-3)},
-        "profiled_pass_ms_per_step": ms_profiled / args.steps,
-        "f32": f32,
-        "cpu_baseline": cpu_baseline,
-        "parity": parity_out,
-    }
-    if multi is not None:
-        line["multi_gpu"] = multi
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     return 0
 
 

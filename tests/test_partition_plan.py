@@ -10,13 +10,18 @@ from mesh_deform_b200 import partition as PT
 from oracle.numpy_ref import cotan_weights
 
 
-@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_block_grid_shapes():
+    assert [PT.block_grid(n) for n in (1, 2, 3, 4, 6, 8)] == [(1, 1), (2, 1), (3, 1), (2, 2), (3, 2), (4, 2)]
+
+
+@pytest.mark.parametrize("owner_kind", ["strips", "blocks"])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
 @pytest.mark.parametrize("mesh", ["grid", "ico"])
-def test_partition_plans_are_consistent_and_spmv_matches(mesh, world):
+def test_partition_plans_are_consistent_and_spmv_matches(mesh, world, owner_kind):
     P, F = G.grid_plane(23, 17) if mesh == "grid" else G.icosphere(6)
     V = P.shape[0]
-    owner = PT.strip_owner(P, world)
-    assert np.bincount(owner, minlength=world).min() >= V // world - 1
+    owner = PT.strip_owner(P, world) if owner_kind == "strips" else PT.block_owner(P, world)
+    assert np.bincount(owner, minlength=world).min() >= V // world - world
     parts = [PT.build_local_part(F, owner, r, world) for r in range(world)]
     assert sum(p.n_owned for p in parts) == V
     assert np.array_equal(np.sort(np.concatenate([p.owned_global for p in parts])), np.arange(V))
