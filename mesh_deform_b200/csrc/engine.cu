@@ -776,7 +776,9 @@ public:
         tiles_built = true;
         use_tiles = false;
         const int R = n_rows;
-        if (getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) == 0) return ARAP_OK;
+        // OFF by default: measured at 1M vertices (profiles/r02_experiments.txt) the staged fp64 kernels are 24-31 % SLOWER than the
+        // direct gathers (CTA-wide stage / barrier / compute phases overlap worse than independent warps do), the fp32 ones equal.
+        if (!(getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) != 0)) return ARAP_OK;
         if (R < 2 * kTile || nnz <= 0) return ARAP_OK;
         n_tiles = (R + kTile - 1) / kTile;
         ARAP_CUDA(tile_halo.ensure((size_t)n_tiles * kTileHaloCap));
@@ -967,7 +969,7 @@ public:
                     if (rank_of[(size_t)a] / kTile != rank_of[(size_t)b] / kTile) ++cut_morton;
                 }
             const bool force = env && atoi(env) == 2;
-            const bool tiling = !(getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) == 0) && owned >= 2 * kTile;
+            const bool tiling = getenv("ARAP_TILES") && atoi(getenv("ARAP_TILES")) != 0 && owned >= 2 * kTile;
             const bool renumber = force || (tiling ? (double)cut_morton < 0.8 * (double)cut_user : (double)near_morton > 1.15 * (double)near_user);
             mg_visit_order.resize((size_t)V);
             for (int i = 0; i < V; ++i) mg_visit_order[(size_t)i] = i;
@@ -1292,6 +1294,9 @@ public:
         ARAP_CUDA(sums.ensure(4));
         ARAP_CUDA(gersh.ensure(1));
         ARAP_CUDA(cudaMemsetAsync(scalars.ptr, 0, 4 * sizeof(int), stream));
+        // the reductions below use the engine's per-block partial sums; V may be the GLOBAL mesh of a partitioned handle, larger
+        // than the local mesh the buffer was sized for
+        ARAP_CUDA(partials.ensure((size_t)(std::min(grid_for((size_t)V), sm_count * 4) + 1) * 8));
         // ---- level 0 as an explicit CSR
         std::unique_ptr<DevCsr> A(new DevCsr());
         ARAP_CUDA(len.ensure((size_t)V + 1));
@@ -1898,7 +1903,7 @@ public:
         tail_grid = false;
         const int L = (int)mg.size();
         const char *env_mode = getenv("ARAP_TAIL");
-        const std::string mode = env_mode ? env_mode : "grid";
+        const std::string mode = env_mode ? env_mode : "0";          // measured at 1M vertices: 105 us for the cooperative kernel vs ~55 us of graph-replayed launches
         if (L < 2 || mg_global || transport || mode == "0") return ARAP_OK;
         int t = 0;
         if (mode == "grid") {

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kBlock) init_state_kernel(int n, const int *__
 #define ARAP_LOCAL_MIN_BLOCKS 4
 #endif
 #ifndef ARAP_RHS_MIN_BLOCKS
-#define ARAP_RHS_MIN_BLOCKS 3
+#define ARAP_RHS_MIN_BLOCKS 2      /* 128 registers, no spills, 2 CTAs per SM: 60.9 us; 3 CTAs (80 registers, 164 B of spills): 65.9 us */
 #endif
 template <typename S> struct GatherChunk;
 template <> struct GatherChunk<float> { static constexpr int value = 6; };
