@@ -137,24 +137,34 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch
         import torch.distributed as dist_mod
-        torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+            dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        else:                       # CPU tests of the host logic (tests/test_bench_multi_gloo.py); bench.py itself needs GPUs
+            dist_mod.init_process_group(backend="gloo")
         dist = dist_mod
     return rank, world, local_rank, dist
+
+
+def _dev(local_rank):
+    """Tensor device of the collectives: the rank's GPU, or the CPU in the gloo tests of the host logic."""
+    import torch
+    return torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
 
 
 def barrier_and_sync(dist):
     import torch
     if dist is not None:
         dist.barrier()
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def max_over_ranks(dist, local_rank, x):
     if dist is None:
         return x
     import torch
-    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    t = torch.tensor([x], dtype=torch.float64, device=_dev(local_rank))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -341,14 +351,14 @@ def partitioned_arm(args):
 def _sync_ok(dist, local_rank, ok):
     """All ranks agree on whether an arm worked (an exception on one rank must not leave the others in a collective)."""
     import torch
-    t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=_dev(local_rank))
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return bool(t.item() > 0.5)
 
 
-def _nccl_id(dist, rank, capi):
+def _nccl_id(dist, rank, capi, local_rank=0):
     import torch
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    uid = torch.zeros(128, dtype=torch.uint8, device=_dev(local_rank))
     if rank == 0:
         uid.copy_(torch.from_numpy(capi.comm_unique_id()))
     dist.broadcast(uid, 0)
@@ -361,7 +371,7 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
     import torch
     from mesh_deform_b200 import capi
     kind = capi.TRANSPORT_PEER if transport == "peer" else capi.TRANSPORT_NCCL
-    part = capi.PartitionedDeformation(P, F, owner, rank, world, kind, _nccl_id(dist, rank, capi), np.float64, device=local_rank)
+    part = capi.PartitionedDeformation(P, F, owner, rank, world, kind, _nccl_id(dist, rank, capi, local_rank), np.float64, device=local_rank)
     part.setConstraints(idx, tgt)
     t0 = time.perf_counter()
     part.prepare()
@@ -376,7 +386,7 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
     stats = part.solver_stats()
     us_ex, us_ar = part.comm_benchmark(comm_rounds)
     us_ex, us_ar = max_over_ranks(dist, local_rank, us_ex), max_over_ranks(dist, local_rank, us_ar)
-    dev = torch.device("cuda", local_rank)
+    dev = _dev(local_rank)
     e = torch.tensor([part.local_energy()], dtype=torch.float64, device=dev)
     dist.all_reduce(e, op=dist.ReduceOp.SUM)
     halo = torch.tensor([float(part.part.n_local - part.part.n_owned)], dtype=torch.float64, device=dev)
