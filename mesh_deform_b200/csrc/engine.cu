@@ -1288,7 +1288,7 @@ public:
         const double theta2 = mo.theta * mo.theta;
         const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
         DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
-        DeviceBuffer<unsigned long long> m1, gersh;
+        DeviceBuffer<unsigned long long> m1, keys, gersh;
         DeviceBuffer<double> vx, vy, sums;
         ARAP_CUDA(scalars.ensure(4));        // [0] active rows, [1] newly elected roots, [2] still undecided, [3] accumulator overflow
         ARAP_CUDA(sums.ensure(4));
@@ -1356,6 +1356,7 @@ public:
                 ARAP_CUDA(agg.ensure((size_t)n));
                 ARAP_CUDA(status.ensure((size_t)n));
                 ARAP_CUDA(m1.ensure((size_t)n));
+                ARAP_CUDA(keys.ensure((size_t)n));
                 ARAP_CUDA(flag.ensure((size_t)n + 1));
                 ARAP_CUDA(root_id.ensure((size_t)n + 1));
                 ARAP_CUDA(joined.ensure((size_t)n));
@@ -1364,8 +1365,9 @@ public:
                 agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, agg.ptr, status.ptr);
                 for (int round = 0; round < 64; ++round) {
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
-                    agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, m1.ptr);
-                    agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, m1.ptr, status.ptr, scalars.ptr + 1);
+                    agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr);
+                    agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr);
+                    agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr, status.ptr, scalars.ptr + 1);
                     agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
                     agg_cover2_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, scalars.ptr + 2);
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 1, scalars.ptr + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -22,9 +22,15 @@ __device__ __forceinline__ unsigned hash_u32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-// key of a vertex in the root election: hash in the high bits (random-looking priorities give well spread roots), index in
-// the low bits (unique, so ties cannot happen). 0 = "not a candidate".
-__device__ __forceinline__ unsigned long long root_key(int i) { return ((unsigned long long)(hash_u32((unsigned)i) | 1u) << 32) | (unsigned)i; }
+// key of a vertex in the root election, largest wins: [number of strong neighbours already decided : 8][hash : 24][index : 32].
+// The index makes keys unique; the hash spreads the first round's roots; the count makes later rounds elect roots right at
+// the rim of what is already covered, the way the sequential greedy walk of the host version packs its aggregates (measured with
+// a numpy model of this election, CG iterations to 1e-8 on a 300 x 300 grid / an 81k icosphere: greedy 15 / 16, hash alone
+// 18 / 17, with the count 16 / 16 -- profiles/r02_experiments.txt). 0 = "not a candidate".
+__device__ __forceinline__ unsigned long long root_key(int i, int decided_neighbours) {
+    const unsigned long long c = (unsigned long long)(decided_neighbours > 255 ? 255 : decided_neighbours);
+    return (c << 56) | ((unsigned long long)((hash_u32((unsigned)i) & 0xffffffu) | 1u) << 32) | (unsigned)i;
+}
 
 // ---- level 0: L = D - W on the free rows as an explicit CSR (full vertex index space, constrained rows empty) ---------
 // pass 1 (fill == 0): row lengths; pass 2: entries sorted by column with the diagonal in place.
@@ -125,26 +131,44 @@ __global__ void __launch_bounds__(kBlock) agg_init_kernel(int n, const int *__re
     agg[i] = has ? kAggUnset : -1;
     status[i] = has ? 0 : 2;              // 0 undecided, 1 root, 2 out of the election
 }
-// m1[i] = largest key among the undecided vertices of the closed strong neighbourhood of i (0 if none)
+// this round's keys: undecided vertices only
+__global__ void __launch_bounds__(kBlock) agg_key_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                         const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                         const int *__restrict__ block, double theta2, const int *__restrict__ status,
+                                                         unsigned long long *__restrict__ key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k0 = 0ULL;
+    if (status[i] == 0) {
+        int decided = 0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] != 0) ++decided;
+        }
+        k0 = root_key(i, decided);
+    }
+    key[i] = k0;
+}
+// m1[i] = largest key in the closed strong neighbourhood of i (0 if none is undecided)
 __global__ void __launch_bounds__(kBlock) agg_max1_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                           const double *__restrict__ val, const double *__restrict__ inv_diag,
-                                                          const int *__restrict__ block, double theta2, const int *__restrict__ status,
+                                                          const int *__restrict__ block, double theta2, const unsigned long long *__restrict__ key,
                                                           unsigned long long *__restrict__ m1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned long long m = status[i] == 0 ? root_key(i) : 0ULL;
+    unsigned long long m = key[i];
     if (inv_diag[i] > 0)
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
             const int j = colidx[k];
-            if (is_strong(i, j, val[k], inv_diag, block, theta2) && status[j] == 0) { const unsigned long long kj = root_key(j); if (kj > m) m = kj; }
+            if (is_strong(i, j, val[k], inv_diag, block, theta2) && key[j] > m) m = key[j];
         }
     m1[i] = m;
 }
 // an undecided vertex whose key is the largest within distance 2 becomes a root
 __global__ void __launch_bounds__(kBlock) agg_elect_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                            const double *__restrict__ val, const double *__restrict__ inv_diag,
-                                                           const int *__restrict__ block, double theta2, const unsigned long long *__restrict__ m1,
-                                                           int *__restrict__ status, int *__restrict__ n_new) {
+                                                           const int *__restrict__ block, double theta2, const unsigned long long *__restrict__ key,
+                                                           const unsigned long long *__restrict__ m1, int *__restrict__ status, int *__restrict__ n_new) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || status[i] != 0) return;
     unsigned long long m = m1[i];
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(kBlock) agg_elect_kernel(int n, const int *__r
         const int j = colidx[k];
         if (is_strong(i, j, val[k], inv_diag, block, theta2) && m1[j] > m) m = m1[j];
     }
-    if (m == root_key(i)) { status[i] = 1; atomicAdd(n_new, 1); }
+    if (m == key[i]) { status[i] = 1; atomicAdd(n_new, 1); }
 }
 // after an election: neighbours of roots leave the election (status 3 = adjacent to a root), then their neighbours do (2)
 __global__ void __launch_bounds__(kBlock) agg_cover1_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
