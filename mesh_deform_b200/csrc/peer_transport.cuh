@@ -285,6 +285,10 @@ public:
     }
 
     bool capturable() const override { return true; }
+    // Large reductions (the right-hand side of the replicated multigrid levels, megabytes) go through the bootstrap transport's
+    // all-reduce when that is NCCL: every rank storing its whole vector into every other rank's mailbox would move world x the
+    // data a ring / tree all-reduce moves. NCCL opens its connections on first use, hence the warm-up before any graph capture.
+    bool needs_warm_up() const override { return !same_process; }
     int poll_error() override {
         if (error_flag && *error_flag) { error = "peer transport: timed out waiting for a neighbour's data"; return -1; }
         return 0;
@@ -464,6 +468,11 @@ private:
         if ((long long)n * world <= 2048) {
             peer_reduce_small_kernel<T><<<1, 256, 0, stream>>>(rd_dev + site, dev, error_flag);
             return cudaGetLastError() == cudaSuccess ? 0 : (error = "peer transport: launch failed", -1);
+        }
+        if (!same_process && (size_t)n * sizeof(T) >= (size_t)256 * 1024) {
+            const int rc = sizeof(T) == 8 ? boot->allreduce_sum(stream, site, (double *)dev, n) : boot->allreduce_sum_f32(stream, site, (float *)dev, n);
+            if (rc) error = boot->error;
+            return rc;
         }
         int pgrid = (int)(((long long)n * world + 4095) / 4096), wgrid = (n + 4095) / 4096;
         pgrid = pgrid < 1 ? 1 : (pgrid > 128 ? 128 : pgrid);
