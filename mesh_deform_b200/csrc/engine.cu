@@ -1401,18 +1401,40 @@ public:
                     ARAP_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(int) * ((size_t)n_agg + 1), stream));
                     transpose_fill_kernel<<<G, kBlock, 0, stream>>>(n, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, R.rowptr.ptr, cursor.ptr, R.colidx.ptr, R.val.ptr);
                     sort_rows_kernel<<<grid_for((size_t)n_agg), kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr);
-                    // ---- AP = A P ; A_c = R (A P)
-                    spgemm_rows_kernel<128><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, 0, len.ptr,
-                                                                      nullptr, nullptr, nullptr, scalars.ptr + 3);
-                    { int rc = csr_allocate(AP, n, n_agg, len.ptr); if (rc) return rc; }
-                    spgemm_rows_kernel<128><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, P.rowptr.ptr, P.colidx.ptr, P.val.ptr, 1, nullptr,
-                                                                      AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, scalars.ptr + 3);
-                    const int Gc = grid_for((size_t)n_agg);
-                    spgemm_rows_kernel<128><<<Gc, kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr, AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, 0, len.ptr,
-                                                                       nullptr, nullptr, nullptr, scalars.ptr + 3);
-                    { int rc = csr_allocate(*Ac, n_agg, n_agg, len.ptr); if (rc) return rc; }
-                    spgemm_rows_kernel<128><<<Gc, kBlock, 0, stream>>>(n_agg, R.rowptr.ptr, R.colidx.ptr, R.val.ptr, AP.rowptr.ptr, AP.colidx.ptr, AP.val.ptr, 1, nullptr,
-                                                                       Ac->rowptr.ptr, Ac->colidx.ptr, Ac->val.ptr, scalars.ptr + 3);
+                    // ---- AP = A P ; A_c = R (A P). Rows are accumulated in per-thread sorted arrays of 128 entries; a product whose rows
+                    // outgrow that (coarse operators of irregular meshes) is redone with 512, and only then is the host setup the fallback.
+                    auto product = [&](const DevCsr &X, const DevCsr &Y, DevCsr &Z) -> int {
+                        const int rows = X.n_rows, Gp = grid_for((size_t)rows);
+                        for (int attempt = 0; attempt < 2; ++attempt) {
+                            ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 3, 0, sizeof(int), stream));
+                            if (attempt == 0)
+                                spgemm_rows_kernel<128><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 0, len.ptr,
+                                                                                   nullptr, nullptr, nullptr, scalars.ptr + 3);
+                            else
+                                spgemm_rows_kernel<512><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 0, len.ptr,
+                                                                                   nullptr, nullptr, nullptr, scalars.ptr + 3);
+                            ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                            ARAP_CUDA(cudaStreamSynchronize(stream));
+                            if (h_scalars[3] != 0) continue;
+                            { int rc = csr_allocate(Z, rows, Y.n_cols, len.ptr); if (rc) return rc; }
+                            if (attempt == 0)
+                                spgemm_rows_kernel<128><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 1, nullptr,
+                                                                                   Z.rowptr.ptr, Z.colidx.ptr, Z.val.ptr, scalars.ptr + 3);
+                            else
+                                spgemm_rows_kernel<512><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 1, nullptr,
+                                                                                   Z.rowptr.ptr, Z.colidx.ptr, Z.val.ptr, scalars.ptr + 3);
+                            return ARAP_OK;
+                        }
+                        return ARAP_OK;                                  // h_scalars[3] != 0: the caller gives up on the device path
+                    };
+                    // the prolongator's own flag first (it shares scalars[3] with the products)
+                    ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    if (h_scalars[3] != 0) return ARAP_OK;
+                    { int rc = product(*A, P, AP); if (rc) return rc; }
+                    if (h_scalars[3] != 0) return ARAP_OK;
+                    { int rc = product(R, AP, *Ac); if (rc) return rc; }
+                    if (h_scalars[3] != 0) return ARAP_OK;
                     DeviceBuffer<int> block_c;
                     if (block) {
                         ARAP_CUDA(block_c.ensure((size_t)n_agg));
