@@ -29,11 +29,11 @@ except Exception as e:
 PY
 }
 if [ "$MODE" = "small" ] || [ "$MODE" = "both" ]; then
-  run small --part-nx 1000 --weak-verts-per-gpu 250000 --batch 512 --oracle-nx 300 --no-f32 --nu 100
+  run small --part-nx 1000 --weak-verts-per-gpu 250000 --batch 512 --oracle-nx 300 --no-f32
 fi
 if [ "$MODE" = "full" ] || [ "$MODE" = "both" ]; then
   run full
 fi
 if [ "$MODE" = "peer" ]; then
-  run peer --transport peer --part-nx 2000 --weak-verts-per-gpu 1000000 --batch 512 --oracle-nx 300 --no-f32 --nu 100
+  run peer --transport peer --part-nx 2000 --weak-verts-per-gpu 1000000 --batch 512 --oracle-nx 300 --no-f32
 fi
