@@ -1287,6 +1287,7 @@ public:
         levels.clear();
         const double theta2 = mo.theta * mo.theta;
         const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
+        bool sweep_keys = false;
         DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
         DeviceBuffer<unsigned long long> m1, keys, gersh;
         DeviceBuffer<double> vx, vy, sums;
@@ -1363,9 +1364,32 @@ public:
                 const int G = grid_for((size_t)n);
                 const double *idg = d->inv_diag.ptr;
                 agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, agg.ptr, status.ptr);
-                for (int round = 0; round < 64; ++round) {
+                // election keys (agg_key_kernel): ordered sweeps for a quad-like strength graph, rim growth from sparse seeds otherwise;
+                // decided once, on the finest level (ARAP_MG_AGG_KEY=sweep|rim overrides)
+                if (l == 0) {
+                    ARAP_CUDA(cudaMemsetAsync(gersh.ptr, 0, sizeof(unsigned long long), stream));
+                    agg_strong_count_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, gersh.ptr);
+                    unsigned long long strong_total = 0;
+                    ARAP_CUDA(cudaMemcpyAsync(&strong_total, gersh.ptr, sizeof(strong_total), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    const double mean_strong = active > 0 ? (double)strong_total / active : 0.0;
+                    const char *kenv = getenv("ARAP_MG_AGG_KEY");
+                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : mean_strong <= 4.5;
+                    if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s keys\n", mean_strong, sweep_keys ? "sweep" : "rim-growth");
+                }
+                // rim growth: 1 vertex in 2^bits is a seed (ARAP_MG_AGG_SEED_BITS, 0 = every vertex; small levels still get a handful);
+                // where a round elects nothing although vertices remain (no seed in that component), the seed set is made 8x denser
+                int seed_bits = getenv("ARAP_MG_AGG_SEED_BITS") ? atoi(getenv("ARAP_MG_AGG_SEED_BITS")) : 12;
+                int log2n = 0;
+                while ((2 << log2n) <= active) ++log2n;
+                seed_bits = std::max(0, std::min(std::min(23, seed_bits), log2n - 3));
+                const int sweep_shift = sweep_keys ? 6 : 0;
+                int rounds_used = 0;
+                for (int round = 0; round < 8192; ++round) {
+                    ++rounds_used;
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
-                    agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr);
+                    agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr,
+                                                             (1u << seed_bits) - 1u, sweep_shift);
                     agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr);
                     agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr, status.ptr, scalars.ptr + 1);
                     agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
@@ -1373,6 +1397,7 @@ public:
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 1, scalars.ptr + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
                     ARAP_CUDA(cudaStreamSynchronize(stream));
                     if (h_scalars[2] == 0) break;
+                    if (h_scalars[1] == 0) seed_bits = std::max(0, seed_bits - 3);
                 }
                 agg_root_flag_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, flag.ptr);
                 { int rc = exclusive_scan(flag.ptr, n, root_id.ptr); if (rc) return rc; }
@@ -1444,7 +1469,7 @@ public:
                     ARAP_CUDA(cudaStreamSynchronize(stream));       // AP dies at scope exit
                     ARAP_CUDA(cudaGetLastError());
                     if (h_scalars[3] != 0) return ARAP_OK;             // a row outgrew its accumulator: the host setup handles it
-                    if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz) -> %d aggregates, omega %.4f\n", l, n, active, A->nnz, n_agg, d->omega);
+                    if (timing) std::fprintf(stderr, "[mg device setup] level %d: %d rows (%d active, %d nnz) -> %d aggregates in %d rounds, omega %.4f\n", l, n, active, A->nnz, n_agg, rounds_used, d->omega);
                     d->A = std::move(A);
                     levels.push_back(std::move(d));
                     A = std::move(Ac);
@@ -1585,6 +1610,9 @@ public:
         std::vector<float> fscratch;
         for (size_t l = 0; l < H.levels.size(); ++l) {
             const MgLevelHost &hl = H.levels[l];
+            if (getenv("ARAP_MG_TIMING"))
+                std::fprintf(stderr, "[mg host setup] level %zu: %d rows (%zu nnz) -> %d aggregates, omega %.4f\n", l, hl.A.n_rows,
+                             hl.A.colidx.size(), hl.P.n_cols, hl.omega);
             std::unique_ptr<MgLevelDev> d(new MgLevelDev());
             d->n = hl.A.n_rows;
             d->omega = hl.omega;

@@ -30,8 +30,10 @@ print(json.dumps({"mesh": sys.argv[1], "V": int(P.shape[0]), "levels": s["mg_lev
 ''' % ROOT
 
 for mesh in sys.argv[1:] or ["grid:1000", "ico:316"]:
-    for dev in ("1", "0"):
+    for dev in (("1",) if os.environ.get("COMPARE_DEVICE_ONLY") else ("1", "0")):
         env = dict(os.environ, ARAP_MG_DEVICE_SETUP=dev)
         out = subprocess.run([sys.executable, "-c", CHILD, mesh], env=env, capture_output=True, text=True)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")]
         print("device" if dev == "1" else "host  ", line[0] if line else out.stderr[-500:], flush=True)
+        if os.environ.get("ARAP_MG_TIMING"):
+            print("".join(l + "\n" for l in out.stderr.splitlines() if "] level" in l), end="", flush=True)
