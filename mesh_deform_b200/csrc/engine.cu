@@ -1455,11 +1455,15 @@ public:
                     // the prolongator's own flag first (it shares scalars[3] with the products)
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     ARAP_CUDA(cudaStreamSynchronize(stream));
-                    if (h_scalars[3] != 0) return ARAP_OK;
+                    auto declined = [&](const char *what) {
+                        if (timing) std::fprintf(stderr, "[mg device setup] level %d (%d rows, %d nnz): a row of %s outgrew its accumulator, host setup instead\n", l, n, A->nnz, what);
+                        return ARAP_OK;
+                    };
+                    if (h_scalars[3] != 0) return declined("P");
                     { int rc = product(*A, P, AP); if (rc) return rc; }
-                    if (h_scalars[3] != 0) return ARAP_OK;
+                    if (h_scalars[3] != 0) return declined("A P");
                     { int rc = product(R, AP, *Ac); if (rc) return rc; }
-                    if (h_scalars[3] != 0) return ARAP_OK;
+                    if (h_scalars[3] != 0) return declined("R A P");
                     DeviceBuffer<int> block_c;
                     if (block) {
                         ARAP_CUDA(block_c.ensure((size_t)n_agg));

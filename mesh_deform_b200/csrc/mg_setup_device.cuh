@@ -296,7 +296,7 @@ struct RowAcc {
 };
 
 // P = (I - omega D^-1 A) T, T piecewise constant over the aggregates. fill == 0: row lengths.
-constexpr int kCapP = 24;
+constexpr int kCapP = 64;
 __global__ void __launch_bounds__(kBlock) prolongator_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                              const double *__restrict__ val, const double *__restrict__ inv_diag,
                                                              const int *__restrict__ agg, double omega, int fill, int *__restrict__ out_len,

@@ -37,3 +37,7 @@ fi
 if [ "$MODE" = "peer" ]; then
   run peer --transport peer --part-nx 2000 --weak-verts-per-gpu 1000000 --batch 512 --oracle-nx 300 --no-f32
 fi
+if [ "$MODE" = "cmp" ]; then     # the two transports on the same mid-size workloads
+  run ncclmid --transport nccl --part-nx 2000 --weak-verts-per-gpu 1000000 --batch 512 --oracle-nx 300 --no-f32 --no-cpu-baseline
+  run peer --transport peer --part-nx 2000 --weak-verts-per-gpu 1000000 --batch 512 --oracle-nx 300 --no-f32 --no-cpu-baseline
+fi
