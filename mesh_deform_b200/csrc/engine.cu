@@ -1281,13 +1281,16 @@ public:
     template <typename W>
     int build_hierarchy_device(int V, const int *d_rowptr, const int *d_colidx, const W *d_weight, const unsigned char *d_is_free,
                                const int *block0, const MgSetupOptions &mo, std::vector<std::unique_ptr<DevLevel>> &levels,
-                               double *operator_complexity, bool *built) {
+                               double *operator_complexity, bool *built, const void *pos_src = nullptr, int pos_scalar_bytes = 8,
+                               int pos_stride = 3) {
         using namespace mgdev;
         *built = false;
         levels.clear();
         const double theta2 = mo.theta * mo.theta;
         const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
         bool sweep_keys = false;
+        DeviceBuffer<double> pos, pos_next, length_total;      // sweep keys: where the level's rows sit, the size of a sweep cell
+        double cell = 0.0;
         DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
         DeviceBuffer<unsigned long long> m1, keys, gersh;
         DeviceBuffer<double> vx, vy, sums;
@@ -1367,15 +1370,29 @@ public:
                 // election keys (agg_key_kernel): ordered sweeps for a quad-like strength graph, rim growth from sparse seeds otherwise;
                 // decided once, on the finest level (ARAP_MG_AGG_KEY=sweep|rim overrides)
                 if (l == 0) {
+                    if (pos_src && !(getenv("ARAP_MG_SWEEP_CELLS") && atoi(getenv("ARAP_MG_SWEEP_CELLS")) == 0)) {
+                        ARAP_CUDA(pos.ensure(3 * (size_t)n));
+                        pos_gather_kernel<<<G, kBlock, 0, stream>>>(n, pos_src, pos_scalar_bytes, pos_stride, pos.ptr);
+                    }
+                    ARAP_CUDA(length_total.ensure(1));
+                    ARAP_CUDA(cudaMemsetAsync(length_total.ptr, 0, sizeof(double), stream));
                     ARAP_CUDA(cudaMemsetAsync(gersh.ptr, 0, sizeof(unsigned long long), stream));
-                    agg_strong_count_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, gersh.ptr);
+                    agg_strong_count_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, pos.ptr, gersh.ptr,
+                                                                      length_total.ptr);
                     unsigned long long strong_total = 0;
+                    double h_length = 0.0;
                     ARAP_CUDA(cudaMemcpyAsync(&strong_total, gersh.ptr, sizeof(strong_total), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaMemcpyAsync(&h_length, length_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
                     ARAP_CUDA(cudaStreamSynchronize(stream));
                     const double mean_strong = active > 0 ? (double)strong_total / active : 0.0;
                     const char *kenv = getenv("ARAP_MG_AGG_KEY");
-                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : mean_strong <= 4.5;
-                    if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s keys\n", mean_strong, sweep_keys ? "sweep" : "rim-growth");
+                    // (aggregates confined to partition blocks: the sweeps lose a whole CG iteration to the seam -- 2000^2 plane in 2 blocks
+                    //  6.35-7.15 against 5.45 unconfined -- rim growth packs against the seam and loses nothing: 6.05-6.1 either way)
+                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : (mean_strong <= 4.5 && block == nullptr);
+                    cell = strong_total > 0 ? 8.0 * h_length / (double)strong_total : 0.0;        // 8 mean edges: ~64 rows of a surface per cell
+                    if (!(cell > 0.0) || !sweep_keys) pos.release();
+                    if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s keys%s\n", mean_strong, sweep_keys ? "sweep" : "rim-growth",
+                                             sweep_keys ? (pos.ptr ? " over spatial cells" : " over runs of 64 rows") : "");
                 }
                 // rim growth: 1 vertex in 2^bits is a seed (ARAP_MG_AGG_SEED_BITS, 0 = every vertex; small levels still get a handful);
                 // where a round elects nothing although vertices remain (no seed in that component), the seed set is made 8x denser
@@ -1383,13 +1400,12 @@ public:
                 int log2n = 0;
                 while ((2 << log2n) <= active) ++log2n;
                 seed_bits = std::max(0, std::min(std::min(23, seed_bits), log2n - 3));
-                const int sweep_shift = sweep_keys ? 6 : 0;
                 int rounds_used = 0;
                 for (int round = 0; round < 8192; ++round) {
                     ++rounds_used;
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
                     agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr,
-                                                             (1u << seed_bits) - 1u, sweep_shift);
+                                                             (1u << seed_bits) - 1u, sweep_keys ? 1 : 0, pos.ptr, cell > 0.0 ? 1.0 / cell : 0.0);
                     agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr);
                     agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr, status.ptr, scalars.ptr + 1);
                     agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
@@ -1469,6 +1485,11 @@ public:
                         ARAP_CUDA(block_c.ensure((size_t)n_agg));
                         agg_block_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, root_id.ptr, block, block_c.ptr);
                     }
+                    if (pos.ptr) {                                   // sweep cells of the next level: ~64 of ITS rows each
+                        ARAP_CUDA(pos_next.ensure(3 * (size_t)n_agg));
+                        pos_coarse_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, root_id.ptr, pos.ptr, pos_next.ptr);
+                        cell *= std::sqrt((double)std::max(1, active) / (double)n_agg);
+                    }
                     ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     ARAP_CUDA(cudaStreamSynchronize(stream));       // AP dies at scope exit
                     ARAP_CUDA(cudaGetLastError());
@@ -1477,6 +1498,7 @@ public:
                     d->A = std::move(A);
                     levels.push_back(std::move(d));
                     A = std::move(Ac);
+                    if (pos.ptr) { std::swap(pos.ptr, pos_next.ptr); std::swap(pos.count, pos_next.count); }
                     if (block) {
                         // the next level copies its block array out of this temporary at the top of the loop; keep it alive there
                         levels.back()->block_next.ptr = block_c.ptr; levels.back()->block_next.count = block_c.count;
@@ -1526,7 +1548,13 @@ public:
         std::vector<std::unique_ptr<DevLevel>> dl;
         double complexity = 0;
         bool ok = false;
-        { int rc = build_hierarchy_device<S>(n_vertices, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, nullptr, mo, dl, &complexity, &ok); if (rc) return rc; }
+        DeviceBuffer<int> fake_block;
+        if (getenv("ARAP_MG_FAKE_BLOCKS") && atoi(getenv("ARAP_MG_FAKE_BLOCKS")) > 1) {
+            ARAP_CUDA(fake_block.ensure((size_t)n_vertices));
+            mgdev::fake_block_kernel<<<grid_for((size_t)n_vertices), kBlock, 0, stream>>>(n_vertices, atoi(getenv("ARAP_MG_FAKE_BLOCKS")), fake_block.ptr);
+        }
+        { int rc = build_hierarchy_device<S>(n_vertices, hot_rowptr.ptr, hot_colidx.ptr, hot_weight.ptr, free_mask.ptr, fake_block.ptr, mo, dl, &complexity, &ok,
+                                                 rest4.ptr, (int)sizeof(S), 4); if (rc) return rc; }
         if (!ok) return ARAP_OK;
         std::vector<std::unique_ptr<MgLevelDev>> levels;
         const size_t L = dl.size();
@@ -1774,7 +1802,8 @@ public:
         std::vector<std::unique_ptr<DevLevel>> dl;
         double complexity = 0;
         bool ok = false;
-        { int rc = build_hierarchy_device<double>(Vg, d_rowptr.ptr, d_colidx.ptr, d_weight.ptr, d_free.ptr, d_owner.ptr, mo, dl, &complexity, &ok); if (rc) return rc; }
+        { int rc = build_hierarchy_device<double>(Vg, d_rowptr.ptr, d_colidx.ptr, d_weight.ptr, d_free.ptr, d_owner.ptr, mo, dl, &complexity, &ok,
+                                                      d_rest.ptr, 8, 3); if (rc) return rc; }
         if (!ok) return ARAP_OK;
         // download: mg_slice_hierarchy works on host matrices
         H.levels.clear();

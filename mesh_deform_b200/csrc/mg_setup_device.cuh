@@ -132,37 +132,88 @@ __global__ void __launch_bounds__(kBlock) agg_init_kernel(int n, const int *__re
     status[i] = has ? 0 : 2;              // 0 undecided, 1 root, 2 out of the election
 }
 // number of strong connections of the level (summed over the rows): its mean tells a quad-like strength graph (a plane of right
-// triangles: the diagonals carry cot(90 deg) = 0) from a triangle-like one, which take different election keys (agg_key_kernel)
+// triangles: the diagonals carry cot(90 deg) = 0) from a triangle-like one, which take different election keys (agg_key_kernel).
+// With positions (3 doubles per row) also the summed length of those connections: the mean edge sizes the sweep cells.
 __global__ void __launch_bounds__(kBlock) agg_strong_count_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                   const double *__restrict__ val, const double *__restrict__ inv_diag,
-                                                                  const int *__restrict__ block, double theta2, unsigned long long *__restrict__ total) {
+                                                                  const int *__restrict__ block, double theta2, const double *__restrict__ pos,
+                                                                  unsigned long long *__restrict__ total, double *__restrict__ length_total) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
+    double len = 0.0;
     if (i < n && inv_diag[i] > 0)
-        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) cnt += is_strong(i, colidx[k], val[k], inv_diag, block, theta2) ? 1 : 0;
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            if (!is_strong(i, j, val[k], inv_diag, block, theta2)) continue;
+            ++cnt;
+            if (pos) {
+                const double dx = pos[3 * (size_t)i] - pos[3 * (size_t)j], dy = pos[3 * (size_t)i + 1] - pos[3 * (size_t)j + 1],
+                             dz = pos[3 * (size_t)i + 2] - pos[3 * (size_t)j + 2];
+                len += sqrt(dx * dx + dy * dy + dz * dz);
+            }
+        }
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); len += __shfl_down_sync(0xffffffffu, len, o); }
+    if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(total, (unsigned long long)cnt); if (pos) atomicAdd(length_total, len); }
+}
+// debugging aid (ARAP_MG_FAKE_BLOCKS=k): k artificial partition blocks of consecutive rows for an unpartitioned solver
+__global__ void __launch_bounds__(kBlock) fake_block_kernel(int n, int k, int *__restrict__ block) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) block[i] = (int)((long long)i * k / n);
+}
+// positions of the finest level as 3 doubles per row, from the engine's own arrays (scalar type and stride vary)
+__global__ void __launch_bounds__(kBlock) pos_gather_kernel(int n, const void *__restrict__ src, int scalar_bytes, int stride, double *__restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < 3; ++c)
+        pos[3 * (size_t)i + c] = scalar_bytes == 4 ? (double)((const float *)src)[(size_t)i * stride + c] : ((const double *)src)[(size_t)i * stride + c];
+}
+// a coarse row sits where the root of its aggregate does
+__global__ void __launch_bounds__(kBlock) pos_coarse_kernel(int n, const int *__restrict__ status, const int *__restrict__ root_id,
+                                                            const double *__restrict__ pos, double *__restrict__ pos_c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] != 1) return;
+    const size_t a = (size_t)root_id[i];
+    pos_c[3 * a] = pos[3 * (size_t)i]; pos_c[3 * a + 1] = pos[3 * (size_t)i + 1]; pos_c[3 * a + 2] = pos[3 * (size_t)i + 2];
+}
+// sweep key of row i: rows of one CELL (a cube of 1 / inv_cell, about 8 mean edges: ~64 rows of a surface mesh) share a hashed
+// priority, inside the cell the Z-curve position on a 16^3 sub-grid decides, then the lower index. Without positions the cells
+// are runs of 64 consecutive rows (compact only if the numbering is).
+__device__ __forceinline__ unsigned long long sweep_key(int i, const double *__restrict__ pos, double inv_cell) {
+    if (!pos)
+        return (1ULL << 63) | ((unsigned long long)(hash_u32((unsigned)(i >> 6)) & 0xffffffu) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    unsigned cell = 0x9e3779b9u, sub = 0u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double x = pos[3 * (size_t)i + c] * inv_cell, fx = floor(x);
+        cell = hash_u32(cell ^ (unsigned)(long long)fx);
+        unsigned q = (unsigned)((x - fx) * 16.0) & 15u;                  // 4 bits of this axis, spread to every third bit
+        q = (q | (q << 4)) & 0x0c3u;
+        q = (q | (q << 2)) & 0x249u;
+        sub |= q << c;
+    }
+    return (1ULL << 63) | ((unsigned long long)(cell & 0x7ffffu) << 44) | ((unsigned long long)(0xfffu - sub) << 32) |
+           (unsigned long long)(0xffffffffu - (unsigned)i);
 }
 // this round's keys, in one of two forms (0 = "not a candidate"):
 //  * rim growth (sweep_shift == 0): candidates are the undecided vertices on the rim of what is already decided, plus a sparse set
 //    of seeds (hash & seed_mask == 0) that start the growth, ordered by root_key(): aggregates pack tightly, ring after ring,
 //    around few centres instead of around the ~n/13 random roots a first round open to every vertex elects;
-//  * ordered sweeps (sweep_shift > 0): every undecided vertex is a candidate; chunks of 2^sweep_shift consecutive rows take
-//    hashed priorities and inside a chunk the lower index wins, so each chunk is swept in index order the way the sequential
-//    greedy pass of the host setup sweeps the whole level, and the aggregates come out as regular as the mesh numbering.
+//  * ordered sweeps (sweep != 0): every undecided vertex is a candidate, keyed by sweep_key(): compact cells of ~64 rows take
+//    hashed priorities and inside a cell the order along a Z-curve decides, so every cell is swept in order the way the sequential
+//    greedy pass of the host setup sweeps the whole level in Morton order, and the aggregates come out as a regular pattern.
 // Measured, CG iterations per ARAP iteration (profiles/r02_experiments.txt): 1M icosphere 8.7 hashed keys / 8.7 host greedy /
 // 7.4 rim growth / 9.8 sweeps; 2000 x 2000 plane (4-neighbour strength graph) 6.5 hashed / 5.35 host greedy / 6.1 rim / 5.4 sweeps.
 __global__ void __launch_bounds__(kBlock) agg_key_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                          const double *__restrict__ val, const double *__restrict__ inv_diag,
                                                          const int *__restrict__ block, double theta2, const int *__restrict__ status,
-                                                         unsigned long long *__restrict__ key, unsigned seed_mask, int sweep_shift) {
+                                                         unsigned long long *__restrict__ key, unsigned seed_mask, int sweep,
+                                                         const double *__restrict__ pos, double inv_cell) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long k0 = 0ULL;
     if (status[i] == 0) {
-        if (sweep_shift > 0) {
-            k0 = (1ULL << 63) | ((unsigned long long)(hash_u32((unsigned)(i >> sweep_shift)) & 0xffffffu) << 32) |
-                 (unsigned long long)(0xffffffffu - (unsigned)i);
+        if (sweep) {
+            k0 = sweep_key(i, pos, inv_cell);
         } else {
             int decided = 0;
             for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {

@@ -1,8 +1,10 @@
-# experiment: where do the extra CG iterations of the partitioned mode come from (in-process partitions on one GPU)
-for nx in 1000 2000; do
-echo "== nx $nx default";                 python tests/tools/gpu_partition_iterations.py $nx 2>&1 | tail -2
-echo "== nx $nx replicate all below L0";  PARTITION_ONLY=1 ARAP_MG_REPLICATE_ROWS=100000000 python tests/tools/gpu_partition_iterations.py $nx 2>&1 | tail -1
-echo "== nx $nx replicate none";          PARTITION_ONLY=1 ARAP_MG_REPLICATE_ROWS=0 python tests/tools/gpu_partition_iterations.py $nx 2>&1 | tail -1
-echo "== nx $nx host setup";              ARAP_MG_DEVICE_SETUP=0 python tests/tools/gpu_partition_iterations.py $nx 2>&1 | tail -2
-echo "== nx $nx rim keys";                ARAP_MG_AGG_KEY=rim python tests/tools/gpu_partition_iterations.py $nx 2>&1 | tail -2
-done
+# experiment: what costs the partitioned hierarchy its quality -- numbering or the block constraint
+T="python tests/tools/gpu_setup_compare.py grid:2000"
+export COMPARE_DEVICE_ONLY=1
+echo "== single default";             $T 2>&1 | grep -E "^device"
+echo "== single, no renumbering";     ARAP_REORDER=0 $T 2>&1 | grep -E "^device"
+echo "== single, no renumbering, index runs"; ARAP_REORDER=0 ARAP_MG_SWEEP_CELLS=0 $T 2>&1 | grep -E "^device"
+echo "== single, 2 fake blocks";      ARAP_MG_FAKE_BLOCKS=2 $T 2>&1 | grep -E "^device"
+echo "== single, 2 fake blocks, no renumbering"; ARAP_REORDER=0 ARAP_MG_FAKE_BLOCKS=2 $T 2>&1 | grep -E "^device"
+echo "== single, 2 fake blocks, rim"; ARAP_MG_AGG_KEY=rim ARAP_MG_FAKE_BLOCKS=2 $T 2>&1 | grep -E "^device"
+echo "== single, 2 fake blocks, host"; COMPARE_DEVICE_ONLY= ARAP_MG_FAKE_BLOCKS=2 $T 2>&1 | grep -E "^host"
