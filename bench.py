@@ -365,7 +365,7 @@ def _nccl_id(dist, rank, capi, local_rank=0):
     return uid.cpu().numpy()
 
 
-def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup, steps, transport, gather=True, comm_rounds=200):
+def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup, steps, transport, gather=True, comm_rounds=200, profile_steps=3):
     """One nx x nz grid over `world` partitions: W warm-up + K timed ARAP iterations. Returns a dict (every rank; the gathered
     positions only on rank 0)."""
     import torch
@@ -400,6 +400,28 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
         if rank == 0:
             positions = full.cpu().numpy()
         del full
+    # where one CG iteration goes: a few more ARAP iterations launch by launch, every kernel, halo exchange and all-reduce bracketed by
+    # CUDA events (rank 0's view; a rank that waits for a neighbour inside an exchange books the wait there -- that IS the cost)
+    phases = None
+    if profile_steps > 0:
+        its0 = part.solver_stats()["cg_iterations_total"]
+        part.profile_enable(True)
+        part.profile_reset()
+        part.arap.timer_start()
+        part.iterate(profile_steps)
+        ms_prof = part.arap.timer_stop()
+        prof = part.profile()
+        part.profile_enable(False)
+        cg_its = max(1, part.solver_stats()["cg_iterations_total"] - its0)
+        groups = {"halo_exchange": ("halo_exchange",), "allreduce_cg_scalars": ("allreduce_scalars", "cg_finalize"), "allreduce_replicated_level_rhs": ("allreduce_level",),
+                  "local_step + rhs_residual + apply_update": ("local_step", "local_step_redo", "rhs_residual", "apply_update"),
+                  "cg_spmv + cg_update": ("cg_spmv", "cg_update_mg"), "multigrid_fine_level": ("mg_fine_residual", "mg_fine_postsmooth"),
+                  "multigrid_coarse_levels": ("mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add", "mg_csr_postsmooth", "mg_dense_solve", "mg_tail")}
+        phases = {g: round(1e3 * sum(prof.get(n, {}).get("ms", 0.0) for n in names) / cg_its, 1) for g, names in groups.items()}
+        phases["sum_of_phases_us"] = round(sum(phases.values()), 1)
+        phases["launch_by_launch_us_per_cg_iteration"] = round(1e3 * ms_prof / cg_its, 1)
+        phases["launches_per_cg_iteration"] = round(sum(v["launches"] for v in prof.values()) / cg_its, 1)
+        barrier_and_sync(dist)
     res = {"iterations_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "energy": float(e.item()),
            "cg_iterations_per_step": stats["cg_iterations_total"] / max(1, stats["global_steps"]),
            "exchanges_per_cg_iteration": stats["comm_exchanges_per_cg_iteration"],
@@ -407,8 +429,8 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
            "halo_bytes_sent_per_cg_iteration_rank0": stats["comm_halo_bytes_per_cg_iteration"],
            "halo_vertices_max": int(halo.item()), "us_per_exchange": us_ex, "us_per_allreduce": us_ar,
            "mg_levels": stats["mg_levels"], "mg_global": bool(stats["mg_global"]), "cg_graph": stats["cg_graph"],
-           "prepare_s": prepare_s, "hierarchy_setup_host_ms": stats["setup_host_ms"], "transport": transport,
-           "positions": positions}
+           "prepare_s": prepare_s, "hierarchy_setup_host_ms": stats["setup_host_ms"], "hierarchy_setup_device_ms": stats["setup_device_ms"],
+           "transport": transport, "us_per_cg_iteration_by_phase_rank0": phases, "positions": positions}
     del part
     return res
 

@@ -167,7 +167,8 @@ enum {
     ARAP_K_CG_UPDATE, ARAP_K_CG_DIRECTION, ARAP_K_APPLY, ARAP_K_ENERGY, ARAP_K_MISC,
     ARAP_K_MG_FINE_RESIDUAL, ARAP_K_MG_FINE_POSTSMOOTH, ARAP_K_MG_CSR_RESIDUAL, ARAP_K_MG_RESTRICT, ARAP_K_MG_PROLONG,
     ARAP_K_MG_CSR_POSTSMOOTH, ARAP_K_MG_DENSE_SOLVE, ARAP_K_CG_UPDATE_MG, ARAP_K_CG_DIRECTION_MG, ARAP_K_CG_DOT,
-    ARAP_K_HALO_PACK, ARAP_K_CG_FINALIZE, ARAP_K_LOCAL_STEP_REDO, ARAP_K_MG_TAIL, ARAP_K_COUNT_MAX = 32
+    ARAP_K_HALO_PACK, ARAP_K_CG_FINALIZE, ARAP_K_LOCAL_STEP_REDO, ARAP_K_MG_TAIL, ARAP_K_ALLREDUCE_SCALARS, ARAP_K_ALLREDUCE_LEVEL,
+    ARAP_K_COUNT_MAX = 32
 };
 typedef struct arap_profile {
     int64_t launches[ARAP_K_COUNT_MAX];

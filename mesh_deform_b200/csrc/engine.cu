@@ -44,7 +44,8 @@ static const char *kKernelNames[ARAP_K_COUNT_MAX] = {
     "init_state", "diagonal", "local_step", "rhs_residual", "cg_spmv",
     "cg_update", "cg_direction", "apply_update", "energy", "misc",
     "mg_fine_residual", "mg_fine_postsmooth", "mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add",
-    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_pack", "cg_finalize", "local_step_redo", "mg_tail"};
+    "mg_csr_postsmooth", "mg_dense_solve", "cg_update_mg", "cg_direction_mg", "cg_dot", "halo_exchange", "cg_finalize", "local_step_redo", "mg_tail",
+    "allreduce_scalars", "allreduce_level"};
 
 static thread_local std::string g_create_error;
 
@@ -1160,7 +1161,10 @@ public:
         double *red = (double *)((char *)cg.ptr + offsetof(CgScalars, red));
         (void)n_values;             // always the whole red[8] block: one site layout for every stage
         if (comm_counting) comm_allreduces += 1;
-        if (transport->allreduce_sum(stream, SITE_RED_BASE + stage, red, 8)) return fail(ARAP_ERR_CUDA, transport->error);
+        begin_launch(ARAP_K_ALLREDUCE_SCALARS);
+        const int rc_red = transport->allreduce_sum(stream, SITE_RED_BASE + stage, red, 8);
+        end_launch();
+        if (rc_red) return fail(ARAP_ERR_CUDA, transport->error);
         pdl_next_plain = true;
         begin_launch(ARAP_K_CG_FINALIZE);
         cg_finalize_kernel<<<1, 1, 0, stream>>>(cg.ptr, stage);
@@ -1941,7 +1945,10 @@ public:
                 // into the replicated part: every rank restricted the rows it owns (zeros elsewhere); sum them, then redo the
                 // pre-smoothing x = omega D^-1 b with the complete right-hand side
                 if (comm_counting) comm_allreduces += 1;
-                if (transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)c.b.ptr, 4 * c.n)) return fail(ARAP_ERR_CUDA, transport->error);
+                begin_launch(ARAP_K_ALLREDUCE_LEVEL);
+                const int rc_red = transport->allreduce_sum_f32(stream, SITE_COARSE_B, (float *)c.b.ptr, 4 * c.n);
+                end_launch();
+                if (rc_red) return fail(ARAP_ERR_CUDA, transport->error);
                 pdl_next_plain = true;
                 if (l + 1 < L - 1)
                     LAUNCH_PDL(ARAP_K_MG_RESTRICT, mg_jacobi_kernel, grid_for((size_t)c.n), c.n, c.inv_diag.ptr, (float)c.omega, c.b.ptr, c.x.ptr);

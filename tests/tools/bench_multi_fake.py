@@ -77,10 +77,19 @@ class FakePartitioned:
     def solver_stats(self):
         return {"cg_iterations_total": 9 * self.its, "global_steps": max(1, self.its), "comm_exchanges_per_cg_iteration": 8,
                 "comm_allreduces_per_cg_iteration": 2, "comm_halo_bytes_per_cg_iteration": 1234, "mg_levels": 4, "mg_global": 1, "cg_graph": 1,
-                "setup_host_ms": 0.0}
+                "setup_host_ms": 0.0, "setup_device_ms": 1.0}
 
     def comm_benchmark(self, rounds=200):
         return 12.0, 15.0
+
+    def profile_enable(self, on=True):
+        pass
+
+    def profile_reset(self):
+        pass
+
+    def profile(self):
+        return {"halo_exchange": {"launches": 8, "ms": 0.1}, "cg_spmv": {"launches": 1, "ms": 0.03}}
 
     def local_energy(self):
         return (1.0 + self.its) / self.world
