@@ -99,6 +99,15 @@ int arap_prepare(arap_handle *h, const void *rest_xyz, int32_t rest_scalar_bytes
  * until arap_prepare (or arap_deform) has run again. Returns ARAP_OK, ARAP_NOT_CONVERGED or an error. */
 int arap_iterate(arap_handle *h, int32_t n_iterations);
 
+/* Pipelined arap_deform (extension; the reference's deform is synchronous): enqueues the dirty block if needed (that part blocks),
+ * n iterations and the write-back of p' into mesh_xyz on a second stream, and returns without waiting. arap_deform_wait blocks until
+ * the OLDEST frame in flight has arrived in its buffer; at most two frames may be in flight, each with its own page-locked buffer
+ * (arap_host_alloc), so that the write-back of frame k overlaps the iterations of frame k + 1:
+ *     arap_deform_async(h, A, 4, 1);  loop { arap_deform_async(h, B, 4, 1); arap_deform_wait(h); use A; swap(A, B); }
+ * The status of the iterations (ARAP_NOT_CONVERGED) is reported by the arap_deform_wait that drains the pipeline. */
+int arap_deform_async(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32_t n_iterations);
+int arap_deform_wait(arap_handle *h);
+
 /* Current p' (V x 3) cast to scalars of out_scalar_bytes (arap.h:133-135). */
 int arap_get_positions(arap_handle *h, void *out_xyz, int32_t out_scalar_bytes);
 

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "arap_default_options", "arap_create", "arap_destroy", "arap_set_constraints", "arap_is_dirty",
     "arap_prepare", "arap_iterate", "arap_get_positions", "arap_deform", "arap_get_csr_nnz", "arap_get_csr",
     "arap_get_free_map", "arap_get_rotations", "arap_get_rhs", "arap_get_render_buffers", "arap_energy", "arap_get_solver_stats", "arap_profile_enable",
+    "arap_deform_async", "arap_deform_wait",
     "arap_profile_reset", "arap_profile_get", "arap_kernel_name", "arap_timer_start", "arap_timer_stop",
     "arap_synchronize", "arap_host_alloc", "arap_host_free", "arap_last_error", "arap_create_error",
     "arap_abi_version", "arap_batch_create", "arap_batch_destroy", "arap_batch_set_constraints", "arap_batch_prepare",
@@ -102,6 +103,8 @@ def lib():
     L.arap_iterate.argtypes = [vp, i32]
     L.arap_get_positions.argtypes = [vp, vp, i32]
     L.arap_deform.argtypes = [vp, vp, i32, i32]
+    L.arap_deform_async.argtypes = [vp, vp, i32, i32]
+    L.arap_deform_wait.argtypes = [vp]
     L.arap_get_csr_nnz.argtypes = [vp, C.POINTER(i32)]
     L.arap_get_csr.argtypes = [vp, vp, vp, vp]
     L.arap_get_free_map.argtypes = [vp, vp, C.POINTER(i32)]
@@ -251,6 +254,18 @@ class AsRigidAsPossibleDeformation:
         if rc in (ARAP_ERR_INVALID, ARAP_ERR_CUDA, ARAP_ERR_ALLOC):
             raise ArapError(rc, lib().arap_last_error(self._h).decode())
         return rc in (ARAP_OK, ARAP_UNCONSTRAINED)     # ARAP_NOT_CONVERGED / ARAP_ERR_SOLVER: the reference's `false`
+
+    def deform_async(self, mesh, numberOfIterations):
+        """Pipelined deform (arap_deform_async): iterations + write-back into `mesh` (a page-locked array of the handle's shape) are
+        enqueued, nothing is waited for; at most two frames in flight, each in its own buffer. deform_wait() completes the oldest."""
+        assert mesh.flags["C_CONTIGUOUS"] and mesh.shape == self.mesh.shape
+        return self._check(lib().arap_deform_async(self._h, _ptr(mesh), mesh.dtype.itemsize, int(numberOfIterations)))
+
+    def deform_wait(self):
+        rc = lib().arap_deform_wait(self._h)
+        if rc in (ARAP_ERR_INVALID, ARAP_ERR_CUDA, ARAP_ERR_ALLOC):
+            raise ArapError(rc, lib().arap_last_error(self._h).decode())
+        return rc in (ARAP_OK, ARAP_UNCONSTRAINED)
 
     # -- split protocol (what deform() is made of) ----------------------------------------------
     @property
@@ -570,6 +585,15 @@ class PartitionedDeformation:
 
     def local_energy(self):
         return self.arap.energy()
+
+    def profile_enable(self, on=True):
+        self.arap.profile_enable(on)
+
+    def profile_reset(self):
+        self.arap.profile_reset()
+
+    def profile(self):
+        return self.arap.profile()
 
     def comm_benchmark(self, rounds=200):
         """(microseconds per halo exchange, per all-reduce) on this rank's stream; collective."""

@@ -100,6 +100,9 @@ public:
     virtual int iterate(int n, bool defer_sync = false) = 0;
     virtual int finish_iterate() = 0;
     virtual int get_positions(void *out, int scalar_bytes) = 0;
+    virtual int deform_async(void *out, int scalar_bytes, int n) = 0;
+    virtual int deform_wait() = 0;
+    virtual bool deform_wait_pending() = 0;
     virtual int get_csr_nnz(int *nnz) = 0;
     virtual int get_csr(int *rowptr, int *colidx, void *weights) = 0;
     virtual int get_free_map(int *free_idx, int *n_free) = 0;
@@ -405,6 +408,8 @@ public:
         for (auto &e : poll_event) if (e) cudaEventDestroy(e);
         if (timer_start) cudaEventDestroy(timer_start);
         if (timer_stop) cudaEventDestroy(timer_stop);
+        for (int k = 0; k < 2; ++k) { if (snap_ready[k]) cudaEventDestroy(snap_ready[k]); if (copy_done[k]) cudaEventDestroy(copy_done[k]); }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -2501,6 +2506,59 @@ public:
         return ARAP_OK;
     }
 
+    // ---- pipelined deform: the write-back of frame k runs on a second stream while frame k + 1 iterates --------------------
+    // deform_async enqueues n iterations, a snapshot of p' in the caller's order and scalar type, and the snapshot's copy to the
+    // caller's (page-locked) buffer on `copy_stream`; nothing blocks the host. deform_wait blocks until the OLDEST frame in flight
+    // is in its buffer. At most two frames are in flight (two host buffers on the caller's side).
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ready[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+    DeviceBuffer<unsigned char> snapshot;
+    unsigned async_head = 0, async_tail = 0;       // frames enqueued / frames waited for
+    int async_status = ARAP_OK;
+
+    int deform_async(void *out, int scalar_bytes, int n) override {
+        if (!out || (scalar_bytes != 4 && scalar_bytes != 8)) return fail(ARAP_ERR_INVALID, "deform_async: bad arguments");
+        if (async_head - async_tail >= 2) return fail(ARAP_ERR_INVALID, "deform_async: two frames are in flight already (call arap_deform_wait)");
+        if (!copy_stream) {
+            ARAP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                ARAP_CUDA(cudaEventCreateWithFlags(&snap_ready[k], cudaEventDisableTiming));
+                ARAP_CUDA(cudaEventCreateWithFlags(&copy_done[k], cudaEventDisableTiming));
+            }
+        }
+        const int rc = iterate(n, /*defer_sync=*/true);
+        if (rc < 0) return rc;
+        if (rc > 0) async_status = rc;
+        const int V = n_vertices;
+        const size_t bytes = (size_t)scalar_bytes * 3 * (size_t)V;
+        const unsigned slot = async_head & 1u;
+        if (async_head > 0) ARAP_CUDA(cudaStreamWaitEvent(stream, copy_done[(async_head - 1) & 1u], 0));   // the snapshot is still being read
+        ARAP_CUDA(snapshot.ensure(bytes));
+        begin_launch(ARAP_K_MISC);
+        if (scalar_bytes == 4) export_positions_kernel<S, float><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, perm.ptr, cur4.ptr, (float *)snapshot.ptr);
+        else export_positions_kernel<S, double><<<grid_for((size_t)V), kBlock, 0, stream>>>(V, perm.ptr, cur4.ptr, (double *)snapshot.ptr);
+        end_launch();
+        pdl_next_plain = true;
+        ARAP_CUDA(cudaEventRecord(snap_ready[slot], stream));
+        ARAP_CUDA(cudaStreamWaitEvent(copy_stream, snap_ready[slot], 0));
+        ARAP_CUDA(cudaMemcpyAsync(out, snapshot.ptr, bytes, cudaMemcpyDeviceToHost, copy_stream));
+        ARAP_CUDA(cudaEventRecord(copy_done[slot], copy_stream));
+        ++async_head;
+        return ARAP_OK;
+    }
+    bool deform_wait_pending() override { return async_head != async_tail; }
+    int deform_wait() override {
+        if (async_head == async_tail) return ARAP_OK;
+        ARAP_CUDA(cudaEventSynchronize(copy_done[async_tail & 1u]));
+        ++async_tail;
+        if (async_head != async_tail) return ARAP_OK;          // the convergence status is booked when the pipeline has drained
+        const int rc = finish_iterate();
+        const int st = async_status;
+        async_status = ARAP_OK;
+        if (rc < 0) return rc;
+        return rc > 0 ? rc : st;
+    }
+
     int get_csr_nnz(int *out) override {
         if (!rowptr.ptr) return fail(ARAP_ERR_INVALID, "get_csr: weights not built (call arap_prepare first)");
         *out = nnz;
@@ -2723,6 +2781,23 @@ int arap_deform(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32
     if (rc_fin < 0) return rc_fin;
     if (rc_pos != ARAP_OK) return rc_pos;
     return rc_fin > 0 ? rc_fin : rc;                                       /* ARAP_NOT_CONVERGED */
+}
+
+int arap_deform_async(arap_handle *h, void *mesh_xyz, int32_t mesh_scalar_bytes, int32_t n_iterations) {
+    ARAP_ENGINE_OR_FAIL(h);
+    if (!mesh_xyz) return h->engine->fail(ARAP_ERR_INVALID, "deform_async: null mesh");
+    if (h->engine->dirty) {                                               /* arap.h:102: the dirty block is synchronous */
+        int rc = h->engine->deform_wait();
+        while (rc >= 0 && h->engine->deform_wait_pending()) rc = h->engine->deform_wait();
+        if (rc < 0) return rc;
+        rc = h->engine->prepare(mesh_xyz, mesh_scalar_bytes);
+        if (rc != ARAP_OK) return rc;
+    }
+    return h->engine->deform_async(mesh_xyz, mesh_scalar_bytes, n_iterations);
+}
+int arap_deform_wait(arap_handle *h) {
+    ARAP_ENGINE_OR_FAIL(h);
+    return h->engine->deform_wait();
 }
 
 int arap_get_csr_nnz(arap_handle *h, int32_t *nnz) {
