@@ -404,23 +404,7 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
     # CUDA events (rank 0's view; a rank that waits for a neighbour inside an exchange books the wait there -- that IS the cost)
     phases = None
     if profile_steps > 0:
-        its0 = part.solver_stats()["cg_iterations_total"]
-        part.profile_enable(True)
-        part.profile_reset()
-        part.arap.timer_start()
-        part.iterate(profile_steps)
-        ms_prof = part.arap.timer_stop()
-        prof = part.profile()
-        part.profile_enable(False)
-        cg_its = max(1, part.solver_stats()["cg_iterations_total"] - its0)
-        groups = {"halo_exchange": ("halo_exchange",), "allreduce_cg_scalars": ("allreduce_scalars", "cg_finalize"), "allreduce_replicated_level_rhs": ("allreduce_level",),
-                  "local_step + rhs_residual + apply_update": ("local_step", "local_step_redo", "rhs_residual", "apply_update"),
-                  "cg_spmv + cg_update": ("cg_spmv", "cg_update_mg"), "multigrid_fine_level": ("mg_fine_residual", "mg_fine_postsmooth"),
-                  "multigrid_coarse_levels": ("mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add", "mg_csr_postsmooth", "mg_dense_solve", "mg_tail")}
-        phases = {g: round(1e3 * sum(prof.get(n, {}).get("ms", 0.0) for n in names) / cg_its, 1) for g, names in groups.items()}
-        phases["sum_of_phases_us"] = round(sum(phases.values()), 1)
-        phases["launch_by_launch_us_per_cg_iteration"] = round(1e3 * ms_prof / cg_its, 1)
-        phases["launches_per_cg_iteration"] = round(sum(v["launches"] for v in prof.values()) / cg_its, 1)
+        phases = phase_profile(part, part.solver_stats, profile_steps)
         barrier_and_sync(dist)
     res = {"iterations_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "energy": float(e.item()),
            "cg_iterations_per_step": stats["cg_iterations_total"] / max(1, stats["global_steps"]),
@@ -433,6 +417,28 @@ def run_partitioned(dist, rank, world, local_rank, P, F, idx, tgt, owner, warmup
            "transport": transport, "us_per_cg_iteration_by_phase_rank0": phases, "positions": positions}
     del part
     return res
+
+
+PHASE_GROUPS = {"halo_exchange": ("halo_exchange",), "allreduce_cg_scalars": ("allreduce_scalars", "cg_finalize"), "allreduce_replicated_level_rhs": ("allreduce_level",),
+                "local_step + rhs_residual + apply_update": ("local_step", "local_step_redo", "rhs_residual", "apply_update"),
+                "cg_spmv + cg_update": ("cg_spmv", "cg_update_mg"), "multigrid_fine_level": ("mg_fine_residual", "mg_fine_postsmooth"),
+                "multigrid_coarse_levels": ("mg_csr_residual", "mg_restrict_presmooth", "mg_prolong_add", "mg_csr_postsmooth", "mg_dense_solve", "mg_tail")}
+
+
+def phase_profile(handle, stats_fn, steps):
+    """`steps` more ARAP iterations launch by launch with every kernel / exchange / all-reduce bracketed by CUDA events -> us per CG
+    iteration by phase (the event brackets add ~5 us per launch: the SHARES are the information)."""
+    its0 = stats_fn()["cg_iterations_total"]
+    handle.profile_enable(True)
+    handle.profile_reset()
+    handle.iterate(steps)
+    prof = handle.profile()
+    handle.profile_enable(False)
+    cg_its = max(1, stats_fn()["cg_iterations_total"] - its0)
+    phases = {g: round(1e3 * sum(prof.get(n, {}).get("ms", 0.0) for n in names) / cg_its, 1) for g, names in PHASE_GROUPS.items()}
+    phases["sum_of_phases_us"] = round(sum(phases.values()), 1)
+    phases["launches_per_cg_iteration"] = round(sum(v["launches"] for v in prof.values()) / cg_its, 1)
+    return phases
 
 
 def run_single_gpu_grid(P, F, idx, tgt, local_rank, warmup, steps):
@@ -454,6 +460,7 @@ def run_single_gpu_grid(P, F, idx, tgt, local_rank, warmup, steps):
     res = {"iterations_per_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "energy": a.energy(),
            "cg_iterations_per_step": st["cg_iterations_total"] / max(1, st["global_steps"]), "prepare_s": prepare_s,
            "positions": a.positions(np.float64)}
+    res["us_per_cg_iteration_by_phase"] = phase_profile(a, a.solver_stats, 3)
     a.close()
     return res
 

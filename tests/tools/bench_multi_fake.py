@@ -27,6 +27,15 @@ class _Timer:
     def synchronize(self):
         pass
 
+    def profile_enable(self, on=True):
+        pass
+
+    def profile_reset(self):
+        pass
+
+    def profile(self):
+        return {"halo_exchange": {"launches": 8, "ms": 0.1}, "cg_spmv": {"launches": 1, "ms": 0.03}}
+
 
 class FakeSingle(_Timer):
     def __init__(self, mesh, faces, precision=None, **kw):
