@@ -1865,7 +1865,10 @@ public:
         MgLocalHierarchy LH;
         std::string err;
         // levels of at most this many rows are replicated on every rank (mg_partition.h): 4 halo exchanges less per level
-        const int replicate_rows = getenv("ARAP_MG_REPLICATE_ROWS") ? atoi(getenv("ARAP_MG_REPLICATE_ROWS")) : 400000;
+        // a level kept whole on every rank costs its full sweep time on each of them plus an all-reduce of its right-hand side; a
+        // partitioned one costs 1 / world of the sweeps plus four halo exchanges (~65 us). Measured break-even at 16M vertices:
+        // the 300k-row level is better replicated on 2 GPUs and better partitioned on 8 (8.4 -> 7.5 ms per ARAP iteration).
+        const int replicate_rows = getenv("ARAP_MG_REPLICATE_ROWS") ? atoi(getenv("ARAP_MG_REPLICATE_ROWS")) : std::max(50000, 800000 / std::max(1, world_size));
         if (!mg_slice_hierarchy(H, my_rank, n_rows, V, global_of_local.data(), LH, err, replicate_rows)) return fail(ARAP_ERR_SOLVER, err);
         mg_first_replicated = LH.first_replicated;
         { MgHierarchyHost().levels.swap(H.levels); }          // the global matrices are no longer needed
