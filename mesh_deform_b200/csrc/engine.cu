@@ -1298,6 +1298,7 @@ public:
         const double theta2 = mo.theta * mo.theta;
         const bool timing = getenv("ARAP_MG_TIMING") != nullptr;
         bool sweep_keys = false;
+        DeviceBuffer<int> lex_work, lex_work_next, lex_roots, lex_adj, lex_far, lex_stamp, lex_count;
         DeviceBuffer<double> pos, pos_next, length_total;      // sweep keys: where the level's rows sit, the size of a sweep cell
         double cell = 0.0;
         DeviceBuffer<int> len, agg, status, flag, root_id, joined, scalars, cursor;
@@ -1376,10 +1377,12 @@ public:
                 const int G = grid_for((size_t)n);
                 const double *idg = d->inv_diag.ptr;
                 agg_init_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, agg.ptr, status.ptr);
-                // election keys (agg_key_kernel): ordered sweeps for a quad-like strength graph, rim growth from sparse seeds otherwise;
-                // decided once, on the finest level (ARAP_MG_AGG_KEY=sweep|rim overrides)
+                // which independent set: the lexicographically first one (a wavefront, lex_*_kernel) for a quad-like strength graph, rim
+                // growth from sparse seeds (agg_key_kernel) otherwise; decided once, on the finest level (ARAP_MG_AGG_KEY=sweep|rim
+                // overrides; ARAP_MG_WAVEFRONT=0 replaces the wavefront by the round-2b sweeps over cells with hashed priorities)
                 if (l == 0) {
-                    if (pos_src && !(getenv("ARAP_MG_SWEEP_CELLS") && atoi(getenv("ARAP_MG_SWEEP_CELLS")) == 0)) {
+                    const bool no_wavefront = getenv("ARAP_MG_WAVEFRONT") && atoi(getenv("ARAP_MG_WAVEFRONT")) == 0;
+                    if (pos_src && no_wavefront && !(getenv("ARAP_MG_SWEEP_CELLS") && atoi(getenv("ARAP_MG_SWEEP_CELLS")) == 0)) {
                         ARAP_CUDA(pos.ensure(3 * (size_t)n));
                         pos_gather_kernel<<<G, kBlock, 0, stream>>>(n, pos_src, pos_scalar_bytes, pos_stride, pos.ptr);
                     }
@@ -1397,11 +1400,11 @@ public:
                     const char *kenv = getenv("ARAP_MG_AGG_KEY");
                     // (aggregates confined to partition blocks: the sweeps lose a whole CG iteration to the seam -- 2000^2 plane in 2 blocks
                     //  6.35-7.15 against 5.45 unconfined -- rim growth packs against the seam and loses nothing: 6.05-6.1 either way)
-                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : (mean_strong <= 4.5 && block == nullptr);
+                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : (mean_strong <= 4.5 && (block == nullptr || !(getenv("ARAP_MG_WAVEFRONT") && atoi(getenv("ARAP_MG_WAVEFRONT")) == 0)));
                     cell = strong_total > 0 ? 8.0 * h_length / (double)strong_total : 0.0;        // 8 mean edges: ~64 rows of a surface per cell
                     if (!(cell > 0.0) || !sweep_keys) pos.release();
-                    if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s keys%s\n", mean_strong, sweep_keys ? "sweep" : "rim-growth",
-                                             sweep_keys ? (pos.ptr ? " over spatial cells" : " over runs of 64 rows") : "");
+                    if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s\n", mean_strong,
+                                             !sweep_keys ? "rim growth" : !no_wavefront ? "wavefront (lexicographically first set)" : pos.ptr ? "sweeps over spatial cells" : "sweeps over runs of 64 rows");
                 }
                 // rim growth: 1 vertex in 2^bits is a seed (ARAP_MG_AGG_SEED_BITS, 0 = every vertex; small levels still get a handful);
                 // where a round elects nothing although vertices remain (no seed in that component), the seed set is made 8x denser
@@ -1410,7 +1413,46 @@ public:
                 while ((2 << log2n) <= active) ++log2n;
                 seed_bits = std::max(0, std::min(std::min(23, seed_bits), log2n - 3));
                 int rounds_used = 0;
-                for (int round = 0; round < 8192; ++round) {
+                const bool wavefront = sweep_keys && !(getenv("ARAP_MG_WAVEFRONT") && atoi(getenv("ARAP_MG_WAVEFRONT")) == 0);
+                if (wavefront) {
+                    // the lexicographically first independent set (the host's greedy walk), as a wavefront over worklists
+                    ARAP_CUDA(lex_work.ensure((size_t)n));
+                    ARAP_CUDA(lex_work_next.ensure((size_t)n));
+                    ARAP_CUDA(lex_roots.ensure((size_t)n));
+                    ARAP_CUDA(lex_adj.ensure((size_t)n));
+                    ARAP_CUDA(lex_far.ensure((size_t)n));
+                    ARAP_CUDA(lex_stamp.ensure((size_t)n));
+                    ARAP_CUDA(lex_count.ensure(8));
+                    ARAP_CUDA(cudaMemsetAsync(lex_count.ptr, 0, 8 * sizeof(int), stream));
+                    LexLists L;
+                    L.work = lex_work.ptr; L.work_next = lex_work_next.ptr; L.roots = lex_roots.ptr; L.adj = lex_adj.ptr; L.far = lex_far.ptr;
+                    L.count = lex_count.ptr; L.stamp = lex_stamp.ptr;
+                    lex_fill_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, L.work, L.count, L.stamp);
+                    const int Gw = std::min(G, sm_count * 8);
+                    int h_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    const int max_rounds = n + 64;
+                    for (int round = 0; round < max_rounds; ++round) {
+                        // the first rounds sweep long lists (round 0: every undecided row); later ones the front only
+                        const int Gr = Gw;                 // one warp per list entry in the elect / next kernels
+                        lex_elect_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                        lex_cover1_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                        lex_cover2_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                        lex_next_kernel<<<Gr, kBlock, 0, stream>>>(L, round, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                        lex_advance_kernel<<<1, 1, 0, stream>>>(L.count, L.count + 5);
+                        std::swap(L.work, L.work_next);
+                        if ((round & 63) == 63) {
+                            ARAP_CUDA(cudaMemcpyAsync(h_count, L.count, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                            ARAP_CUDA(cudaStreamSynchronize(stream));
+                            if (h_count[0] == 0) break;
+                        }
+                    }
+                    ARAP_CUDA(cudaMemcpyAsync(h_count, L.count, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    ARAP_CUDA(cudaStreamSynchronize(stream));
+                    ARAP_CUDA(cudaGetLastError());
+                    rounds_used = h_count[5] + 1;
+                    if (h_count[0] != 0) return fail(ARAP_ERR_SOLVER, "multigrid setup: the aggregation wavefront did not terminate");
+                }
+                for (int round = 0; round < 8192 && !wavefront; ++round) {
                     ++rounds_used;
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
                     agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr,

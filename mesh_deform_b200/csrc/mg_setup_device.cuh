@@ -277,6 +277,163 @@ __global__ void __launch_bounds__(kBlock) agg_cover2_kernel(int n, const int *__
     }
     atomicAdd(n_undecided, 1);
 }
+// ---- the lexicographically first maximal independent set of the squared strength graph, as a wavefront ---------------------------
+// What the host setup's sequential greedy pass computes (visit the rows in order; a row none of whose strong neighbours is
+// aggregated yet becomes a root and takes them): row i is a root iff no LOWER row within distance 2 is one. In parallel: i is decided
+// as soon as every lower row within distance 2 is, so each round elects the undecided rows whose lower distance-2 neighbourhood is
+// fully decided, covers their surroundings, and hands the undecided rows within distance 2 of anything decided this round to the
+// next round as its worklist. One coherent sweep over the whole level -- no seams between independently grown patches, which is what
+// the hashed / rim-growth / cell-sweep elections lose 20-40 % of the preconditioner's quality to on regular quad-like meshes --
+// at the price of as many rounds as the longest dependency chain (~ the side length of the mesh): the rounds work on worklists
+// (the front), with device-side counts and no host synchronisation except a termination check every 64 rounds.
+struct LexLists {
+    int *work, *work_next, *roots, *adj, *far;      // this round's candidates, next round's, newly: roots / next to a root / distance 2
+    int *count;                                       // [0] work [1] work_next [2] roots [3] adj [4] far
+    int *stamp;                                       // round in which a row was last put on a worklist
+};
+__global__ void __launch_bounds__(kBlock) lex_fill_kernel(int n, const int *__restrict__ status, int *__restrict__ work, int *__restrict__ count,
+                                                          int *__restrict__ stamp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    stamp[i] = -1;
+    if (status[i] == 0) work[atomicAdd(&count[0], 1)] = i;
+}
+// One WARP per candidate: a single thread would walk ~50 dependent, uncached loads (rows of the neighbours of the neighbours) one
+// after the other, ~100 us per round whatever the size of the front; the lanes take the neighbours' rows in parallel.
+__global__ void __launch_bounds__(kBlock) lex_elect_kernel(LexLists L, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                           const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                           const int *__restrict__ block, double theta2, const int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_work = L.count[0];
+    for (int t = warp; t < n_work; t += n_warps) {
+        const int i = L.work[t];
+        if (status[i] != 0) continue;                                   // uniform over the warp
+        const int b = rowptr[i], e = rowptr[i + 1];
+        bool blocked = false;
+        for (int base = b; base < e && !blocked; base += 32) {
+            // every lane fetches one neighbour u of i and the extent of u's row
+            const int k = base + lane;
+            int u = -1, ub = 0, ue = 0;
+            if (k < e) {
+                u = colidx[k];
+                if (is_strong(i, u, val[k], inv_diag, block, theta2)) { ub = rowptr[u]; ue = rowptr[u + 1]; } else u = -1;
+            }
+            bool bl = u >= 0 && u < i && status[u] == 0;
+            const int cnt = min(32, e - base);
+            for (int l = 0; l < cnt; ++l) {                              // then the warp walks u's row together
+                const int uu = __shfl_sync(0xffffffffu, u, l);
+                if (uu < 0) continue;
+                const int qb = __shfl_sync(0xffffffffu, ub, l), qe = __shfl_sync(0xffffffffu, ue, l);
+                for (int q = qb + lane; q < qe; q += 32) {
+                    const int w = colidx[q];
+                    if (w < i && status[w] == 0 && is_strong(uu, w, val[q], inv_diag, block, theta2)) bl = true;
+                }
+            }
+            blocked = __any_sync(0xffffffffu, bl);
+        }
+        if (!blocked && lane == 0) L.roots[atomicAdd(&L.count[2], 1)] = i;
+    }
+}
+// new roots take their undecided strong neighbours (two roots of one round are at distance >= 3: no neighbour is shared).
+// One warp per root, one lane per row entry; the list append is one atomic per warp.
+__device__ __forceinline__ void lex_append(bool take, int value, int *__restrict__ list, int *__restrict__ counter) {
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+__global__ void __launch_bounds__(kBlock) lex_cover1_kernel(LexLists L, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                            const int *__restrict__ block, double theta2, int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_roots = L.count[2];
+    for (int t = warp; t < n_roots; t += n_warps) {
+        const int r = L.roots[t];
+        if (lane == 0) status[r] = 1;
+        const int b = rowptr[r], e = rowptr[r + 1];
+        for (int base = b; base < e; base += 32) {
+            const int k = base + lane;
+            bool take = false;
+            int u = -1;
+            if (k < e) {
+                u = colidx[k];
+                take = is_strong(r, u, val[k], inv_diag, block, theta2) && status[u] == 0;
+                if (take) status[u] = 3;
+            }
+            lex_append(take, u, L.adj, &L.count[3]);
+        }
+    }
+}
+// ... and the undecided rows next to those leave the election (distance 2 from a root)
+__global__ void __launch_bounds__(kBlock) lex_cover2_kernel(LexLists L, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                            const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                            const int *__restrict__ block, double theta2, int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_adj = L.count[3];
+    for (int t = warp; t < n_adj; t += n_warps) {
+        const int u = L.adj[t];
+        const int b = rowptr[u], e = rowptr[u + 1];
+        for (int base = b; base < e; base += 32) {
+            const int k = base + lane;
+            bool take = false;
+            int w = -1;
+            if (k < e) {
+                w = colidx[k];
+                take = is_strong(u, w, val[k], inv_diag, block, theta2) && atomicCAS(&status[w], 0, 2) == 0;
+            }
+            lex_append(take, w, L.far, &L.count[4]);
+        }
+    }
+}
+// next round's worklist: the undecided rows within distance 2 of a row decided in this round (one warp per decided row)
+__global__ void __launch_bounds__(kBlock) lex_next_kernel(LexLists L, int round, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                                                          const double *__restrict__ val, const double *__restrict__ inv_diag,
+                                                          const int *__restrict__ block, double theta2, const int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_roots = L.count[2], n_adj = L.count[3], n_far = L.count[4];
+    const int total = n_roots + n_adj + n_far;
+    for (int t = warp; t < total; t += n_warps) {
+        const int v = t < n_roots ? L.roots[t] : t < n_roots + n_adj ? L.adj[t - n_roots] : L.far[t - n_roots - n_adj];
+        const int b = rowptr[v], e = rowptr[v + 1];
+        for (int base = b; base < e; base += 32) {
+            const int k = base + lane;
+            int u = -1, ub = 0, ue = 0;
+            if (k < e) {
+                u = colidx[k];
+                if (is_strong(v, u, val[k], inv_diag, block, theta2)) { ub = rowptr[u]; ue = rowptr[u + 1]; } else u = -1;
+            }
+            lex_append(u >= 0 && status[u] == 0 && atomicExch(&L.stamp[u], round) != round, u, L.work_next, &L.count[1]);
+            const int cnt = min(32, e - base);
+            for (int l = 0; l < cnt; ++l) {
+                const int uu = __shfl_sync(0xffffffffu, u, l);
+                if (uu < 0) continue;
+                const int qb = __shfl_sync(0xffffffffu, ub, l), qe = __shfl_sync(0xffffffffu, ue, l);
+                for (int q0 = qb; q0 < qe; q0 += 32) {
+                    const int q = q0 + lane;
+                    int w = -1;
+                    bool take = false;
+                    if (q < qe) {
+                        w = colidx[q];
+                        take = status[w] == 0 && is_strong(uu, w, val[q], inv_diag, block, theta2) && atomicExch(&L.stamp[w], round) != round;
+                    }
+                    lex_append(take, w, L.work_next, &L.count[1]);
+                }
+            }
+        }
+    }
+}
+__global__ void lex_advance_kernel(int *__restrict__ count, int *__restrict__ rounds_with_work) {
+    count[0] = count[1];
+    count[1] = count[2] = count[3] = count[4] = 0;
+    if (count[0] > 0) *rounds_with_work += 1;
+}
 __global__ void __launch_bounds__(kBlock) agg_root_flag_kernel(int n, const int *__restrict__ status, int *__restrict__ flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = status[i] == 1 ? 1 : 0;
