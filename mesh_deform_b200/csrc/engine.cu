@@ -1480,11 +1480,28 @@ public:
                     DevCsr &P = *d->P, &R = *d->R;
                     DevCsr AP;
                     std::unique_ptr<DevCsr> Ac(new DevCsr());
-                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 0, len.ptr,
-                                                                 nullptr, nullptr, nullptr, scalars.ptr + 3);
+                    // (rows of P: 64 entries, 512 on the dense coarse levels thin partition blocks produce -- 111 entries per row of A there)
+                    bool wide_p = A->nnz > 40 * (long long)n;
+                    for (int attempt = wide_p ? 1 : 0; attempt < 2; ++attempt) {
+                        wide_p = attempt == 1;
+                        ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 3, 0, sizeof(int), stream));
+                        if (!wide_p) prolongator_kernel<64><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 0, len.ptr,
+                                                                                     nullptr, nullptr, nullptr, scalars.ptr + 3);
+                        else prolongator_kernel<512><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 0, len.ptr,
+                                                                               nullptr, nullptr, nullptr, scalars.ptr + 3);
+                        ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                        ARAP_CUDA(cudaStreamSynchronize(stream));
+                        if (h_scalars[3] == 0) break;
+                    }
+                    if (h_scalars[3] != 0) {
+                        if (timing) std::fprintf(stderr, "[mg device setup] level %d (%d rows, %d nnz): a row of P outgrew 512 entries, host setup instead\n", l, n, A->nnz);
+                        return ARAP_OK;
+                    }
                     { int rc = csr_allocate(P, n, n_agg, len.ptr); if (rc) return rc; }
-                    prolongator_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 1, nullptr,
-                                                                 P.rowptr.ptr, P.colidx.ptr, P.val.ptr, scalars.ptr + 3);
+                    if (!wide_p) prolongator_kernel<64><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 1, nullptr,
+                                                                                 P.rowptr.ptr, P.colidx.ptr, P.val.ptr, scalars.ptr + 3);
+                    else prolongator_kernel<512><<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, joined.ptr, d->omega, 1, nullptr,
+                                                                           P.rowptr.ptr, P.colidx.ptr, P.val.ptr, scalars.ptr + 3);
                     // ---- R = P^T, rows sorted
                     ARAP_CUDA(cursor.ensure((size_t)n_agg + 1));
                     ARAP_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(int) * ((size_t)n_agg + 1), stream));
@@ -1497,14 +1514,18 @@ public:
                     // outgrow that (coarse operators of irregular meshes) is redone with 512, and only then is the host setup the fallback.
                     auto product = [&](const DevCsr &X, const DevCsr &Y, DevCsr &Z) -> int {
                         const int rows = X.n_rows, Gp = grid_for((size_t)rows);
-                        for (int attempt = 0; attempt < 2; ++attempt) {
+                        for (int attempt = 0; attempt < 3; ++attempt) {
+                            if (attempt == 2 && rows > 200000) break;              // 24 KB of accumulator per thread: small levels only
                             ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 3, 0, sizeof(int), stream));
                             if (attempt == 0)
                                 spgemm_rows_kernel<128><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 0, len.ptr,
                                                                                    nullptr, nullptr, nullptr, scalars.ptr + 3);
-                            else
+                            else if (attempt == 1)
                                 spgemm_rows_kernel<512><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 0, len.ptr,
                                                                                    nullptr, nullptr, nullptr, scalars.ptr + 3);
+                            else
+                                spgemm_rows_kernel<2048><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 0, len.ptr,
+                                                                                    nullptr, nullptr, nullptr, scalars.ptr + 3);
                             ARAP_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.ptr + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
                             ARAP_CUDA(cudaStreamSynchronize(stream));
                             if (h_scalars[3] != 0) continue;
@@ -1512,9 +1533,12 @@ public:
                             if (attempt == 0)
                                 spgemm_rows_kernel<128><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 1, nullptr,
                                                                                    Z.rowptr.ptr, Z.colidx.ptr, Z.val.ptr, scalars.ptr + 3);
-                            else
+                            else if (attempt == 1)
                                 spgemm_rows_kernel<512><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 1, nullptr,
                                                                                    Z.rowptr.ptr, Z.colidx.ptr, Z.val.ptr, scalars.ptr + 3);
+                            else
+                                spgemm_rows_kernel<2048><<<Gp, kBlock, 0, stream>>>(rows, X.rowptr.ptr, X.colidx.ptr, X.val.ptr, Y.rowptr.ptr, Y.colidx.ptr, Y.val.ptr, 1, nullptr,
+                                                                                    Z.rowptr.ptr, Z.colidx.ptr, Z.val.ptr, scalars.ptr + 3);
                             return ARAP_OK;
                         }
                         return ARAP_OK;                                  // h_scalars[3] != 0: the caller gives up on the device path

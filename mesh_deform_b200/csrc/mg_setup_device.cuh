@@ -504,7 +504,7 @@ struct RowAcc {
 };
 
 // P = (I - omega D^-1 A) T, T piecewise constant over the aggregates. fill == 0: row lengths.
-constexpr int kCapP = 64;
+template <int CAP>
 __global__ void __launch_bounds__(kBlock) prolongator_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                              const double *__restrict__ val, const double *__restrict__ inv_diag,
                                                              const int *__restrict__ agg, double omega, int fill, int *__restrict__ out_len,
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kBlock) prolongator_kernel(int n, const int *_
                                                              int *__restrict__ error) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    RowAcc<kCapP> acc;
+    RowAcc<CAP> acc;
     const double d = inv_diag[i];
     if (d > 0) {
         if (agg[i] >= 0) acc.add(agg[i], 1.0);
