@@ -1398,10 +1398,10 @@ public:
                     ARAP_CUDA(cudaStreamSynchronize(stream));
                     const double mean_strong = active > 0 ? (double)strong_total / active : 0.0;
                     const char *kenv = getenv("ARAP_MG_AGG_KEY");
-                    // (aggregates confined to partition blocks take rim growth. Measured at 16M vertices over 8 GPUs, CG iterations per ARAP
-                    //  iteration, strips / blocks: rim growth 9.64 / 8.56, wavefront 11.08 / 8.84 with coarse levels of 58-220 entries per row and
-                    //  a seventh level; on 2 and 4 partitions the wavefront is the better one, 7.8 / 7.25 against 8.2 / 8.4: ARAP_MG_AGG_KEY=sweep)
-                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : (mean_strong <= 4.5 && block == nullptr);
+                    // (aggregates confined to MANY partition blocks take rim growth. Measured at 16M vertices, CG iterations per ARAP iteration:
+                    //  8 GPUs, strips / blocks: rim growth 9.64 / 8.56, wavefront 11.08 / 8.84 -- coarse levels of 58-220 entries per row and a
+                    //  seventh level; 2 and 4 partitions: wavefront 7.8 / 7.25, rim growth 8.2 / 8.4-9.2)
+                    sweep_keys = kenv ? std::strcmp(kenv, "sweep") == 0 : (mean_strong <= 4.5 && (block == nullptr || world_size <= 4));
                     cell = strong_total > 0 ? 8.0 * h_length / (double)strong_total : 0.0;        // 8 mean edges: ~64 rows of a surface per cell
                     if (!(cell > 0.0) || !sweep_keys) pos.release();
                     if (timing) std::fprintf(stderr, "[mg device setup] %.2f strong connections per row: %s\n", mean_strong,

@@ -627,3 +627,22 @@ def test_hierarchy_reuse_across_dirty_cycles_keeps_parity():
     assert a.deform(2) and o.deform(2)
     assert a.solver_stats()["setup_host_ms"] + a.solver_stats()["setup_device_ms"] > 0
     assert np.abs(mesh - omesh).max() <= POS_TOL * bbox_diag(P)
+
+
+@pytest.mark.parametrize("agg_key", ["rim", "sweep"])
+def test_partitioned_strips_with_either_aggregation(agg_key, monkeypatch):
+    """The global hierarchy of a partitioned solver with its aggregates confined to the partition blocks, built with each of the
+    two root elections of the device setup (ARAP_MG_AGG_KEY: rim growth is the default beyond 4 partitions, the wavefront up to 4):
+    same parity bar against the unpartitioned oracle, global hierarchy in use."""
+    monkeypatch.setenv("ARAP_MG_AGG_KEY", agg_key)
+    nx, nz, iters = 200, 160, 4
+    P, F = G.grid_plane(nx, nz)
+    idx, tgt = G.grid_constraints(nx, nz, P)
+    pos, st = _run_partitioned(P, F, idx, tgt, 2, 3100 + (agg_key == "rim"), iters, position_tolerance=1e-8)
+    omesh = P.copy()
+    o = O.ArapOracle(omesh, F, np.float64)
+    constrain(o, idx, tgt)
+    assert o.deform(iters)
+    err = np.abs(pos - omesh).max() / bbox_diag(P)
+    print("strips", agg_key, "err/diag", err, "levels", st["mg_levels"], "CG iterations", st["cg_iterations_total"])
+    assert err <= POS_TOL and st["mg_global"] == 1 and st["mg_levels"] >= 3 and st["setup_device_ms"] > 0
