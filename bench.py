@@ -882,9 +882,11 @@ def main():
         # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
         ncu_file = next((f for f in ("r02_ncu_summary.json", "r01_h_ncu_summary.json") if os.path.exists(os.path.join(ROOT, "profiles", f))), None)
         ncu = json.load(open(os.path.join(ROOT, "profiles", ncu_file))) if ncu_file and args.nu == 316 and args.precision == "f64" else {}
+        ncu_alias = {"cg_spmv": "cg_spmv_z", "cg_update_mg": "cg_fused_update"}         # profile id -> kernel name in the capture
         for name, entry in kernels.items():
-            if name in ncu and "traffic_bytes" in ncu[name]:
-                entry["ncu_dram_traffic_bytes"] = ncu[name]["traffic_bytes"]
+            rec = ncu.get(name) or ncu.get(ncu_alias.get(name, ""))
+            if rec and "traffic_bytes" in rec:
+                entry["ncu_dram_traffic_bytes"] = rec["traffic_bytes"]
         # The roofline object is pinned to the kernel BASELINE.json's metric names (the local step); the whole step's aggregate and
         # every other kernel sit beside it. (Round 1 picked "the kernel with the largest share", which flipped between three ~11 % kernels.)
         pinned_kernel = "local_step" if "local_step" in kernels and "achieved_gbs" in kernels["local_step"] else \
