@@ -1415,6 +1415,7 @@ public:
                 seed_bits = std::max(0, std::min(std::min(23, seed_bits), log2n - 3));
                 int rounds_used = 0;
                 const bool wavefront = sweep_keys && !(getenv("ARAP_MG_WAVEFRONT") && atoi(getenv("ARAP_MG_WAVEFRONT")) == 0);
+                bool finish_with_rim = false;
                 if (wavefront) {
                     // the lexicographically first independent set (the host's greedy walk), as a wavefront over worklists
                     ARAP_CUDA(lex_work.ensure((size_t)n));
@@ -1431,7 +1432,10 @@ public:
                     lex_fill_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, L.work, L.count, L.stamp);
                     const int Gw = std::min(G, sm_count * 8);
                     int h_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    const int max_rounds = n + 64;
+                    // round budget: a few times the side length of a surface mesh (the dependency chain of a compact mesh); a mesh with
+                    // a longer chain (a ribbon a few rows wide) finishes with rim growth from what the wavefront has decided so far
+                    int max_rounds = std::max(4096, 8 * (int)std::sqrt((double)n));
+                    if (getenv("ARAP_MG_WAVEFRONT_ROUNDS")) max_rounds = std::max(1, atoi(getenv("ARAP_MG_WAVEFRONT_ROUNDS")));
                     for (int round = 0; round < max_rounds; ++round) {
                         // the first rounds sweep long lists (round 0: every undecided row); later ones the front only
                         const int Gr = Gw;                 // one warp per list entry in the elect / next kernels
@@ -1451,13 +1455,15 @@ public:
                     ARAP_CUDA(cudaStreamSynchronize(stream));
                     ARAP_CUDA(cudaGetLastError());
                     rounds_used = h_count[5] + 1;
-                    if (h_count[0] != 0) return fail(ARAP_ERR_SOLVER, "multigrid setup: the aggregation wavefront did not terminate");
+                    finish_with_rim = h_count[0] != 0;
+                    if (finish_with_rim && timing)
+                        std::fprintf(stderr, "[mg device setup] level %d: wavefront stopped after %d rounds, rim growth takes over\n", l, max_rounds);
                 }
-                for (int round = 0; round < 8192 && !wavefront; ++round) {
+                for (int round = 0; round < 8192 && (!wavefront || finish_with_rim); ++round) {
                     ++rounds_used;
                     ARAP_CUDA(cudaMemsetAsync(scalars.ptr + 1, 0, 2 * sizeof(int), stream));
                     agg_key_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, keys.ptr,
-                                                             (1u << seed_bits) - 1u, sweep_keys ? 1 : 0, pos.ptr, cell > 0.0 ? 1.0 / cell : 0.0);
+                                                             (1u << seed_bits) - 1u, sweep_keys && !finish_with_rim ? 1 : 0, pos.ptr, cell > 0.0 ? 1.0 / cell : 0.0);
                     agg_max1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr);
                     agg_elect_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, keys.ptr, m1.ptr, status.ptr, scalars.ptr + 1);
                     agg_cover1_kernel<<<G, kBlock, 0, stream>>>(n, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);

@@ -318,3 +318,23 @@ def test_pipelined_deform_matches_synchronous(prec):
     assert len(got) == frames
     for k in range(frames):
         assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
+
+
+def test_wavefront_round_budget_hands_over_to_rim_growth(monkeypatch):
+    """The wavefront aggregation of quad-like meshes needs as many rounds as the longest dependency chain of the mesh; beyond its
+    budget (ARAP_MG_WAVEFRONT_ROUNDS, by default a few times sqrt(rows)) the rest of the level is aggregated by rim growth from what
+    is decided so far. Forced here after 64 rounds on a 220 x 180 plane: still a device-built hierarchy, same parity."""
+    monkeypatch.setenv("ARAP_MG_WAVEFRONT_ROUNDS", "64")
+    P, F = G.grid_plane(220, 180)
+    idx, tgt = G.grid_constraints(220, 180, P)
+    m = P.copy()
+    a = ARAP(m, F, np.float64)
+    a.setConstraints(idx, tgt)
+    assert a.deform(4)
+    st = a.solver_stats()
+    o, omesh = oracle_for(P, F, idx, tgt)
+    assert o.deform(4)
+    dp, de = np.abs(m - omesh).max() / bbox_diag(P), abs(a.energy() - o.energy()) / o.energy()
+    print("budgeted wavefront: levels", st["mg_levels"], "CG iterations", st["cg_iterations_total"], "dp/diag", dp, "rel dE", de)
+    assert st["setup_device_ms"] > 0 and st["mg_levels"] >= 3
+    assert dp <= POS_TOL and de <= E_TOL
