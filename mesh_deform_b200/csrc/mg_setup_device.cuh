@@ -286,6 +286,10 @@ __global__ void __launch_bounds__(kBlock) agg_cover2_kernel(int n, const int *__
 // the hashed / rim-growth / cell-sweep elections lose 20-40 % of the preconditioner's quality to on regular quad-like meshes --
 // at the price of as many rounds as the longest dependency chain (~ the side length of the mesh): the rounds work on worklists
 // (the front), with device-side counts and no host synchronisation except a termination check every 64 rounds.
+// One relaxation (tests/test_aggregation_model.py models both forms): lex_cover1_kernel takes only UNDECIDED neighbours of a new
+// root; a neighbour that an earlier root had marked "distance 2" keeps that mark, so the rows behind it are not covered by the new
+// root and stay electable. The set is a few per cent denser than the walk's (roots at distance 2 through an already covered row),
+// never has adjacent roots, is deterministic, and is what round 2 measured; `status[u] == 0 || status[u] == 2` there makes it exact.
 struct LexLists {
     int *work, *work_next, *roots, *adj, *far;      // this round's candidates, next round's, newly: roots / next to a root / distance 2
     int *count;                                       // [0] work [1] work_next [2] roots [3] adj [4] far
