@@ -1431,6 +1431,7 @@ public:
                     L.count = lex_count.ptr; L.stamp = lex_stamp.ptr;
                     lex_fill_kernel<<<G, kBlock, 0, stream>>>(n, status.ptr, L.work, L.count, L.stamp);
                     const int Gw = std::min(G, sm_count * 8);
+                    const int lex_exact = getenv("ARAP_MG_WAVEFRONT_EXACT") && atoi(getenv("ARAP_MG_WAVEFRONT_EXACT")) != 0 ? 1 : 0;
                     int h_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     // round budget: a few times the side length of a surface mesh (the dependency chain of a compact mesh); a mesh with
                     // a longer chain (a ribbon a few rows wide) finishes with rim growth from what the wavefront has decided so far
@@ -1440,7 +1441,7 @@ public:
                         // the first rounds sweep long lists (round 0: every undecided row); later ones the front only
                         const int Gr = Gw;                 // one warp per list entry in the elect / next kernels
                         lex_elect_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
-                        lex_cover1_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
+                        lex_cover1_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr, lex_exact);
                         lex_cover2_kernel<<<Gr, kBlock, 0, stream>>>(L, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
                         lex_next_kernel<<<Gr, kBlock, 0, stream>>>(L, round, A->rowptr.ptr, A->colidx.ptr, A->val.ptr, idg, block, theta2, status.ptr);
                         lex_advance_kernel<<<1, 1, 0, stream>>>(L.count, L.count + 5);

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(kBlock) agg_cover2_kernel(int n, const int *__
 // One relaxation (tests/test_aggregation_model.py models both forms): lex_cover1_kernel takes only UNDECIDED neighbours of a new
 // root; a neighbour that an earlier root had marked "distance 2" keeps that mark, so the rows behind it are not covered by the new
 // root and stay electable. The set is a few per cent denser than the walk's (roots at distance 2 through an already covered row),
-// never has adjacent roots, is deterministic, and is what round 2 measured; `status[u] == 0 || status[u] == 2` there makes it exact.
+// never has adjacent roots, is deterministic, and is what round 2 measured; ARAP_MG_WAVEFRONT_EXACT=1 re-marks (`exact`) and gives the
+// walk's set (not yet measured on the hardware).
 struct LexLists {
     int *work, *work_next, *roots, *adj, *far;      // this round's candidates, next round's, newly: roots / next to a root / distance 2
     int *count;                                       // [0] work [1] work_next [2] roots [3] adj [4] far
@@ -352,7 +353,7 @@ __device__ __forceinline__ void lex_append(bool take, int value, int *__restrict
 }
 __global__ void __launch_bounds__(kBlock) lex_cover1_kernel(LexLists L, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                             const double *__restrict__ val, const double *__restrict__ inv_diag,
-                                                            const int *__restrict__ block, double theta2, int *__restrict__ status) {
+                                                            const int *__restrict__ block, double theta2, int *__restrict__ status, int exact) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_roots = L.count[2];
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kBlock) lex_cover1_kernel(LexLists L, const in
             int u = -1;
             if (k < e) {
                 u = colidx[k];
-                take = is_strong(r, u, val[k], inv_diag, block, theta2) && status[u] == 0;
+                take = is_strong(r, u, val[k], inv_diag, block, theta2) && (status[u] == 0 || (exact && status[u] == 2));
                 if (take) status[u] = 3;
             }
             lex_append(take, u, L.adj, &L.count[3]);
