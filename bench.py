@@ -561,6 +561,19 @@ def multi_gpu_arms(args, rank, world, local_rank, dist, out):
                             % (res["exchanges_per_cg_iteration"] + res["allreduces_per_cg_iteration"], res["us_per_exchange"], res["us_per_allreduce"],
                                res["exchanges_per_cg_iteration"] * res["us_per_exchange"] + res["allreduces_per_cg_iteration"] * res["us_per_allreduce"],
                                1e3 * res["ms_per_step"] / max(1.0, res["cg_iterations_per_step"])))
+        if single:
+            # the two factors of the speed-up: what the partition costs the preconditioner, and how one CG iteration scales
+            t_single = 1e3 * single["ms_per_step"] / max(1.0, single["cg_iterations_per_step"])
+            t_part = 1e3 * res["ms_per_step"] / max(1.0, res["cg_iterations_per_step"])
+            entry["limiter"] += ("; CG iterations per ARAP iteration %.2f vs %.2f unpartitioned (aggregates confined to the partition blocks); "
+                                 "one CG iteration %.0f us vs %.0f us on one GPU = %.2fx on %d GPUs"
+                                 % (res["cg_iterations_per_step"], single["cg_iterations_per_step"], t_part, t_single, t_single / t_part, world))
+            ph, ph1 = res.get("us_per_cg_iteration_by_phase_rank0"), single.get("us_per_cg_iteration_by_phase")
+            if ph and ph1:
+                comm = ph["halo_exchange"] + ph["allreduce_cg_scalars"] + ph["allreduce_replicated_level_rhs"]
+                entry["limiter"] += ("; event-timed phases: communication %.0f us, coarse multigrid levels %.0f us (one GPU: %.0f), fine-level kernels %.0f us (one GPU: %.0f)"
+                                     % (comm, ph["multigrid_coarse_levels"], ph1["multigrid_coarse_levels"],
+                                        ph["sum_of_phases_us"] - comm - ph["multigrid_coarse_levels"], ph1["sum_of_phases_us"] - ph1["multigrid_coarse_levels"]))
         out[name] = entry
     if rank == 0 and single:
         out["single_gpu_reference_%dx%d" % (nx, nx)] = _strip(single)
